@@ -1,0 +1,493 @@
+// of_gemm: persistent, warp-specialised tcgen05 GEMM / implicit-GEMM conv1d for sm_100a.
+//
+//   warp 0 (1 lane)  : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1 (1 lane)  : MMA issuer     (tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 accumulator stages)
+//   warps 2..5       : epilogue       (tcgen05.ld TMEM->regs, bias/residual/SiLU/dSiLU/GroupNorm-stats, global stores)
+//
+// One CTA per SM, tiles 128 x BN (BN <= 256) distributed round-robin; the epilogue of tile i overlaps the
+// main loop of tile i+1 through the double-buffered TMEM accumulator.
+//
+// Reference ops replaced: see include/osufusion_b200.h (of_gemm).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ofx {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccStride = 256;
+
+struct GemmKParams {
+  int mode, b_mn, batch, rows, N, K, taps, shift0, shift_step;
+  int BN, num_stages;
+  uint32_t stage_bytes, tx_bytes;
+  int m_tiles, n_tiles, num_tiles;
+  int k_chunks;       // FWD: ceil(K/64); WGRAD: ceil(rows/64)
+  int k_iters_total;  // FWD: taps*k_chunks; WGRAD: batch*k_chunks
+  int split_k, k_iters_per_split;
+  // epilogue
+  const float* bias;
+  const float* aux_f32;
+  long long aux_f32_ld, aux_f32_bs;
+  const __nv_bfloat16* aux_bf16;
+  long long aux_bf16_ld, aux_bf16_bs;
+  int aux_is_dsilu, act;
+  __nv_bfloat16* pre_bf16;
+  __nv_bfloat16* out_bf16;
+  long long out_bf16_ld, out_bf16_bs;
+  float* out_f32;
+  long long out_f32_ld, out_f32_bs;
+  double* stats;
+};
+
+struct TileCoord {
+  int b, m0, n0, tap, k_begin, k_end;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
+  TileCoord tc;
+  if (p.mode == OF_GEMM_FWD) {
+    int n_blk = tile % p.n_tiles;
+    int rest = tile / p.n_tiles;
+    int m_blk = rest % p.m_tiles;
+    tc.b = rest / p.m_tiles;
+    tc.m0 = m_blk * kBM;
+    tc.n0 = n_blk * p.BN;
+    tc.tap = 0;
+    tc.k_begin = 0;
+    tc.k_end = p.k_iters_total;
+  } else {
+    int split = tile % p.split_k;
+    int rest = tile / p.split_k;
+    int n_blk = rest % p.n_tiles;
+    rest /= p.n_tiles;
+    int m_blk = rest % p.m_tiles;
+    tc.tap = rest / p.m_tiles;
+    tc.b = 0;
+    tc.m0 = m_blk * kBM;
+    tc.n0 = n_blk * p.BN;
+    tc.k_begin = split * p.k_iters_per_split;
+    tc.k_end = min(tc.k_begin + p.k_iters_per_split, p.k_iters_total);
+  }
+  return tc;
+}
+
+__device__ __forceinline__ void st_global_v4(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* ptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned tile ring (SWIZZLE_128B atoms), barriers after it.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.num_stages * p.stage_bytes);
+  uint64_t* full_bar = bars;                       // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages; // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const bool a_mn = (p.mode == OF_GEMM_WGRAD);
+  const bool b_mn = (p.mode == OF_GEMM_WGRAD) || (p.b_mn != 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        TileCoord tc = decode_tile(p, tile);
+        for (int it = tc.k_begin; it < tc.k_end; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = ring + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
+          if (p.mode == OF_GEMM_FWD) {
+            int t = it / p.k_chunks;
+            int kc = it - t * p.k_chunks;
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], kc * kBK, tc.m0 + p.shift0 + t * p.shift_step, tc.b);
+            if (!b_mn) {
+              tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * kBK, tc.n0, t);
+            } else {
+              for (int j = 0; j < p.BN / 64; ++j)
+                tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, kc * kBK, t);
+            }
+          } else {
+            int b = it / p.k_chunks;
+            int lc = it - b * p.k_chunks;
+            for (int j = 0; j < 2; ++j)
+              tma_load_3d(sa + j * 8192, &tmap_a, &full_bar[stage], tc.m0 + j * 64, lc * kBK, b);
+            int shift = p.shift0 + tc.tap * p.shift_step;
+            for (int j = 0; j < p.BN / 64; ++j)
+              tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, lc * kBK + shift, b);
+          }
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBM, p.BN, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        TileCoord tc = decode_tile(p, tile);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        for (int it = tc.k_begin; it < tc.k_end; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          uint32_t sa = smem_u32(ring + (size_t)stage * p.stage_bytes);
+          uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            uint64_t da = a_mn ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            uint64_t db = b_mn ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16_ss(tmem_d, da, db, idesc, (it > tc.k_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      TileCoord tc = decode_tile(p, tile);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m = tc.m0 + r;
+      const bool k_nonempty = tc.k_end > tc.k_begin;
+      float s1 = 0.f, s2 = 0.f;
+      if (p.mode == OF_GEMM_FWD) {
+        const bool row_ok = m < p.rows;
+        const long long brow = (long long)tc.b;
+        const float* aux32 = p.aux_f32 ? p.aux_f32 + brow * p.aux_f32_bs + (long long)m * p.aux_f32_ld : nullptr;
+        const __nv_bfloat16* aux16 =
+            p.aux_bf16 ? p.aux_bf16 + brow * p.aux_bf16_bs + (long long)m * p.aux_bf16_ld : nullptr;
+        __nv_bfloat16* o16 = p.out_bf16 ? p.out_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
+        __nv_bfloat16* pre16 = p.pre_bf16 ? p.pre_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
+        float* o32 = p.out_f32 ? p.out_f32 + brow * p.out_f32_bs + (long long)m * p.out_f32_ld : nullptr;
+        for (int c = 0; c < p.BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c * 32, v);
+          tmem_wait_ld();
+          const int nb = tc.n0 + c * 32;
+          if (row_ok && nb < p.N) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = nb + g * 8;
+              if (n < p.N) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = k_nonempty ? __uint_as_float(v[g * 8 + j]) : 0.f;
+                if (p.bias) {
+                  float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
+                  float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (aux32) {
+                  float4 a0 = *reinterpret_cast<const float4*>(aux32 + n);
+                  float4 a1 = *reinterpret_cast<const float4*>(aux32 + n + 4);
+                  f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+                  f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+                }
+                float x16[8];
+                if (aux16) {
+                  uint4 u = *reinterpret_cast<const uint4*>(aux16 + n);
+                  float2 t0 = unpack_bf16x2(u.x), t1 = unpack_bf16x2(u.y), t2 = unpack_bf16x2(u.z),
+                         t3 = unpack_bf16x2(u.w);
+                  x16[0] = t0.x; x16[1] = t0.y; x16[2] = t1.x; x16[3] = t1.y;
+                  x16[4] = t2.x; x16[5] = t2.y; x16[6] = t3.x; x16[7] = t3.y;
+                  if (!p.aux_is_dsilu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += x16[j];
+                  }
+                }
+                if (pre16) {
+                  st_global_v4(pre16 + n, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                               pack_bf16x2(f[6], f[7]));
+                }
+                if (p.act == OF_ACT_SILU) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+                }
+                if (aux16 && p.aux_is_dsilu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] *= dsilu_f(x16[j]);
+                }
+                if (o16) {
+                  st_global_v4(o16 + n, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                               pack_bf16x2(f[6], f[7]));
+                }
+                if (o32) {
+                  *reinterpret_cast<float4*>(o32 + n) = make_float4(f[0], f[1], f[2], f[3]);
+                  *reinterpret_cast<float4*>(o32 + n + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                }
+                if (p.stats) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    float rv = bf16_round(f[j]);
+                    s1 += rv;
+                    s2 += rv * rv;
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (p.stats) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (lane == 0) {
+            atomicAdd(p.stats + 2 * tc.b, (double)s1);
+            atomicAdd(p.stats + 2 * tc.b + 1, (double)s2);
+          }
+        }
+      } else {
+        // WGRAD: atomically accumulate fp32 into out_f32[tap][m][n]
+        const bool row_ok = (m < p.K) && k_nonempty;
+        float* o32 = p.out_f32 + (long long)tc.tap * p.out_f32_bs + (long long)m * p.out_f32_ld;
+        for (int c = 0; c < p.BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c * 32, v);
+          tmem_wait_ld();
+          const int nb = tc.n0 + c * 32;
+          if (row_ok && nb < p.N) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int n = nb + g * 4;
+              if (n < p.N) {
+                red_add_v4(o32 + n, __uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
+                           __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace ofx
+
+using namespace ofx;
+
+extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(a != nullptr, "of_gemm: null args");
+  OF_REQUIRE(a->mode == OF_GEMM_FWD || a->mode == OF_GEMM_WGRAD, "of_gemm: bad mode %d", a->mode);
+  OF_REQUIRE(a->batch >= 1 && a->rows >= 1 && a->N >= 1 && a->K >= 1 && a->taps >= 1, "of_gemm: bad sizes");
+  OF_REQUIRE(a->N % 8 == 0, "of_gemm: N=%d must be a multiple of 8", a->N);
+  OF_REQUIRE(a->a && a->b, "of_gemm: null operand");
+  OF_REQUIRE(a->a_ld % 8 == 0 && a->b_ld % 8 == 0, "of_gemm: leading dims must be multiples of 8");
+
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = a->mode;
+  p.b_mn = a->b_mn_major;
+  p.batch = a->batch;
+  p.rows = a->rows;
+  p.N = a->N;
+  p.K = a->K;
+  p.taps = a->taps;
+  p.shift0 = a->shift0;
+  p.shift_step = a->shift_step;
+  const bool wgrad = a->mode == OF_GEMM_WGRAD;
+  const bool b_mn = wgrad || a->b_mn_major;
+
+  // ---- tile N
+  int BN = a->block_n;
+  if (BN <= 0) {
+    if (a->N >= 256) BN = 256;
+    else if (a->N > 128) BN = (a->N > 192) ? 256 : 192;
+    else if (a->N > 64) BN = 128;
+    else if (a->N > 32) BN = 64;
+    else BN = b_mn ? 64 : 32;
+    // prefer more tiles when the grid would be badly under-filled
+    if (!wgrad && BN == 256) {
+      long long tiles256 = (long long)a->batch * ceil_div(a->rows, kBM) * ceil_div(a->N, 256);
+      if (tiles256 < device_sm_count()) BN = 128;
+    }
+  }
+  OF_REQUIRE(BN % 32 == 0 && BN >= 32 && BN <= 256, "of_gemm: block_n=%d invalid", BN);
+  if (b_mn) OF_REQUIRE(BN % 64 == 0, "of_gemm: block_n=%d must be a multiple of 64 for MN-major B", BN);
+  p.BN = BN;
+  const uint32_t b_bytes = (uint32_t)BN * 128u;
+  p.stage_bytes = kABytes + b_bytes;
+  p.tx_bytes = p.stage_bytes;
+  int stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.num_stages = stages;
+
+  if (!wgrad) {
+    p.m_tiles = ceil_div(a->rows, kBM);
+    p.n_tiles = ceil_div(a->N, BN);
+    p.num_tiles = a->batch * p.m_tiles * p.n_tiles;
+    p.k_chunks = ceil_div(a->K, kBK);
+    p.k_iters_total = a->taps * p.k_chunks;
+    p.split_k = 1;
+    p.k_iters_per_split = p.k_iters_total;
+  } else {
+    OF_REQUIRE(a->out_f32 != nullptr, "of_gemm(wgrad): out_f32 required");
+    OF_REQUIRE(a->K % 8 == 0, "of_gemm(wgrad): M=%d must be a multiple of 8", a->K);
+    p.m_tiles = ceil_div(a->K, kBM);
+    p.n_tiles = ceil_div(a->N, BN);
+    p.k_chunks = ceil_div(a->rows, kBK);
+    p.k_iters_total = a->batch * p.k_chunks;
+    int base_tiles = a->taps * p.m_tiles * p.n_tiles;
+    int split = a->split_k;
+    if (split <= 0) {
+      split = ceil_div(2 * device_sm_count(), base_tiles);
+      int max_split = ceil_div(p.k_iters_total, 4);  // at least 4 k-iterations per split
+      if (split > max_split) split = max_split;
+      if (split < 1) split = 1;
+    }
+    if (split > p.k_iters_total) split = p.k_iters_total;
+    p.k_iters_per_split = ceil_div(p.k_iters_total, split);
+    p.split_k = ceil_div(p.k_iters_total, p.k_iters_per_split);
+    p.num_tiles = base_tiles * p.split_k;
+  }
+
+  p.bias = a->bias;
+  p.aux_f32 = a->aux_f32;
+  p.aux_f32_ld = a->aux_f32_ld;
+  p.aux_f32_bs = a->aux_f32_batch_stride;
+  p.aux_bf16 = reinterpret_cast<const __nv_bfloat16*>(a->aux_bf16);
+  p.aux_bf16_ld = a->aux_bf16_ld;
+  p.aux_bf16_bs = a->aux_bf16_batch_stride;
+  p.aux_is_dsilu = a->aux_is_dsilu;
+  p.act = a->act;
+  p.pre_bf16 = reinterpret_cast<__nv_bfloat16*>(a->pre_bf16);
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  p.out_bf16_ld = a->out_bf16_ld;
+  p.out_bf16_bs = a->out_bf16_batch_stride;
+  p.out_f32 = a->out_f32;
+  p.out_f32_ld = a->out_f32_ld;
+  p.out_f32_bs = a->out_f32_batch_stride;
+  p.stats = a->stats;
+  if (!wgrad) {
+    OF_REQUIRE(p.out_bf16 || p.out_f32 || p.pre_bf16, "of_gemm: no output");
+    if (p.out_bf16 || p.pre_bf16) OF_REQUIRE(p.out_bf16_ld % 8 == 0, "of_gemm: out_bf16_ld %% 8");
+    if (p.out_f32) OF_REQUIRE(p.out_f32_ld % 4 == 0, "of_gemm: out_f32_ld %% 4");
+    if (p.aux_f32) OF_REQUIRE(p.aux_f32_ld % 4 == 0, "of_gemm: aux_f32_ld %% 4");
+    if (p.aux_bf16) OF_REQUIRE(p.aux_bf16_ld % 8 == 0, "of_gemm: aux_bf16_ld %% 8");
+  } else {
+    OF_REQUIRE(p.out_f32_ld % 4 == 0, "of_gemm(wgrad): out_f32_ld %% 4");
+  }
+
+  // ---- tensor maps
+  CUtensorMap ta, tb;
+  int rc;
+  if (!wgrad) {
+    unsigned long long bs = a->batch > 1 ? (unsigned long long)a->a_batch_stride : (unsigned long long)a->rows * a->a_ld;
+    unsigned long long dims[3] = {(unsigned long long)a->K, (unsigned long long)a->rows, (unsigned long long)a->batch};
+    unsigned long long str[2] = {(unsigned long long)a->a_ld * 2ull, bs * 2ull};
+    unsigned box[3] = {64, (unsigned)kBM, 1};
+    if ((rc = make_tmap_bf16(&ta, a->a, 3, dims, str, box)) != OF_OK) return rc;
+    if (!b_mn) {
+      unsigned long long ts = a->taps > 1 ? (unsigned long long)a->b_tap_stride : (unsigned long long)a->N * a->b_ld;
+      unsigned long long bd[3] = {(unsigned long long)a->K, (unsigned long long)a->N, (unsigned long long)a->taps};
+      unsigned long long bstr[2] = {(unsigned long long)a->b_ld * 2ull, ts * 2ull};
+      unsigned bbox[3] = {64, (unsigned)BN, 1};
+      if ((rc = make_tmap_bf16(&tb, a->b, 3, bd, bstr, bbox)) != OF_OK) return rc;
+    } else {
+      unsigned long long ts = a->taps > 1 ? (unsigned long long)a->b_tap_stride : (unsigned long long)a->K * a->b_ld;
+      unsigned long long bd[3] = {(unsigned long long)a->N, (unsigned long long)a->K, (unsigned long long)a->taps};
+      unsigned long long bstr[2] = {(unsigned long long)a->b_ld * 2ull, ts * 2ull};
+      unsigned bbox[3] = {64, 64, 1};
+      if ((rc = make_tmap_bf16(&tb, a->b, 3, bd, bstr, bbox)) != OF_OK) return rc;
+    }
+  } else {
+    unsigned long long abs_ = a->batch > 1 ? (unsigned long long)a->a_batch_stride : (unsigned long long)a->rows * a->a_ld;
+    unsigned long long bbs = a->batch > 1 ? (unsigned long long)a->b_tap_stride : (unsigned long long)a->rows * a->b_ld;
+    unsigned long long ad[3] = {(unsigned long long)a->K, (unsigned long long)a->rows, (unsigned long long)a->batch};
+    unsigned long long astr[2] = {(unsigned long long)a->a_ld * 2ull, abs_ * 2ull};
+    unsigned long long bd[3] = {(unsigned long long)a->N, (unsigned long long)a->rows, (unsigned long long)a->batch};
+    unsigned long long bstr[2] = {(unsigned long long)a->b_ld * 2ull, bbs * 2ull};
+    unsigned box[3] = {64, 64, 1};
+    if ((rc = make_tmap_bf16(&ta, a->a, 3, ad, astr, box)) != OF_OK) return rc;
+    if ((rc = make_tmap_bf16(&tb, a->b, 3, bd, bstr, box)) != OF_OK) return rc;
+  }
+
+  size_t smem_bytes = (size_t)p.num_stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
+  gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
