@@ -100,6 +100,35 @@ typedef struct {
 
 int of_gemm(const of_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * of_attn_fwd / of_attn_bwd — multi-query flash attention (tcgen05/TMEM), non-causal, no mask, bf16.
+ * Replaces: `Attend.forward` = F.scaled_dot_product_attention on bf16-cast q,k,v (attention.py:77-101) and the
+ *   GQA expansion `repeat(k|v, "b h n d -> b (r h) n d")` (unet.py:135-137), plus their autograd backward.
+ * Layout: q (B, L, H*D), k and v (B, L, KVH*D) channels-last views (ld / batch stride in elements), q head i uses
+ *   kv head i % KVH (einops "(r h)" ordering).  D <= 64, D % 8 == 0.  scale <= 0 selects 1/sqrt(D).
+ * fwd: out (B, L, H*D) bf16, lse (B, H, L) fp32 = log2-domain log-sum-exp (row max + log2 sum), saved for bwd.
+ * bwd: inputs q,k,v,out,dout (bf16), lse; workspace delta (B,H,L) fp32;
+ *      dq (B, L, H*D) fp32 and dkv = [dk | dv] (B, L, 2*KVH*D) fp32 are ACCUMULATED atomically: caller zero-fills.
+ * variant: 0 = default (P operand kept in tensor memory), 1 = P staged through shared memory.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int B, H, KVH, L, D;
+  float scale;
+  int variant;
+  const void* q; long long q_ld, q_batch_stride;
+  const void* k; const void* v; long long kv_ld, kv_batch_stride;
+  void* out; long long out_ld, out_batch_stride;      /* fwd: output; bwd: forward output (input) */
+  float* lse;
+  /* backward only */
+  const void* dout; long long dout_ld, dout_batch_stride;
+  float* delta;                                        /* (B, H, L) workspace */
+  float* dq; long long dq_ld, dq_batch_stride;
+  float* dk; float* dv; long long dkv_ld, dkv_batch_stride;
+} of_attn_args;
+
+int of_attn_fwd(const of_attn_args* args, void* stream);
+int of_attn_bwd(const of_attn_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

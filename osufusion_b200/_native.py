@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
         _lib.of_last_error.restype = C.c_char_p
         _lib.of_launch_count.restype = C.c_longlong
         _lib.of_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+        _lib.of_attn_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+        _lib.of_attn_bwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     return _lib
 
 
@@ -62,3 +64,18 @@ def stream_ptr() -> int:
 
 def ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("H", C.c_int), ("KVH", C.c_int), ("L", C.c_int), ("D", C.c_int),
+        ("scale", C.c_float), ("variant", C.c_int),
+        ("q", C.c_void_p), ("q_ld", C.c_longlong), ("q_batch_stride", C.c_longlong),
+        ("k", C.c_void_p), ("v", C.c_void_p), ("kv_ld", C.c_longlong), ("kv_batch_stride", C.c_longlong),
+        ("out", C.c_void_p), ("out_ld", C.c_longlong), ("out_batch_stride", C.c_longlong),
+        ("lse", C.c_void_p),
+        ("dout", C.c_void_p), ("dout_ld", C.c_longlong), ("dout_batch_stride", C.c_longlong),
+        ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("dq_ld", C.c_longlong), ("dq_batch_stride", C.c_longlong),
+        ("dk", C.c_void_p), ("dv", C.c_void_p), ("dkv_ld", C.c_longlong), ("dkv_batch_stride", C.c_longlong),
+    ]

@@ -1,0 +1,346 @@
+// of_attn_bwd: multi-query flash attention backward on tcgen05/TMEM (sm_100a).
+//
+// Replaces autograd's backward of F.scaled_dot_product_attention (reference attention.py:94-99) and of the GQA
+// `repeat` (unet.py:135-137): dK/dV of the single shared KV head are summed over all q heads.
+//
+// One CTA = one 128-key KV tile of one (batch, q head); it loops over all 128-row Q tiles:
+//   S  = Q_i K^T,  dP = dO_i V^T                         (SS MMAs into TMEM)
+//   P  = exp2(S*scale*log2e - lse2),  dS = P o (dP - delta) * scale     (one thread per q row, bf16 -> swizzled smem)
+//   dV += P^T dO_i,  dK += dS^T Q_i                      (MN-major A straight from the same smem tiles; TMEM accum)
+//   dQ_i = dS K                                          (TMEM -> fp32 red.global.add, summed over KV tiles)
+// At the end dK/dV tiles are atomically added (fp32) to the shared-KV-head gradient (16 q heads contribute).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ofx {
+
+int make_head_tmap(CUtensorMap* m, const void* base, int D, int heads, int L, int B, long long ld, long long bs,
+                   unsigned box_rows);
+
+constexpr int kBThreads = 192;
+constexpr uint32_t kTile = 128 * 64 * 2;  // 16 KB
+
+struct AttnBwdParams {
+  int B, H, KVH, L, D;
+  int n_q_tiles;
+  float scale, scale_log2;
+  const float* lse;
+  const float* delta;
+  float* dq;
+  long long dq_ld, dq_bs;
+  float* dk;
+  float* dv;
+  long long dkv_ld, dkv_bs;
+};
+
+__device__ __forceinline__ float ex2b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void red_add4(float* ptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kBThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kTile;
+  uint8_t* sQdO = sV + kTile;      // 2 stages x (Q 16 KB + dO 16 KB)
+  uint8_t* sP = sQdO + 4 * kTile;  // 32 KB
+  uint8_t* sdS = sP + 2 * kTile;   // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * kTile);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;    // [2]
+  uint64_t* qdo_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* sdp_empty = bars + 6;
+  uint64_t* pds_full = bars + 7;
+  uint64_t* pds_empty = bars + 8;
+  uint64_t* dq_full = bars + 9;
+  uint64_t* dq_empty = bars + 10;
+  uint64_t* acc_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h % p.KVH;
+  const int n = p.n_q_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, 4);
+    mbar_init(pds_full, 4);
+    mbar_init(pds_empty, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * kTile);
+      tma_load_4d(sK, &tmap_k, kv_full, 0, kvh, k0, b);
+      tma_load_4d(sV, &tmap_v, kv_full, 0, kvh, k0, b);
+      for (int i = 0; i < n; ++i) {
+        const int st = i & 1, use = i >> 1;
+        mbar_wait(&qdo_empty[st], (use & 1) ^ 1);
+        uint8_t* sq = sQdO + st * 2 * kTile;
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * kTile);
+        tma_load_4d(sq, &tmap_q, &qdo_full[st], 0, h, i * 128, b);
+        tma_load_4d(sq + kTile, &tmap_do, &qdo_full[st], 0, h, i * 128, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_kv = make_idesc_bf16(128, 64, 1, 1);  // dV, dK: A = P^T / dS^T (MN-major), B MN-major
+      const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);  // dQ: A = dS (K-major), B = K (MN-major)
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < n; ++i) {
+        const int st = i & 1;
+        const uint32_t aQ = smem_u32(sQdO + st * 2 * kTile), adO = aQ + kTile;
+        mbar_wait(&qdo_full[st], (i >> 1) & 1);
+        mbar_wait(sdp_empty, (i & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s,
+                      k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tdP, make_smem_desc(adO + k * 32, 16, 1024), make_smem_desc(aV + k * 32, 16, 1024), idesc_s,
+                      k > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+
+        mbar_wait(pds_full, i & 1);
+        mbar_wait(dq_empty, (i & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV += P^T dO   (K = 128 q rows, 16 per step)
+          umma_f16_ss(tdV, make_smem_desc(aP + k * 2048, 2 * kTile / 2, 1024), make_smem_desc(adO + k * 2048, 8192, 1024),
+                      idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK += dS^T Q
+          umma_f16_ss(tdK, make_smem_desc(adS + k * 2048, 2 * kTile / 2, 1024), make_smem_desc(aQ + k * 2048, 8192, 1024),
+                      idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ = dS K      (K = 128 keys, 16 per step)
+          umma_f16_ss(tdQ, make_smem_desc(adS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(aK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
+        umma_commit(dq_full);
+        umma_commit(pds_empty);
+        umma_commit(&qdo_empty[st]);
+      }
+      umma_commit(acc_done);
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const long long bh = (long long)b * p.H + h;
+    for (int i = 0; i < n; ++i) {
+      const int qrow = i * 128 + row;
+      const bool q_ok = qrow < p.L;
+      const float lse2 = q_ok ? p.lse[bh * p.L + qrow] : 0.f;
+      const float dlt = q_ok ? p.delta[bh * p.L + qrow] : 0.f;
+      mbar_wait(sdp_full, i & 1);
+      mbar_wait(pds_empty, (i & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t s[64], dp[64];
+        {
+          uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+          uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+          uint32_t (&d0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dp[0]);
+          uint32_t (&d1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dp[32]);
+          tmem_ld_32x32b_x32(tS + lane_off + hf * 64, s0);
+          tmem_ld_32x32b_x32(tS + lane_off + hf * 64 + 32, s1);
+          tmem_ld_32x32b_x32(tdP + lane_off + hf * 64, d0);
+          tmem_ld_32x32b_x32(tdP + lane_off + hf * 64 + 32, d1);
+          tmem_wait_ld();
+        }
+        const int key_base = k0 + hf * 64;
+        uint8_t* prow = sP + hf * kTile + row * 128;
+        uint8_t* dsrow = sdS + hf * kTile + row * 128;
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {
+          uint32_t pw[4], dw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c0 = pc * 8 + e * 2;
+            float p0 = ex2b(fmaf(__uint_as_float(s[c0]), p.scale_log2, -lse2));
+            float p1 = ex2b(fmaf(__uint_as_float(s[c0 + 1]), p.scale_log2, -lse2));
+            if (!q_ok || key_base + c0 >= p.L) p0 = 0.f;
+            if (!q_ok || key_base + c0 + 1 >= p.L) p1 = 0.f;
+            float ds0 = p0 * (__uint_as_float(dp[c0]) - dlt) * p.scale;
+            float ds1 = p1 * (__uint_as_float(dp[c0 + 1]) - dlt) * p.scale;
+            pw[e] = pack_bf16x2(p0, p1);
+            dw[e] = pack_bf16x2(ds0, ds1);
+          }
+          const int off = (pc ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + off) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(sdp_empty);
+        mbar_arrive(pds_full);
+      }
+      // ---- dQ tile -> global (fp32 atomics; summed over KV tiles)
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      uint32_t dq[64];
+      {
+        uint32_t (&q0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dq[0]);
+        uint32_t (&q1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dq[32]);
+        tmem_ld_32x32b_x32(tdQ + lane_off, q0);
+        tmem_ld_32x32b_x32(tdQ + lane_off + 32, q1);
+        tmem_wait_ld();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+      if (q_ok) {
+        float* dst = p.dq + (long long)b * p.dq_bs + (long long)qrow * p.dq_ld + (long long)h * p.D;
+#pragma unroll
+        for (int g = 0; g < 16; ++g)
+          if (g * 4 < p.D)
+            red_add4(dst + g * 4, __uint_as_float(dq[g * 4]), __uint_as_float(dq[g * 4 + 1]),
+                     __uint_as_float(dq[g * 4 + 2]), __uint_as_float(dq[g * 4 + 3]));
+      }
+    }
+    // ---- dK / dV tiles -> global (fp32 atomics; summed over q heads)
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const int key = k0 + row;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t a[64];
+      uint32_t (&a0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&a[0]);
+      uint32_t (&a1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&a[32]);
+      const uint32_t t = which == 0 ? tdV : tdK;
+      tmem_ld_32x32b_x32(t + lane_off, a0);
+      tmem_ld_32x32b_x32(t + lane_off + 32, a1);
+      tmem_wait_ld();
+      if (key < p.L) {
+        float* dst = (which == 0 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)key * p.dkv_ld + (long long)kvh * p.D;
+#pragma unroll
+        for (int g = 0; g < 16; ++g)
+          if (g * 4 < p.D)
+            red_add4(dst + g * 4, __uint_as_float(a[g * 4]), __uint_as_float(a[g * 4 + 1]), __uint_as_float(a[g * 4 + 2]),
+                     __uint_as_float(a[g * 4 + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// delta[b,h,l] = sum_d dO[b,l,h,d] * O[b,l,h,d]
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, long long out_ld, long long out_bs,
+                                  const __nv_bfloat16* __restrict__ dout, long long do_ld, long long do_bs,
+                                  float* __restrict__ delta, int B, int H, int L, int D) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * L * H;
+  if (idx >= total) return;
+  int h = (int)(idx % H);
+  long long r = idx / H;
+  int l = (int)(r % L);
+  int b = (int)(r / L);
+  const __nv_bfloat16* o = out + (long long)b * out_bs + (long long)l * out_ld + (long long)h * D;
+  const __nv_bfloat16* d = dout + (long long)b * do_bs + (long long)l * do_ld + (long long)h * D;
+  float acc = 0.f;
+  for (int c = 0; c < D; c += 8) {
+    uint4 uo = *reinterpret_cast<const uint4*>(o + c);
+    uint4 ud = *reinterpret_cast<const uint4*>(d + c);
+    float2 a0 = unpack_bf16x2(uo.x), a1 = unpack_bf16x2(uo.y), a2 = unpack_bf16x2(uo.z), a3 = unpack_bf16x2(uo.w);
+    float2 b0 = unpack_bf16x2(ud.x), b1 = unpack_bf16x2(ud.y), b2 = unpack_bf16x2(ud.z), b3 = unpack_bf16x2(ud.w);
+    acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+  }
+  delta[((long long)b * H + h) * L + l] = acc;
+}
+
+}  // namespace ofx
+
+using namespace ofx;
+
+extern "C" int of_attn_bwd(const of_attn_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(a && a->q && a->k && a->v && a->out && a->dout && a->lse && a->delta && a->dq && a->dk && a->dv,
+             "of_attn_bwd: null pointer");
+  OF_REQUIRE(a->D >= 8 && a->D <= 64 && a->D % 8 == 0, "of_attn_bwd: head dim %d unsupported", a->D);
+  OF_REQUIRE(a->H >= 1 && a->KVH >= 1 && a->H % a->KVH == 0, "of_attn_bwd: bad head counts");
+  OF_REQUIRE(a->dq_ld % 4 == 0 && a->dkv_ld % 4 == 0, "of_attn_bwd: fp32 gradient lds must be multiples of 4");
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = make_head_tmap(&tq, a->q, a->D, a->H, a->L, a->B, a->q_ld, a->q_batch_stride, 128)) != OF_OK) return rc;
+  if ((rc = make_head_tmap(&tk, a->k, a->D, a->KVH, a->L, a->B, a->kv_ld, a->kv_batch_stride, 128)) != OF_OK) return rc;
+  if ((rc = make_head_tmap(&tv, a->v, a->D, a->KVH, a->L, a->B, a->kv_ld, a->kv_batch_stride, 128)) != OF_OK) return rc;
+  if ((rc = make_head_tmap(&tdo, a->dout, a->D, a->H, a->L, a->B, a->dout_ld, a->dout_batch_stride, 128)) != OF_OK)
+    return rc;
+  {
+    long long total = (long long)a->B * a->L * a->H;
+    int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    attn_delta_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->out), a->out_ld, a->out_batch_stride,
+        reinterpret_cast<const __nv_bfloat16*>(a->dout), a->dout_ld, a->dout_batch_stride, a->delta, a->B, a->H, a->L,
+        a->D);
+    OF_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  AttnBwdParams p;
+  p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.L = a->L; p.D = a->D;
+  p.n_q_tiles = (a->L + 127) / 128;
+  p.scale = a->scale > 0.f ? a->scale : 1.0f / sqrtf((float)a->D);
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.lse = a->lse;
+  p.delta = a->delta;
+  p.dq = a->dq; p.dq_ld = a->dq_ld; p.dq_bs = a->dq_batch_stride;
+  p.dk = a->dk; p.dv = a->dv; p.dkv_ld = a->dkv_ld; p.dkv_bs = a->dkv_batch_stride;
+  size_t smem_bytes = 1024 + kTile * 10 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OF_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((a->L + 127) / 128, a->H, a->B);
+  attn_bwd_kernel<<<grid, kBThreads, smem_bytes, stream>>>(tq, tk, tv, tdo, p);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}

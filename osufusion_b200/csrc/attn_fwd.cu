@@ -1,0 +1,328 @@
+// of_attn_fwd: multi-query flash attention forward on tcgen05/TMEM (sm_100a).
+//
+// Replaces `Attend.forward` (reference osu_fusion/modules/attention.py:77-101: bf16 q,k,v, non-causal, no mask,
+// scale 1/sqrt(D)) together with the GQA `repeat` of k,v (unet.py:135-137), which is never materialised here: every
+// q head reads the single shared KV head through its own TMA descriptor coordinates.
+//
+// One CTA = 128 query rows of one (batch, head); KV tiles of 128 keys stream through a TMA ring.
+//   warp 0 : TMA producer (Q once; K/V ring)
+//   warp 1 : MMA issuer: S_j = Q K_j^T (SS, M128 N128 K64) into a double-buffered TMEM S; O += P_j V_j
+//            (P from TMEM [TS mode] or from 128B-swizzled smem, V consumed MN-major straight from its row-major tile)
+//   warps 2-5: one thread per query row: online softmax in registers (exp2, lazy rescale of the TMEM O accumulator),
+//            P written back as bf16, final O/l and log-sum-exp written to global.
+// Head dim D <= 64 (zero-padded to 64 by TMA out-of-bounds fill); any L (key tail masked).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ofx {
+
+constexpr int kAThreads = 192;
+constexpr int kKvStages = 3;
+constexpr uint32_t kTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
+
+struct AttnFwdParams {
+  int B, H, KVH, L, D;
+  int n_kv_tiles;
+  float scale_log2;
+  int p_in_tmem;
+  __nv_bfloat16* out;
+  long long out_ld, out_bs;
+  float* lse;  // (B, H, L) log2-domain log-sum-exp
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                  // 16 KB
+  uint8_t* sKV = sQ + kTileBytes;                      // kKvStages x (K 16 KB + V 16 KB)
+  uint8_t* sP = sKV + kKvStages * 2 * kTileBytes;      // 32 KB (only used when !p_in_tmem)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;               // [kKvStages]
+  uint64_t* kv_empty = kv_full + kKvStages;   // [kKvStages]
+  uint64_t* s_full = kv_empty + kKvStages;    // [2]
+  uint64_t* s_empty = s_full + 2;             // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* pv_done = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem;            // 2 x 128 cols
+  const uint32_t tO = tmem + 256;      // 64 cols
+  const uint32_t tP = tmem + 320;      // 64 cols (bf16x2 packed)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, h, q0, b);
+      const int kvh = h % p.KVH;
+      for (int j = 0; j < n; ++j) {
+        const int st = j % kKvStages, use = j / kKvStages;
+        mbar_wait(&kv_empty[st], (use & 1) ^ 1);
+        uint8_t* sk = sKV + st * 2 * kTileBytes;
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kTileBytes);
+        tma_load_4d(sk, &tmap_k, &kv_full[st], 0, kvh, j * 128, b);
+        tma_load_4d(sk + kTileBytes, &tmap_v, &kv_full[st], 0, kvh, j * 128, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t aQ = smem_u32(sQ);
+      auto issue_s = [&](int j) {
+        const int st = j % kKvStages;
+        const uint32_t aK = smem_u32(sKV + st * 2 * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tS + (j & 1) * 128, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024),
+                      idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) {
+          const int j1 = j + 1;
+          mbar_wait(&kv_full[j1 % kKvStages], (j1 / kKvStages) & 1);
+          mbar_wait(&s_empty[j1 & 1], ((j1 >> 1) & 1) ^ 1);
+          tc_fence_after();
+          issue_s(j1);
+        }
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const int st = j % kKvStages;
+        const uint32_t aV = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
+        if (p.p_in_tmem) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        } else {
+          const uint32_t aP = smem_u32(sP);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_f16_ss(tO, make_smem_desc(aP + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                        make_smem_desc(aV + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    float m_run = -INFINITY, m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t (&sc)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
+        tmem_ld_32x32b_x32(tS + lane_off + (j & 1) * 128 + c * 32, sc);
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+
+      const int kv_valid = p.L - j * 128;  // keys of this tile that exist
+      float mx = -INFINITY;
+      if (kv_valid >= 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          float v = (i < kv_valid) ? __uint_as_float(s[i]) : -INFINITY;
+          s[i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+      }
+      m_run = fmaxf(m_run, mx * p.scale_log2);
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        const bool need = (m_run - m_used) > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = ex2(m_used - m_run);
+          m_used = m_run;
+          l *= f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tO + lane_off + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            uint32_t (&o0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[0]);
+            uint32_t (&o1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[16]);
+            tmem_st_32x32b_x16(tO + lane_off + c * 32, o0);
+            tmem_st_32x32b_x16(tO + lane_off + c * 32 + 16, o1);
+          }
+          tmem_wait_st();
+        }
+      } else {
+        m_used = m_run;
+      }
+      float sum = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
+        float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
+        sum += p0 + p1;
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      l += sum;
+      if (p.p_in_tmem) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&pc)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[c * 16]);
+          tmem_st_32x32b_x16(tP + lane_off + c * 16, pc);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+      } else {
+        // K-major A tile, two 64-key chunks, 128B rows with the hardware 128B swizzle (16B piece ^= row & 7)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint8_t* rowp = sP + c * kTileBytes + row * 128;
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc) {
+            uint4 v = make_uint4(pk[c * 32 + pc * 4], pk[c * 32 + pc * 4 + 1], pk[c * 32 + pc * 4 + 2],
+                                 pk[c * 32 + pc * 4 + 3]);
+            *reinterpret_cast<uint4*>(rowp + ((pc ^ (row & 7)) << 4)) = v;
+          }
+        }
+        fence_proxy_async();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue
+    mbar_wait(pv_done, (n - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int qrow = q0 + row;
+    uint32_t o[64];
+    {
+      uint32_t (&o0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
+      uint32_t (&o1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[32]);
+      tmem_ld_32x32b_x32(tO + lane_off, o0);
+      tmem_ld_32x32b_x32(tO + lane_off + 32, o1);
+      tmem_wait_ld();
+    }
+    if (qrow < p.L) {
+      __nv_bfloat16* dst = p.out + (long long)b * p.out_bs + (long long)qrow * p.out_ld + (long long)h * p.D;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (g * 8 < p.D) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + g * 8) = v;
+        }
+      }
+      if (p.lse) p.lse[((long long)b * p.H + h) * p.L + qrow] = m_used + log2f(l);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// (D, heads, L, B) view of a (B, L, heads*D [+ more]) channels-last buffer; box (64, 1, 128, 1).
+int make_head_tmap(CUtensorMap* m, const void* base, int D, int heads, int L, int B, long long ld, long long bs,
+                   unsigned box_rows) {
+  unsigned long long dims[4] = {(unsigned long long)D, (unsigned long long)heads, (unsigned long long)L,
+                                (unsigned long long)B};
+  unsigned long long bstride = B > 1 ? (unsigned long long)bs : (unsigned long long)L * ld;
+  unsigned long long hstride = heads > 1 ? (unsigned long long)D : (unsigned long long)8;
+  unsigned long long str[3] = {hstride * 2ull, (unsigned long long)ld * 2ull, bstride * 2ull};
+  unsigned box[4] = {64, 1, box_rows, 1};
+  return make_tmap_bf16(m, base, 4, dims, str, box);
+}
+
+}  // namespace ofx
+
+using namespace ofx;
+
+extern "C" int of_attn_fwd(const of_attn_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(a && a->q && a->k && a->v && a->out, "of_attn_fwd: null pointer");
+  OF_REQUIRE(a->D >= 8 && a->D <= 64 && a->D % 8 == 0, "of_attn_fwd: head dim %d unsupported (8..64, multiple of 8)", a->D);
+  OF_REQUIRE(a->H >= 1 && a->KVH >= 1 && a->H % a->KVH == 0, "of_attn_fwd: bad head counts");
+  OF_REQUIRE(a->B >= 1 && a->L >= 1, "of_attn_fwd: bad sizes");
+  OF_REQUIRE(a->out_ld % 8 == 0, "of_attn_fwd: out_ld %% 8");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_head_tmap(&tq, a->q, a->D, a->H, a->L, a->B, a->q_ld, a->q_batch_stride, 128)) != OF_OK) return rc;
+  if ((rc = make_head_tmap(&tk, a->k, a->D, a->KVH, a->L, a->B, a->kv_ld, a->kv_batch_stride, 128)) != OF_OK) return rc;
+  if ((rc = make_head_tmap(&tv, a->v, a->D, a->KVH, a->L, a->B, a->kv_ld, a->kv_batch_stride, 128)) != OF_OK) return rc;
+  AttnFwdParams p;
+  p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.L = a->L; p.D = a->D;
+  p.n_kv_tiles = (a->L + 127) / 128;
+  p.scale_log2 = (a->scale > 0.f ? a->scale : 1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
+  p.p_in_tmem = a->variant == 1 ? 0 : 1;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.out_ld = a->out_ld;
+  p.out_bs = a->out_batch_stride;
+  p.lse = a->lse;
+  size_t smem_bytes = 1024 + kTileBytes * (1 + 2 * kKvStages + 2) + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((a->L + 127) / 128, a->H, a->B);
+  attn_fwd_kernel<<<grid, kAThreads, smem_bytes, stream>>>(tq, tk, tv, p);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}

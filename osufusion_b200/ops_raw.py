@@ -89,3 +89,42 @@ def gemm_wgrad(dy, x, out_f32, *, M, N_out, taps=1, shift0=0, shift_step=0, spli
     g.split_k = split_k
     g.block_n = block_n
     N.check(N.lib().of_gemm(C.byref(g), N.stream_ptr()), "of_gemm(wgrad)")
+
+
+def _attn_common(q, k, v, H, KVH, D, variant):
+    g = N.AttnArgs()
+    g.B, g.L = q.shape[0], q.shape[1]
+    g.H, g.KVH, g.D = H, KVH, D
+    g.scale = 0.0
+    g.variant = variant
+    g.q = q.data_ptr()
+    g.q_batch_stride, g.q_ld = _bl(q)
+    g.k, g.v = k.data_ptr(), v.data_ptr()
+    assert _bl(k) == _bl(v)
+    g.kv_batch_stride, g.kv_ld = _bl(k)
+    return g
+
+
+def attn_fwd(q, k, v, out, lse, *, H, KVH, D, variant=0):
+    """q (B,L,H*D), k/v (B,L,KVH*D) bf16 views; out (B,L,H*D) bf16; lse (B,H,L) fp32."""
+    g = _attn_common(q, k, v, H, KVH, D, variant)
+    g.out = out.data_ptr()
+    g.out_batch_stride, g.out_ld = _bl(out)
+    g.lse = N.ptr(lse)
+    N.check(N.lib().of_attn_fwd(C.byref(g), N.stream_ptr()), "of_attn_fwd")
+
+
+def attn_bwd(q, k, v, out, lse, dout, delta, dq, dk, dv, *, H, KVH, D, variant=0):
+    g = _attn_common(q, k, v, H, KVH, D, variant)
+    g.out = out.data_ptr()
+    g.out_batch_stride, g.out_ld = _bl(out)
+    g.lse = lse.data_ptr()
+    g.dout = dout.data_ptr()
+    g.dout_batch_stride, g.dout_ld = _bl(dout)
+    g.delta = delta.data_ptr()
+    g.dq = dq.data_ptr()
+    g.dq_batch_stride, g.dq_ld = _bl(dq)
+    g.dk, g.dv = dk.data_ptr(), dv.data_ptr()
+    assert _bl(dk) == _bl(dv)
+    g.dkv_batch_stride, g.dkv_ld = _bl(dk)
+    N.check(N.lib().of_attn_bwd(C.byref(g), N.stream_ptr()), "of_attn_bwd")
