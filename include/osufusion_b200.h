@@ -129,6 +129,140 @@ typedef struct {
 int of_attn_fwd(const of_attn_args* args, void* stream);
 int of_attn_bwd(const of_attn_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ResidualBlock bandwidth kernels (channels-last, GroupNorm(1,C) statistics come from of_gemm's epilogue).
+ * Replace, per ResidualBlock (residual.py:118-137): nn.GroupNorm(1,C) + FiLM `x*(scale+1)+shift` + SiLU
+ * (residual.py:71-83), GlobalContext `to_k` 1x1 conv + softmax over L + pooled einsum (residual.py:29-31),
+ * `h * se(h) + res_conv(x)` (residual.py:135-137) and their autograd backward.
+ * h = SiLU(FiLM(GN(y))) is never stored for block2: every consumer recomputes it from the bf16 conv output y.
+ *
+ *   of_rb_apply_fwd       out_bf16 = h                                   (block1: input of the second conv)
+ *   of_rb_rowdot          mode 0: out_rows[b,l] = bf16r( sum_c bf16r(h)*bf16r(vec[c]) + vec_bias )     (to_k logits)
+ *                         mode 1: out_rows[b,l] = p[b,l] * ( sum_c bf16r(h)*vec[b,c] - sum_c vec[b,c]*pooled[b,c] )
+ *                                 (= d logits, with vec = d pooled)
+ *   of_softmax_rows       p[b,:] = bf16r(softmax_L(logits[b,:]))          in place on out_rows
+ *   of_rb_pool            acc_bc[b,c] += sum_l bf16r(h[b,l,c]) * p[b,l]
+ *   of_rb_gate_fwd        out = h * gate[b,c] + res   -> out_f32 and/or out_bf16
+ *   of_rb_gate_bwd_reduce acc_bc[b,c] += sum_l dout_f32[b,l,c] * h[b,l,c]                              (d gate)
+ *   of_rb_bwd_pass1       mode 0 (block2): dh = dout_f32*gate + dpooled[b,c]*p[b,l] + da[b,l]*wk[c]
+ *                         mode 1 (block1): dh = dh_bf16
+ *                         df = dh*silu'(f); dss += (df*z | df); dz = df*(scale+1); dgamma += dz*xhat; dbeta += dz;
+ *                         dxhat_bf16 = dz*gamma; dstats[b] += (sum dxhat, sum dxhat*xhat);
+ *                         mode 0 also: dwk[c] += da*bf16r(h), dbk += da, optional dout_bf16 = bf16(dout_f32)
+ *   of_rb_bwd_apply       dy_bf16 = rstd*(dxhat - S1/n - xhat*S2/n);  dbias[c] += dy
+ * Constraints: C % 8 == 0, C <= 2048.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int B, L, C;
+  float eps;
+  int mode;
+  const void* y; long long y_ld, y_bs;
+  const double* stats;
+  const float* gamma; const float* beta;
+  const float* ss;
+  const float* vec; long long vec_bs;
+  const float* vec_bias;
+  const float* p;
+  const float* pooled;
+  const float* gate;
+  const float* res_f32; long long res_f32_ld, res_f32_bs;
+  const void* res_bf16; long long res_bf16_ld, res_bf16_bs;
+  float* out_f32; long long out_f32_ld, out_f32_bs;
+  void* out_bf16; long long out_bf16_ld, out_bf16_bs;
+  float* out_rows;
+  float* acc_bc;
+  const float* dout_f32; long long dout_f32_ld, dout_f32_bs;
+  const void* dh_bf16; long long dh_ld, dh_bs;
+  const float* dpooled;
+  const float* da;
+  const float* wk;
+  double* dstats;
+  float* dgamma; float* dbeta;
+  float* dwk; float* dbk;
+  float* dss;
+  void* dxhat_bf16; long long dxhat_ld, dxhat_bs;
+  void* dout_bf16; long long dout_bf16_ld, dout_bf16_bs;
+  void* dy_bf16; long long dy_ld, dy_bs;
+  float* dbias;
+} of_rb_args;
+
+int of_rb_apply_fwd(const of_rb_args* a, void* stream);
+int of_rb_rowdot(const of_rb_args* a, void* stream);
+int of_rb_pool(const of_rb_args* a, void* stream);
+int of_rb_gate_fwd(const of_rb_args* a, void* stream);
+int of_rb_gate_bwd_reduce(const of_rb_args* a, void* stream);
+int of_rb_bwd_pass1(const of_rb_args* a, void* stream);
+int of_rb_bwd_apply(const of_rb_args* a, void* stream);
+int of_softmax_rows(float* rows, int B, int L, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Transformer-block and glue kernels.
+ * of_layernorm_fwd/bwd : nn.LayerNorm(C) of `Attention.norm` (unet.py:117,127) on the fp32 residual stream; emits the
+ *                        fp32 normed tensor (the residual of unet.py:141) and its bf16 copy for the q/kv GEMM.
+ * of_rope_fwd/bwd      : RotaryPositionEmbedding.forward + apply_rotary_pos_emb/rotate_half (attention.py:52-58,
+ *                        utils.py:25-32) applied in place to the q and k slots of the fused qkv buffer; the cos/sin
+ *                        tables (L, D) are generated by the host exactly as the reference does (attention.py:33-49).
+ *                        bwd also converts the fp32 attention gradients to the bf16 (B, L, (H+2KVH)*D) layout.
+ * of_linear_small_*    : nn.Linear with M <= 16 rows: time_mlp / cond_mlp (unet.py:356-366), FiLM heads
+ *                        (residual.py:104-111), GlobalContext.layers 1x1 convs on the pooled (B,C,1) vector
+ *                        (residual.py:22-27).  act: 0 none, 1 SiLU, 2 Sigmoid.  round_bf16 mimics autocast rounding
+ *                        of inputs, weights and outputs.  bwd: dW/dbias accumulate (+=), dx accumulates atomically.
+ * of_colsum_bf16       : bias gradients of the large Linear/Conv layers: db[n] += sum_rows dy[row, n].
+ * of_pack_input        : F.pad(x, value=-1) / F.pad(a, value=-23) (unet.py:475-480) + channel-first -> channels-last
+ *                        bf16, fused with `add_noise` (diffusion.py:96) / `t*x+(1-t)*noise` (rectified_flow.py:95).
+ * of_unpack_output     : `final_conv(x)[:, :, :n]` slice + layout back to (B, 6, N) fp32 (unet.py:513).
+ * of_upsample2x_*      : F.interpolate(scale_factor=2, mode="nearest") of `Upsample` (unet.py:65) and its backward.
+ * of_cast_copy         : strided fp32/bf16 copy, cast or accumulate on (B, L, C) views (concat slices, grad sums).
+ * of_time_embed        : SinusoidalPositionEmbedding (unet.py:26-39).
+ * of_silu_small        : nn.SiLU on the (B, 2*dim_emb) conditioning vector (residual.py:105) and its backward.
+ * of_mse_fwd/bwd       : F.mse_loss(pred, target, "none") + orig_len mask + mean (diffusion.py:101-111).
+ * of_sampler_update    : CFG combine (unet.py:458-465) fused with DDIMScheduler.step (diffusers 0.29.2, eta=0,
+ *                        clip_sample; call site diffusion.py:75) or the midpoint axpy of torchdiffeq's fixed-grid
+ *                        solver (rectified_flow.py:78); also emits the packed bf16 input of the next denoiser call.
+ * of_pack_conv_weight / of_unpack_conv_wgrad / of_cast_f32_bf16 : parameter layout conversion between the
+ *                        reference's state_dict layout (Cout, Cin, k) fp32 and the [tap][Cout][Cin] bf16 GEMM operand.
+ * ------------------------------------------------------------------------------------------------ */
+int of_layernorm_fwd(const float* x, long long x_ld, int rows, int C, const float* gamma, const float* beta, float eps,
+                     float* out_f32, void* out_bf16, long long out_ld, float* mean_rstd, void* stream);
+int of_layernorm_bwd(const float* dy, long long dy_ld, const float* x, long long x_ld, int rows, int C, const float* gamma,
+                     const float* mean_rstd, float* dx_f32, void* dx_bf16, long long dx_ld, float* dgamma, float* dbeta,
+                     void* stream);
+int of_rope_fwd(void* qkv, long long ld, long long bs, int B, int L, int H, int KVH, int D, const void* cos_bf16,
+                const void* sin_bf16, void* stream);
+int of_rope_bwd(const float* dq, long long dq_ld, long long dq_bs, const float* dk, const float* dv, long long dkv_ld,
+                long long dkv_bs, void* dqkv_bf16, long long out_ld, long long out_bs, int B, int L, int H, int KVH, int D,
+                const void* cos_bf16, const void* sin_bf16, void* stream);
+int of_linear_small_fwd(const float* x, long long x_ld, int M, int N, int K, const float* W, long long w_ld, const float* bias,
+                        int act, int round_bf16, float* y, long long y_ld, float* ypre, void* stream);
+int of_linear_small_bwd(const float* dy, long long dy_ld, const float* ypre, int act, const float* x, long long x_ld, int M,
+                        int N, int K, const float* W, long long w_ld, int round_bf16, float* dW, float* dbias, float* dx,
+                        long long dx_ld, void* stream);
+int of_colsum_bf16(const void* dy, long long ld, long long rows, int N, float* db, void* stream);
+int of_pack_input(const float* x, const float* noise, const float* ca, const float* cb, int B, int C, int N, void* out, int Lp,
+                  int Cp, float pad_value, void* stream);
+int of_unpack_output(const void* y, long long ld, long long bs, int B, int C, int N, float* out, void* stream);
+int of_upsample2x_fwd(const void* x, long long x_ld, long long x_bs, int B, int L, int C, void* out, long long o_ld,
+                      long long o_bs, void* stream);
+int of_upsample2x_bwd(const float* d, long long d_ld, long long d_bs, int B, int L, int C, float* out_f32, void* out_bf16,
+                      long long o_ld, long long o_bs, void* stream);
+int of_cast_copy(const float* src32, const void* src16, long long s_ld, long long s_bs, int B, int L, int C, float* dst32,
+                 void* dst16, long long d_ld, long long d_bs, int accumulate, void* stream);
+int of_time_embed(const float* t, int B, int dim, float theta, float* out, void* stream);
+int of_silu_small(const float* x, const float* dy, float* out, long long n, void* stream);
+int of_mse_fwd(const void* pred, long long ld, long long bs, const float* x, const float* noise, float ta, float tb,
+               const long long* orig_len, int B, int C, int N, float* accum2, float* loss, void* stream);
+int of_mse_bwd(const void* pred, long long ld, long long bs, const float* x, const float* noise, float ta, float tb,
+               const long long* orig_len, int B, int C, int N, int Lp, int Cp, const float* accum2, const float* gscale,
+               void* dpred, void* stream);
+int of_sampler_update(const float* xin, const void* cond, const void* null_, long long ld, long long bs, float cond_scale,
+                      int mode, float c_eps, float c_div, float c_x0, float c_dir, int B, int C, int N, float* xout,
+                      void* packed, int Lp, int Cp, float pad_value, void* stream);
+int of_pack_conv_weight(const float* w, int Cout, int Cin, int k, void* out, int Cin_pad, int tap_offset, int taps_total,
+                        void* stream);
+int of_unpack_conv_wgrad(const float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw, int accumulate,
+                         void* stream);
+int of_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

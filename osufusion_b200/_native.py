@@ -13,6 +13,8 @@ from .build import LIB_PATH, build_native
 
 _lib = None
 
+P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
 
 class NativeError(RuntimeError):
     pass
@@ -20,20 +22,95 @@ class NativeError(RuntimeError):
 
 class GemmArgs(C.Structure):
     _fields_ = [
-        ("mode", C.c_int), ("b_mn_major", C.c_int), ("batch", C.c_int), ("rows", C.c_int),
-        ("N", C.c_int), ("K", C.c_int), ("taps", C.c_int), ("shift0", C.c_int), ("shift_step", C.c_int),
-        ("a", C.c_void_p), ("a_ld", C.c_longlong), ("a_batch_stride", C.c_longlong),
-        ("b", C.c_void_p), ("b_ld", C.c_longlong), ("b_tap_stride", C.c_longlong),
-        ("bias", C.c_void_p),
-        ("aux_f32", C.c_void_p), ("aux_f32_ld", C.c_longlong), ("aux_f32_batch_stride", C.c_longlong),
-        ("aux_bf16", C.c_void_p), ("aux_bf16_ld", C.c_longlong), ("aux_bf16_batch_stride", C.c_longlong),
-        ("aux_is_dsilu", C.c_int), ("act", C.c_int),
-        ("pre_bf16", C.c_void_p),
-        ("out_bf16", C.c_void_p), ("out_bf16_ld", C.c_longlong), ("out_bf16_batch_stride", C.c_longlong),
-        ("out_f32", C.c_void_p), ("out_f32_ld", C.c_longlong), ("out_f32_batch_stride", C.c_longlong),
-        ("stats", C.c_void_p),
-        ("block_n", C.c_int), ("split_k", C.c_int),
+        ("mode", I), ("b_mn_major", I), ("batch", I), ("rows", I),
+        ("N", I), ("K", I), ("taps", I), ("shift0", I), ("shift_step", I),
+        ("a", P), ("a_ld", LL), ("a_batch_stride", LL),
+        ("b", P), ("b_ld", LL), ("b_tap_stride", LL),
+        ("bias", P),
+        ("aux_f32", P), ("aux_f32_ld", LL), ("aux_f32_batch_stride", LL),
+        ("aux_bf16", P), ("aux_bf16_ld", LL), ("aux_bf16_batch_stride", LL),
+        ("aux_is_dsilu", I), ("act", I),
+        ("pre_bf16", P),
+        ("out_bf16", P), ("out_bf16_ld", LL), ("out_bf16_batch_stride", LL),
+        ("out_f32", P), ("out_f32_ld", LL), ("out_f32_batch_stride", LL),
+        ("stats", P),
+        ("block_n", I), ("split_k", I),
     ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("B", I), ("H", I), ("KVH", I), ("L", I), ("D", I),
+        ("scale", F), ("variant", I),
+        ("q", P), ("q_ld", LL), ("q_batch_stride", LL),
+        ("k", P), ("v", P), ("kv_ld", LL), ("kv_batch_stride", LL),
+        ("out", P), ("out_ld", LL), ("out_batch_stride", LL),
+        ("lse", P),
+        ("dout", P), ("dout_ld", LL), ("dout_batch_stride", LL),
+        ("delta", P),
+        ("dq", P), ("dq_ld", LL), ("dq_batch_stride", LL),
+        ("dk", P), ("dv", P), ("dkv_ld", LL), ("dkv_batch_stride", LL),
+    ]
+
+
+class RbArgs(C.Structure):
+    _fields_ = [
+        ("B", I), ("L", I), ("C", I), ("eps", F), ("mode", I),
+        ("y", P), ("y_ld", LL), ("y_bs", LL),
+        ("stats", P), ("gamma", P), ("beta", P), ("ss", P),
+        ("vec", P), ("vec_bs", LL), ("vec_bias", P),
+        ("p", P), ("pooled", P), ("gate", P),
+        ("res_f32", P), ("res_f32_ld", LL), ("res_f32_bs", LL),
+        ("res_bf16", P), ("res_bf16_ld", LL), ("res_bf16_bs", LL),
+        ("out_f32", P), ("out_f32_ld", LL), ("out_f32_bs", LL),
+        ("out_bf16", P), ("out_bf16_ld", LL), ("out_bf16_bs", LL),
+        ("out_rows", P), ("acc_bc", P),
+        ("dout_f32", P), ("dout_f32_ld", LL), ("dout_f32_bs", LL),
+        ("dh_bf16", P), ("dh_ld", LL), ("dh_bs", LL),
+        ("dpooled", P), ("da", P), ("wk", P),
+        ("dstats", P), ("dgamma", P), ("dbeta", P), ("dwk", P), ("dbk", P), ("dss", P),
+        ("dxhat_bf16", P), ("dxhat_ld", LL), ("dxhat_bs", LL),
+        ("dout_bf16", P), ("dout_bf16_ld", LL), ("dout_bf16_bs", LL),
+        ("dy_bf16", P), ("dy_ld", LL), ("dy_bs", LL),
+        ("dbias", P),
+    ]
+
+
+# name -> argtypes (the trailing stream pointer included); mirrors include/osufusion_b200.h
+_SIGS = {
+    "of_gemm": [C.POINTER(GemmArgs), P],
+    "of_attn_fwd": [C.POINTER(AttnArgs), P],
+    "of_attn_bwd": [C.POINTER(AttnArgs), P],
+    "of_rb_apply_fwd": [C.POINTER(RbArgs), P],
+    "of_rb_rowdot": [C.POINTER(RbArgs), P],
+    "of_rb_pool": [C.POINTER(RbArgs), P],
+    "of_rb_gate_fwd": [C.POINTER(RbArgs), P],
+    "of_rb_gate_bwd_reduce": [C.POINTER(RbArgs), P],
+    "of_rb_bwd_pass1": [C.POINTER(RbArgs), P],
+    "of_rb_bwd_apply": [C.POINTER(RbArgs), P],
+    "of_softmax_rows": [P, I, I, P],
+    "of_layernorm_fwd": [P, LL, I, I, P, P, F, P, P, LL, P, P],
+    "of_layernorm_bwd": [P, LL, P, LL, I, I, P, P, P, P, LL, P, P, P],
+    "of_rope_fwd": [P, LL, LL, I, I, I, I, I, P, P, P],
+    "of_rope_bwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, P, P, P],
+    "of_linear_small_fwd": [P, LL, I, I, I, P, LL, P, I, I, P, LL, P, P],
+    "of_linear_small_bwd": [P, LL, P, I, P, LL, I, I, I, P, LL, I, P, P, P, LL, P],
+    "of_colsum_bf16": [P, LL, LL, I, P, P],
+    "of_pack_input": [P, P, P, P, I, I, I, P, I, I, F, P],
+    "of_unpack_output": [P, LL, LL, I, I, I, P, P],
+    "of_upsample2x_fwd": [P, LL, LL, I, I, I, P, LL, LL, P],
+    "of_upsample2x_bwd": [P, LL, LL, I, I, I, P, P, LL, LL, P],
+    "of_cast_copy": [P, P, LL, LL, I, I, I, P, P, LL, LL, I, P],
+    "of_time_embed": [P, I, I, F, P, P],
+    "of_silu_small": [P, P, P, LL, P],
+    "of_mse_fwd": [P, LL, LL, P, P, F, F, P, I, I, I, P, P, P],
+    "of_mse_bwd": [P, LL, LL, P, P, F, F, P, I, I, I, I, I, P, P, P, P],
+    "of_sampler_update": [P, P, P, LL, LL, F, I, F, F, F, F, I, I, I, P, P, I, I, F, P],
+    "of_pack_conv_weight": [P, I, I, I, P, I, I, I, P],
+    "of_unpack_conv_wgrad": [P, I, I, I, I, I, P, I, P],
+    "of_cast_f32_bf16": [P, P, LL, P],
+}
+EXPORTS = ["of_last_error", "of_version", "of_launch_count", "of_reset_launch_count", *_SIGS.keys()]
 
 
 def lib() -> C.CDLL:
@@ -47,9 +124,10 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(path))
         _lib.of_last_error.restype = C.c_char_p
         _lib.of_launch_count.restype = C.c_longlong
-        _lib.of_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
-        _lib.of_attn_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
-        _lib.of_attn_bwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+        for name, sig in _SIGS.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = sig
+            fn.restype = C.c_int
     return _lib
 
 
@@ -58,24 +136,17 @@ def check(rc: int, what: str) -> None:
         raise NativeError(f"{what} failed (rc={rc}): {lib().of_last_error().decode()}")
 
 
+def call(name: str, *args) -> None:
+    """Invoke an entry point with the current torch CUDA stream appended; raises on a non-zero return."""
+    fn = getattr(lib(), name)
+    rc = fn(*args, stream_ptr())
+    if rc != 0:
+        raise NativeError(f"{name} failed (rc={rc}): {lib().of_last_error().decode()}")
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
 def ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
-
-
-class AttnArgs(C.Structure):
-    _fields_ = [
-        ("B", C.c_int), ("H", C.c_int), ("KVH", C.c_int), ("L", C.c_int), ("D", C.c_int),
-        ("scale", C.c_float), ("variant", C.c_int),
-        ("q", C.c_void_p), ("q_ld", C.c_longlong), ("q_batch_stride", C.c_longlong),
-        ("k", C.c_void_p), ("v", C.c_void_p), ("kv_ld", C.c_longlong), ("kv_batch_stride", C.c_longlong),
-        ("out", C.c_void_p), ("out_ld", C.c_longlong), ("out_batch_stride", C.c_longlong),
-        ("lse", C.c_void_p),
-        ("dout", C.c_void_p), ("dout_ld", C.c_longlong), ("dout_batch_stride", C.c_longlong),
-        ("delta", C.c_void_p),
-        ("dq", C.c_void_p), ("dq_ld", C.c_longlong), ("dq_batch_stride", C.c_longlong),
-        ("dk", C.c_void_p), ("dv", C.c_void_p), ("dkv_ld", C.c_longlong), ("dkv_batch_stride", C.c_longlong),
-    ]

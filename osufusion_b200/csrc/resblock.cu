@@ -1,0 +1,403 @@
+// ResidualBlock bandwidth kernels: GroupNorm(1,C)+FiLM+SiLU recompute, GlobalContext pooling, gate+residual and
+// their backward passes.  See include/osufusion_b200.h (of_rb_*) for the exact contracts and reference citations.
+//
+// Thread mapping ("channel-owner"): a CTA of 256 threads covers `vecs = C/8` 16-byte channel vectors times
+// `rpar = 256/vecs` rows at once; each thread keeps its 8 channels' constants (gamma, beta, FiLM, gate, ...) in
+// registers and walks down the rows of its chunk, so per-channel reductions are register-local until one final
+// atomic per channel.  Row-wise dot products use the warp-per-row kernel (of_rb_rowdot) instead.
+#include "host_common.h"
+#include "rowops.cuh"
+
+namespace ofx {
+
+constexpr int kRbThreads = 256;
+constexpr int kRowsPerCta = 64;
+
+struct GnCtx {
+  int B, L, C;
+  float eps;
+  const __nv_bfloat16* y;
+  long long y_ld, y_bs;
+  const double* stats;
+  const float* gamma;
+  const float* beta;
+  const float* ss;
+};
+
+__device__ __forceinline__ GnCtx make_ctx(const of_rb_args& a) {
+  GnCtx g;
+  g.B = a.B; g.L = a.L; g.C = a.C; g.eps = a.eps;
+  g.y = reinterpret_cast<const __nv_bfloat16*>(a.y); g.y_ld = a.y_ld; g.y_bs = a.y_bs;
+  g.stats = a.stats; g.gamma = a.gamma; g.beta = a.beta; g.ss = a.ss;
+  return g;
+}
+
+// Per-thread constants for its 8 channels.
+struct ChanConst {
+  V8 gamma, beta, sp1, shift;
+  float mean, rstd;
+  bool film;
+};
+
+__device__ __forceinline__ ChanConst load_consts(const GnCtx& g, int b, int c0) {
+  ChanConst k;
+  k.gamma = ld_f32x8(g.gamma + c0);
+  k.beta = ld_f32x8(g.beta + c0);
+  k.film = g.ss != nullptr;
+  if (k.film) {
+    V8 sc = ld_f32x8(g.ss + (long long)b * 2 * g.C + c0);
+    k.shift = ld_f32x8(g.ss + (long long)b * 2 * g.C + g.C + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) k.sp1.v[j] = bf16_round(sc.v[j] + 1.0f);  // reference: bf16 `scale + 1` under autocast
+  }
+  gn_mean_rstd(g.stats, b, (double)g.L * (double)g.C, g.eps, k.mean, k.rstd);
+  return k;
+}
+
+// xhat, z = xhat*gamma+beta, f = FiLM(z), h = silu(f) for one 8-channel vector.
+__device__ __forceinline__ void gn_eval(const ChanConst& k, const V8& y, V8& xhat, V8& z, V8& f, V8& h) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    xhat.v[j] = (y.v[j] - k.mean) * k.rstd;
+    z.v[j] = xhat.v[j] * k.gamma.v[j] + k.beta.v[j];
+    f.v[j] = k.film ? (z.v[j] * k.sp1.v[j] + k.shift.v[j]) : z.v[j];
+    h.v[j] = silu_acc(f.v[j]);
+  }
+}
+
+struct Map {
+  int vecs, rpar, vi, rsub, c0, b, l_begin, l_end;
+  bool active;
+};
+__device__ __forceinline__ Map make_map(int C, int L) {
+  Map m;
+  m.vecs = C >> 3;
+  m.rpar = kRbThreads / m.vecs;
+  m.vi = threadIdx.x % m.vecs;
+  m.rsub = threadIdx.x / m.vecs;
+  m.active = m.rsub < m.rpar;
+  m.c0 = m.vi * 8;
+  m.b = blockIdx.y;
+  m.l_begin = blockIdx.x * kRowsPerCta;
+  m.l_end = min(m.l_begin + kRowsPerCta, L);
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(kRbThreads) rb_apply_fwd_kernel(const of_rb_args a) {
+  GnCtx g = make_ctx(a);
+  Map m = make_map(a.C, a.L);
+  if (!m.active) return;
+  ChanConst k = load_consts(g, m.b, m.c0);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
+    gn_eval(k, y, xh, z, f, h);
+    st_bf16x8(out + m.b * a.out_bf16_bs + (long long)l * a.out_bf16_ld + m.c0, h);
+  }
+}
+
+// warp per row: dot(h_row, vec)
+__global__ void __launch_bounds__(256) rb_rowdot_kernel(const of_rb_args a) {
+  GnCtx g = make_ctx(a);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int vecs = a.C >> 3;
+  float mean, rstd;
+  gn_mean_rstd(g.stats, b, (double)g.L * (double)g.C, g.eps, mean, rstd);
+  const float* vec = a.vec + (long long)b * a.vec_bs;
+  float T = 0.f;
+  if (a.mode == 1) {
+    for (int v = lane; v < vecs; v += 32) {
+      V8 d = ld_f32x8(vec + v * 8), pl = ld_f32x8(a.pooled + (long long)b * a.C + v * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) T += d.v[j] * pl.v[j];
+    }
+    T = warp_sum(T);
+  }
+  const float bias = a.vec_bias ? *a.vec_bias : 0.f;
+  const int rows_per_cta = 8 * 8;  // 8 warps x 8 rows
+  const int l0 = blockIdx.x * rows_per_cta;
+  for (int rr = warp; rr < rows_per_cta; rr += 8) {
+    const int l = l0 + rr;
+    if (l >= a.L) break;
+    float acc = 0.f;
+    for (int v = lane; v < vecs; v += 32) {
+      const int c0 = v * 8;
+      ChanConst k;
+      k.gamma = ld_f32x8(g.gamma + c0);
+      k.beta = ld_f32x8(g.beta + c0);
+      k.film = g.ss != nullptr;
+      if (k.film) {
+        V8 sc = ld_f32x8(g.ss + (long long)b * 2 * g.C + c0);
+        k.shift = ld_f32x8(g.ss + (long long)b * 2 * g.C + g.C + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) k.sp1.v[j] = bf16_round(sc.v[j] + 1.0f);
+      }
+      k.mean = mean;
+      k.rstd = rstd;
+      V8 y = ld_bf16x8(g.y + b * g.y_bs + (long long)l * g.y_ld + c0), xh, z, f, h;
+      gn_eval(k, y, xh, z, f, h);
+      V8 w = ld_f32x8(vec + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += bf16_round(h.v[j]) * (a.mode == 0 ? bf16_round(w.v[j]) : w.v[j]);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float r;
+      if (a.mode == 0) r = bf16_round(acc + bias);
+      else r = a.p[(long long)b * a.L + l] * (acc - T);
+      a.out_rows[(long long)b * a.L + l] = r;
+    }
+  }
+}
+
+// one CTA per sample: p = bf16r(softmax(logits)) in place
+__global__ void __launch_bounds__(1024) softmax_rows_kernel(float* rows, int L) {
+  __shared__ float sm[32];
+  float* r = rows + (long long)blockIdx.x * L;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, r[i]);
+  mx = block_max(mx, sm);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s += expf(r[i] - mx);
+  s = block_sum(s, sm);
+  const float inv = 1.0f / s;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] = bf16_round(expf(r[i] - mx) * inv);
+}
+
+__global__ void __launch_bounds__(kRbThreads) rb_pool_kernel(const of_rb_args a) {
+  GnCtx g = make_ctx(a);
+  Map m = make_map(a.C, a.L);
+  if (!m.active) return;
+  ChanConst k = load_consts(g, m.b, m.c0);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
+    gn_eval(k, y, xh, z, f, h);
+    const float pl = a.p[(long long)m.b * a.L + l];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += bf16_round(h.v[j]) * pl;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(a.acc_bc + (long long)m.b * a.C + m.c0 + j, acc[j]);
+}
+
+__global__ void __launch_bounds__(kRbThreads) rb_gate_fwd_kernel(const of_rb_args a) {
+  GnCtx g = make_ctx(a);
+  Map m = make_map(a.C, a.L);
+  if (!m.active) return;
+  ChanConst k = load_consts(g, m.b, m.c0);
+  V8 gate = ld_f32x8(a.gate + (long long)m.b * a.C + m.c0);
+  const __nv_bfloat16* r16 = reinterpret_cast<const __nv_bfloat16*>(a.res_bf16);
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h, o;
+    gn_eval(k, y, xh, z, f, h);
+    V8 r;
+    if (a.res_f32) r = ld_f32x8(a.res_f32 + m.b * a.res_f32_bs + (long long)l * a.res_f32_ld + m.c0);
+    else r = ld_bf16x8(r16 + m.b * a.res_bf16_bs + (long long)l * a.res_bf16_ld + m.c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = h.v[j] * gate.v[j] + r.v[j];
+    if (a.out_f32) st_f32x8(a.out_f32 + m.b * a.out_f32_bs + (long long)l * a.out_f32_ld + m.c0, o);
+    if (o16) st_bf16x8(o16 + m.b * a.out_bf16_bs + (long long)l * a.out_bf16_ld + m.c0, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(kRbThreads) rb_gate_bwd_reduce_kernel(const of_rb_args a) {
+  GnCtx g = make_ctx(a);
+  Map m = make_map(a.C, a.L);
+  if (!m.active) return;
+  ChanConst k = load_consts(g, m.b, m.c0);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
+    gn_eval(k, y, xh, z, f, h);
+    V8 d = ld_f32x8(a.dout_f32 + m.b * a.dout_f32_bs + (long long)l * a.dout_f32_ld + m.c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += d.v[j] * h.v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(a.acc_bc + (long long)m.b * a.C + m.c0 + j, acc[j]);
+}
+
+__global__ void __launch_bounds__(kRbThreads) rb_bwd_pass1_kernel(const of_rb_args a) {
+  __shared__ float sm[32];
+  GnCtx g = make_ctx(a);
+  Map m = make_map(a.C, a.L);
+  float s1 = 0.f, s2 = 0.f, sda = 0.f;
+  if (m.active) {
+    ChanConst k = load_consts(g, m.b, m.c0);
+    V8 gate, dpool, wk;
+    if (a.mode == 0) {
+      gate = ld_f32x8(a.gate + (long long)m.b * a.C + m.c0);
+      dpool = ld_f32x8(a.dpooled + (long long)m.b * a.C + m.c0);
+      wk = ld_f32x8(a.wk + m.c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wk.v[j] = bf16_round(wk.v[j]);
+    }
+    float dgam[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbet[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float dsc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dsh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dwk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const __nv_bfloat16* dh16 = reinterpret_cast<const __nv_bfloat16*>(a.dh_bf16);
+    __nv_bfloat16* dxh = reinterpret_cast<__nv_bfloat16*>(a.dxhat_bf16);
+    __nv_bfloat16* do16 = reinterpret_cast<__nv_bfloat16*>(a.dout_bf16);
+    for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+      V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h, dh, dx;
+      gn_eval(k, y, xh, z, f, h);
+      if (a.mode == 0) {
+        V8 d = ld_f32x8(a.dout_f32 + m.b * a.dout_f32_bs + (long long)l * a.dout_f32_ld + m.c0);
+        const float pl = a.p[(long long)m.b * a.L + l];
+        const float da = a.da[(long long)m.b * a.L + l];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dh.v[j] = d.v[j] * gate.v[j] + dpool.v[j] * pl + da * wk.v[j];
+          dwk[j] += da * bf16_round(h.v[j]);
+        }
+        if (m.vi == 0) sda += da;
+        if (do16) st_bf16x8(do16 + m.b * a.dout_bf16_bs + (long long)l * a.dout_bf16_ld + m.c0, d);
+      } else {
+        dh = ld_bf16x8(dh16 + m.b * a.dh_bs + (long long)l * a.dh_ld + m.c0);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float df = dh.v[j] * dsilu_acc(f.v[j]);
+        float dz = df;
+        if (k.film) {
+          dsc[j] += df * z.v[j];
+          dsh[j] += df;
+          dz = df * k.sp1.v[j];
+        }
+        dgam[j] += dz * xh.v[j];
+        dbet[j] += dz;
+        dx.v[j] = dz * k.gamma.v[j];
+        float dxr = bf16_round(dx.v[j]);  // what pass 2 will read back
+        s1 += dxr;
+        s2 += dxr * xh.v[j];
+      }
+      st_bf16x8(dxh + m.b * a.dxhat_bs + (long long)l * a.dxhat_ld + m.c0, dx);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(a.dgamma + m.c0 + j, dgam[j]);
+      atomicAdd(a.dbeta + m.c0 + j, dbet[j]);
+      if (k.film) {
+        atomicAdd(a.dss + (long long)m.b * 2 * a.C + m.c0 + j, dsc[j]);
+        atomicAdd(a.dss + (long long)m.b * 2 * a.C + a.C + m.c0 + j, dsh[j]);
+      }
+      if (a.mode == 0) atomicAdd(a.dwk + m.c0 + j, dwk[j]);
+    }
+  }
+  s1 = block_sum(s1, sm);
+  s2 = block_sum(s2, sm);
+  if (a.mode == 0) sda = block_sum(sda, sm);
+  if (threadIdx.x == 0) {
+    atomicAdd(a.dstats + 2 * blockIdx.y, (double)s1);
+    atomicAdd(a.dstats + 2 * blockIdx.y + 1, (double)s2);
+    if (a.mode == 0 && a.dbk) atomicAdd(a.dbk, sda);
+  }
+}
+
+__global__ void __launch_bounds__(kRbThreads) rb_bwd_apply_kernel(const of_rb_args a) {
+  GnCtx g = make_ctx(a);
+  Map m = make_map(a.C, a.L);
+  if (!m.active) return;
+  float mean, rstd;
+  const double n = (double)a.L * (double)a.C;
+  gn_mean_rstd(g.stats, m.b, n, g.eps, mean, rstd);
+  const float m1 = (float)(a.dstats[2 * m.b] / n), m2 = (float)(a.dstats[2 * m.b + 1] / n);
+  const __nv_bfloat16* dxh = reinterpret_cast<const __nv_bfloat16*>(a.dxhat_bf16);
+  __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(a.dy_bf16);
+  float db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0);
+    V8 dx = ld_bf16x8(dxh + m.b * a.dxhat_bs + (long long)l * a.dxhat_ld + m.c0), o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float xh = (y.v[j] - mean) * rstd;
+      o.v[j] = rstd * (dx.v[j] - m1 - xh * m2);
+      db[j] += bf16_round(o.v[j]);
+    }
+    st_bf16x8(dy + m.b * a.dy_bs + (long long)l * a.dy_ld + m.c0, o);
+  }
+  if (a.dbias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(a.dbias + m.c0 + j, db[j]);
+  }
+}
+
+static int check_common(const of_rb_args* a, const char* who) {
+  OF_REQUIRE(a != nullptr, "%s: null args", who);
+  OF_REQUIRE(a->B >= 1 && a->L >= 1 && a->C >= 8 && a->C % 8 == 0 && a->C <= 2048, "%s: unsupported C=%d (need C%%8==0, C<=2048)",
+             who, a->C);
+  OF_REQUIRE(a->y && a->stats && a->gamma && a->beta, "%s: null GroupNorm input", who);
+  OF_REQUIRE(a->y_ld % 8 == 0, "%s: y_ld %% 8", who);
+  return OF_OK;
+}
+static dim3 rb_grid(const of_rb_args* a) { return dim3((a->L + kRowsPerCta - 1) / kRowsPerCta, a->B); }
+
+}  // namespace ofx
+
+using namespace ofx;
+
+#define RB_LAUNCH(kernel, grid, threads)                                           \
+  kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);       \
+  OF_CHECK_CUDA(cudaGetLastError());                                              \
+  count_launch();                                                                 \
+  return OF_OK;
+
+extern "C" int of_rb_apply_fwd(const of_rb_args* a, void* stream) {
+  int rc = check_common(a, "of_rb_apply_fwd");
+  if (rc) return rc;
+  OF_REQUIRE(a->out_bf16 && a->out_bf16_ld % 8 == 0, "of_rb_apply_fwd: bad out_bf16");
+  RB_LAUNCH(rb_apply_fwd_kernel, rb_grid(a), kRbThreads)
+}
+extern "C" int of_rb_rowdot(const of_rb_args* a, void* stream) {
+  int rc = check_common(a, "of_rb_rowdot");
+  if (rc) return rc;
+  OF_REQUIRE(a->vec && a->out_rows, "of_rb_rowdot: null vec/out_rows");
+  if (a->mode == 1) OF_REQUIRE(a->p && a->pooled, "of_rb_rowdot(mode 1): null p/pooled");
+  RB_LAUNCH(rb_rowdot_kernel, dim3((a->L + 63) / 64, a->B), 256)
+}
+extern "C" int of_softmax_rows(float* rows, int B, int L, void* stream) {
+  OF_REQUIRE(rows && B >= 1 && L >= 1, "of_softmax_rows: bad args");
+  softmax_rows_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rows, L);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
+extern "C" int of_rb_pool(const of_rb_args* a, void* stream) {
+  int rc = check_common(a, "of_rb_pool");
+  if (rc) return rc;
+  OF_REQUIRE(a->p && a->acc_bc, "of_rb_pool: null p/acc_bc");
+  RB_LAUNCH(rb_pool_kernel, rb_grid(a), kRbThreads)
+}
+extern "C" int of_rb_gate_fwd(const of_rb_args* a, void* stream) {
+  int rc = check_common(a, "of_rb_gate_fwd");
+  if (rc) return rc;
+  OF_REQUIRE(a->gate && (a->res_f32 || a->res_bf16) && (a->out_f32 || a->out_bf16), "of_rb_gate_fwd: null gate/res/out");
+  RB_LAUNCH(rb_gate_fwd_kernel, rb_grid(a), kRbThreads)
+}
+extern "C" int of_rb_gate_bwd_reduce(const of_rb_args* a, void* stream) {
+  int rc = check_common(a, "of_rb_gate_bwd_reduce");
+  if (rc) return rc;
+  OF_REQUIRE(a->dout_f32 && a->acc_bc, "of_rb_gate_bwd_reduce: null dout/acc");
+  RB_LAUNCH(rb_gate_bwd_reduce_kernel, rb_grid(a), kRbThreads)
+}
+extern "C" int of_rb_bwd_pass1(const of_rb_args* a, void* stream) {
+  int rc = check_common(a, "of_rb_bwd_pass1");
+  if (rc) return rc;
+  OF_REQUIRE(a->dxhat_bf16 && a->dstats && a->dgamma && a->dbeta, "of_rb_bwd_pass1: null outputs");
+  if (a->ss) OF_REQUIRE(a->dss, "of_rb_bwd_pass1: dss required with FiLM");
+  if (a->mode == 0)
+    OF_REQUIRE(a->dout_f32 && a->gate && a->dpooled && a->p && a->da && a->wk && a->dwk, "of_rb_bwd_pass1(mode 0): null inputs");
+  else
+    OF_REQUIRE(a->dh_bf16, "of_rb_bwd_pass1(mode 1): null dh");
+  RB_LAUNCH(rb_bwd_pass1_kernel, rb_grid(a), kRbThreads)
+}
+extern "C" int of_rb_bwd_apply(const of_rb_args* a, void* stream) {
+  int rc = check_common(a, "of_rb_bwd_apply");
+  if (rc) return rc;
+  OF_REQUIRE(a->dxhat_bf16 && a->dstats && a->dy_bf16, "of_rb_bwd_apply: null pointers");
+  RB_LAUNCH(rb_bwd_apply_kernel, rb_grid(a), kRbThreads)
+}

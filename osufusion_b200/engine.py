@@ -1,0 +1,737 @@
+"""Execution engine of the B200 denoiser: a hand-rolled forward/backward "tape" over the C-ABI kernels.
+
+torch is used for device memory (torch.empty/zeros), the CUDA stream, parameters and tiny (B, dim_emb) glue; every
+FLOP and every full-tensor pass of the denoiser runs in libosufusion_sm100.so.  torch.autograd sees the whole UNet as
+ONE node (modules.UNetFunction): the backward pass is the reversed tape below, which lets gradients be accumulated by
+GEMM epilogues / fp32 atomics in place and lets the data-parallel wrapper launch NCCL buckets while backward still runs.
+
+Numerics = the reference under CUDA bf16 autocast (mode "M1"): bf16 GEMM/attention operands with
+fp32 accumulation, fp32 residual stream, fp32 norms; rounding points of the reference are reproduced where cheap.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional
+
+import torch
+
+from . import _native as N
+from . import ops_raw as R
+
+BF16, F32, F64 = torch.bfloat16, torch.float32, torch.float64
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _bl(t: torch.Tensor):
+    assert t.dim() == 3 and t.stride(2) == 1, (t.shape, t.stride())
+    return t.stride(0), t.stride(1)
+
+
+class Act:
+    """Channels-last activation (B, L, C): fp32 residual-stream copy and/or bf16 GEMM-operand copy, plus its fp32 grad."""
+    __slots__ = ("f32", "bf16", "grad")
+
+    def __init__(self, f32: Optional[torch.Tensor] = None, bf16: Optional[torch.Tensor] = None) -> None:
+        self.f32, self.bf16, self.grad = f32, bf16, None
+
+    @property
+    def shape(self):
+        return (self.f32 if self.f32 is not None else self.bf16).shape
+
+    def add_grad(self, g: torch.Tensor) -> None:
+        """Accumulate an fp32 (B, L, C) gradient view; the first contribution is adopted without a copy."""
+        if self.grad is None:
+            self.grad = g
+        else:
+            cast_copy(g, self.grad, accumulate=True)
+
+
+class Tape:
+    def __init__(self) -> None:
+        self.ops: List[Callable[[], None]] = []
+
+    def push(self, fn: Callable[[], None]) -> None:
+        self.ops.append(fn)
+
+    def run_backward(self, after_op: Optional[Callable[[int], None]] = None) -> None:
+        n = len(self.ops)
+        for i in range(n - 1, -1, -1):
+            self.ops[i]()
+            self.ops[i] = None
+            if after_op is not None:
+                after_op(i)
+        self.ops.clear()
+
+
+# ------------------------------------------------------------------------------------------------ raw helpers
+def empty(shape, dtype, device):
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def zeros(shape, dtype, device):
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
+def cast_copy(src: torch.Tensor, dst: torch.Tensor, accumulate: bool = False) -> None:
+    """dst (fp32|bf16 (B,L,C) view) = / += src (fp32|bf16 (B,L,C) view)."""
+    B, L, Cc = src.shape
+    s_bs, s_ld = _bl(src)
+    d_bs, d_ld = _bl(dst)
+    N.call("of_cast_copy", _p(src) if src.dtype == F32 else None, _p(src) if src.dtype == BF16 else None, s_ld, s_bs,
+           B, L, Cc, _p(dst) if dst.dtype == F32 else None, _p(dst) if dst.dtype == BF16 else None, d_ld, d_bs,
+           int(accumulate))
+
+
+def linear_small_fwd(x, W, bias, act=0, want_pre=False):
+    """x (M,K) fp32 contiguous, W (N,K[,1]) fp32 parameter -> y (M,N) fp32 (bf16-rounded values)."""
+    M, K = x.shape
+    Nn = W.shape[0]
+    y = empty((M, Nn), F32, x.device)
+    pre = empty((M, Nn), F32, x.device) if want_pre else None
+    N.call("of_linear_small_fwd", _p(x), x.stride(0), M, Nn, K, _p(W), K, _p(bias), act, 1, _p(y), Nn, _p(pre))
+    return y, pre
+
+
+def linear_small_bwd(dy, pre, act, x, W, dW, dbias, dx):
+    M, K = x.shape
+    Nn = W.shape[0]
+    N.call("of_linear_small_bwd", _p(dy), dy.stride(0), _p(pre), act, _p(x), x.stride(0), M, Nn, K, _p(W), K, 1, _p(dW),
+           _p(dbias), _p(dx), dx.stride(0) if dx is not None else 0)
+
+
+def colsum(dy16: torch.Tensor, out: torch.Tensor) -> None:
+    """out[n] += sum over all rows of the (B, L, N) bf16 view (rows must be uniformly strided: bs == L*ld)."""
+    B, L, Nn = dy16.shape
+    bs, ld = _bl(dy16)
+    if B > 1 and bs != L * ld:
+        for b in range(B):
+            N.call("of_colsum_bf16", _p(dy16[b]), ld, L, Nn, _p(out))
+    else:
+        N.call("of_colsum_bf16", _p(dy16), ld, B * L, Nn, _p(out))
+
+
+# ------------------------------------------------------------------------------------------------ parameter staging
+class ParamStore:
+    """bf16 GEMM-operand copies of the fp32 master parameters and the fp32 gradient buffers the kernels accumulate into.
+
+    `refresh=True` (training): operand copies are rebuilt on every forward (the reference's autocast also re-casts every
+    weight each iteration).  `refresh=False` (sampling): copies are cached per parameter version.
+    """
+
+    def __init__(self) -> None:
+        self.cache = {}
+        self.grads = {}
+        self.refresh = True
+        self.epoch = 0
+
+    def begin_forward(self, refresh: bool) -> None:
+        self.refresh = refresh
+        self.epoch += 1
+
+    def _cached(self, key, params, build):
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] == ver and (not self.refresh or hit[2] == self.epoch):
+            return hit[1]
+        val = build()
+        self.cache[key] = (ver, val, self.epoch)
+        return val
+
+    # ---- operand builders
+    def linear_w(self, *ws: torch.nn.Parameter) -> torch.Tensor:
+        """[sum N_i][K] bf16 = row-concatenation of Linear / 1x1-conv weights."""
+        def build():
+            K = ws[0].shape[1]
+            out = empty((sum(w.shape[0] for w in ws), K), BF16, ws[0].device)
+            r = 0
+            for w in ws:
+                N.call("of_cast_f32_bf16", _p(w), out[r:].data_ptr(), w.numel())
+                r += w.shape[0]
+            return out
+        return self._cached(("lin",) + tuple(id(w) for w in ws), ws, build)
+
+    def conv_w(self, w: torch.nn.Parameter) -> torch.Tensor:
+        """(Cout, Cin, k) fp32 -> [k][Cout][Cin_pad] bf16."""
+        def build():
+            Cout, Cin, k = w.shape
+            cp = (Cin + 7) // 8 * 8
+            out = empty((k, Cout, cp), BF16, w.device)
+            N.call("of_pack_conv_weight", _p(w), Cout, Cin, k, _p(out), cp, 0, k)
+            return out
+        return self._cached(("conv", id(w)), (w,), build)
+
+    def down_w(self, w: torch.nn.Parameter) -> torch.Tensor:
+        """stride-2 conv as a 2-tap conv over the (B, L/2, 2C) view: [2][Cout][2Cin] = [W0|W1], [W2|0]."""
+        def build():
+            Cout, Cin, _ = w.shape
+            out = zeros((2, Cout, 2 * Cin), F32, w.device)
+            out[0, :, :Cin] = w[:, :, 0]
+            out[0, :, Cin:] = w[:, :, 1]
+            out[1, :, :Cin] = w[:, :, 2]
+            return out.to(BF16)
+        return self._cached(("down", id(w)), (w,), build)
+
+    def cross_w(self, convs) -> torch.Tensor:
+        """CrossEmbedLayer: all branches zero-padded to the widest kernel -> [kmax][dim_out][Cin_pad]."""
+        ws = tuple(c.weight for c in convs)
+
+        def build():
+            kmax = max(w.shape[2] for w in ws)
+            Cin = ws[0].shape[1]
+            cp = (Cin + 7) // 8 * 8
+            out = zeros((kmax, sum(w.shape[0] for w in ws), cp), F32, ws[0].device)
+            r = 0
+            for w in ws:
+                k = w.shape[2]
+                o = kmax // 2 - k // 2
+                out[o:o + k, r:r + w.shape[0], :Cin] = w.detach().permute(2, 0, 1)
+                r += w.shape[0]
+            return out.to(BF16)
+        return self._cached(("cross",) + tuple(id(w) for w in ws), ws, build)
+
+    def padded_rows_w(self, w: torch.nn.Parameter, rows: int) -> torch.Tensor:
+        """(N, K[,1]) -> [rows][K] bf16 with zero rows appended (final_conv: N=6 -> 8)."""
+        def build():
+            out = zeros((rows, w.shape[1]), BF16, w.device)
+            out[:w.shape[0]] = w.detach().reshape(w.shape[0], w.shape[1]).to(BF16)
+            return out
+        return self._cached(("padrows", id(w), rows), (w,), build)
+
+    # ---- gradient buffers (fp32, zero-initialised, torch layout) handed back to autograd at the end of backward
+    def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
+        g = self.grads.get(id(p))
+        if g is None:
+            g = zeros(p.shape, F32, p.device)
+            self.grads[id(p)] = g
+        return g
+
+    def set_grad(self, p: torch.nn.Parameter, g: torch.Tensor) -> None:
+        old = self.grads.get(id(p))
+        if old is None:
+            self.grads[id(p)] = g
+        else:
+            old.add_(g)
+
+    def take_grads(self, params):
+        out = [self.grads.get(id(p)) if p.requires_grad else None for p in params]
+        self.grads = {}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ GEMM-shaped layers
+def _wgrad_conv(store: ParamStore, w: torch.nn.Parameter, dy16, x16, taps, shift0):
+    """Conv1d weight gradient: packed [k][Cout][Cin_pad] fp32 accumulation, then back to the (Cout, Cin, k) layout."""
+    if not w.requires_grad:
+        return
+    Cout, Cin, k = w.shape
+    cp = (Cin + 7) // 8 * 8
+    tmp = zeros((k, Cout, cp), F32, w.device)
+    R.gemm_wgrad(dy16, x16, tmp, M=Cout, N_out=cp, taps=taps, shift0=shift0, shift_step=1)
+    g = store.grads.get(id(w))
+    if g is None:
+        g = empty(w.shape, F32, w.device)
+        store.grads[id(w)] = g
+        acc = 0
+    else:
+        acc = 1
+    N.call("of_unpack_conv_wgrad", _p(tmp), Cout, Cin, k, cp, 0, _p(g), acc)
+
+
+def _wgrad_linear(store: ParamStore, w: torch.nn.Parameter, dy16, x16, row0: int = 0, rows: Optional[int] = None):
+    """Linear / 1x1-conv weight gradient accumulated atomically straight into the (N, K) fp32 grad buffer."""
+    if not w.requires_grad:
+        return
+    g = store.grad(w)
+    Nn = w.shape[0] if rows is None else rows
+    K = w.shape[1]
+    R.gemm_wgrad(dy16, x16, g.view(1, w.shape[0], K)[:, row0:row0 + Nn], M=Nn, N_out=K)
+
+
+def _bias_grad(store: ParamStore, b: Optional[torch.nn.Parameter], dy16) -> None:
+    if b is not None and b.requires_grad:
+        colsum(dy16, store.grad(b))
+
+
+def _dgrad_into(x: Act, dy16, wpack, *, N_out, K, taps=1, shift0=0, shift_step=0, b_ld=None, want_bf16=False,
+                want_f32=True):
+    """x.grad (+)= dY * W^T.  The GEMM epilogue adds the already-accumulated gradient (aux) and writes in place."""
+    B, L = dy16.shape[0], dy16.shape[1]
+    prev = x.grad
+    out = None
+    if want_f32:
+        out = prev if prev is not None else empty((B, L, N_out), F32, dy16.device)
+    o16 = empty((B, L, N_out), BF16, dy16.device) if want_bf16 else None
+    R.gemm_fwd(dy16, wpack, N_out=N_out, K=K, taps=taps, shift0=shift0, shift_step=shift_step, b_mn_major=True,
+               b_ld=b_ld, aux_f32=prev, out_f32=out, out_bf16=o16)
+    x.grad = out
+    return o16
+
+
+class Ctx:
+    """Per-forward context: device, tape (None = inference), parameter store, conditioning vector."""
+
+    def __init__(self, device, store: ParamStore, tape: Optional[Tape]) -> None:
+        self.device, self.store, self.tape = device, store, tape
+        self.emb_act = None      # (B, 2*dim_emb) fp32 = SiLU(cat(t, c))  (shared input of every FiLM head)
+        self.d_emb_act = None    # its gradient accumulator
+        self.rope_cache = {}
+        self.attn_variant = 0
+
+
+def conv3(ctx: Ctx, x16, conv, *, stats=None, out=None):
+    """nn.Conv1d(k=3, padding=1) as implicit GEMM; returns bf16 (B, L, Cout)."""
+    B, L, _ = x16.shape
+    Cout, Cin, k = conv.weight.shape
+    w = ctx.store.conv_w(conv.weight)
+    y = out if out is not None else empty((B, L, Cout), BF16, ctx.device)
+    R.gemm_fwd(x16, w, N_out=Cout, K=w.shape[2], taps=k, shift0=-(k // 2), shift_step=1, bias=conv.bias, out_bf16=y, stats=stats)
+    return y
+
+
+def conv3_bwd(ctx: Ctx, conv, x: Act, x16, dy16, need_dx=True, want_bf16=False, want_f32=True):
+    Cout, Cin, k = conv.weight.shape
+    _wgrad_conv(ctx.store, conv.weight, dy16, x16, taps=k, shift0=-(k // 2))
+    if need_dx:
+        w = ctx.store.conv_w(conv.weight)
+        return _dgrad_into(x, dy16, w, N_out=Cin, K=Cout, taps=k, shift0=k // 2, shift_step=-1, b_ld=w.shape[2],
+                           want_bf16=want_bf16, want_f32=want_f32)
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ ResidualBlock
+def _rb_args(B, L, Cc, y, stats, norm, ss):
+    a = N.RbArgs()
+    a.B, a.L, a.C, a.eps = B, L, Cc, norm.eps
+    a.y = y.data_ptr()
+    a.y_bs, a.y_ld = _bl(y)
+    a.stats = stats.data_ptr()
+    a.gamma, a.beta = norm.weight.data_ptr(), norm.bias.data_ptr()
+    a.ss = _p(ss)
+    return a
+
+
+def residual_block(ctx: Ctx, m, x: Act) -> Act:
+    """ResidualBlock.forward (reference residual.py:118-137)."""
+    st, dev = ctx.store, ctx.device
+    x16 = x.bf16
+    B, L, Cin = x16.shape
+    Cout = m.block1.proj.weight.shape[0]
+    ss = None
+    if m.mlp is not None:
+        ss, _ = linear_small_fwd(ctx.emb_act, m.mlp[1].weight, m.mlp[1].bias)
+    stats1 = zeros((B, 2), F64, dev)
+    y1 = conv3(ctx, x16, m.block1.proj, stats=stats1)
+    a1 = _rb_args(B, L, Cout, y1, stats1, m.block1.norm, ss)
+    h1 = empty((B, L, Cout), BF16, dev)
+    a1.out_bf16 = h1.data_ptr()
+    a1.out_bf16_bs, a1.out_bf16_ld = _bl(h1)
+    N.call("of_rb_apply_fwd", C.byref(a1))
+    stats2 = zeros((B, 2), F64, dev)
+    y2 = conv3(ctx, h1, m.block2.proj, stats=stats2)
+    # GlobalContext: logits -> softmax over L -> pooled -> 2-layer gate MLP
+    se = m.se
+    wk = se.to_k.weight.view(-1)
+    a2 = _rb_args(B, L, Cout, y2, stats2, m.block2.norm, None)
+    p = empty((B, L), F32, dev)
+    a2.mode = 0
+    a2.vec, a2.vec_bs, a2.vec_bias = wk.data_ptr(), 0, se.to_k.bias.data_ptr()
+    a2.out_rows = p.data_ptr()
+    N.call("of_rb_rowdot", C.byref(a2))
+    N.call("of_softmax_rows", _p(p), B, L)
+    pooled = zeros((B, Cout), F32, dev)
+    a2.p, a2.acc_bc = p.data_ptr(), pooled.data_ptr()
+    N.call("of_rb_pool", C.byref(a2))
+    Wa, Wb = se.layers[0].weight, se.layers[2].weight
+    g1, g1pre = linear_small_fwd(pooled, Wa.view(Wa.shape[0], -1), se.layers[0].bias, act=1, want_pre=True)
+    gate, gatepre = linear_small_fwd(g1, Wb.view(Wb.shape[0], -1), se.layers[2].bias, act=2, want_pre=True)
+    # residual branch
+    has_res = not isinstance(m.res_conv, torch.nn.Identity)
+    out32 = empty((B, L, Cout), F32, dev)
+    out16 = empty((B, L, Cout), BF16, dev)
+    a2.gate = gate.data_ptr()
+    if has_res:
+        wres = st.linear_w(m.res_conv.weight)
+        r16 = empty((B, L, Cout), BF16, dev)
+        R.gemm_fwd(x16, wres, N_out=Cout, K=Cin, bias=m.res_conv.bias, out_bf16=r16)
+        a2.res_bf16 = r16.data_ptr()
+        a2.res_bf16_bs, a2.res_bf16_ld = _bl(r16)
+    elif x.f32 is not None:
+        a2.res_f32 = x.f32.data_ptr()
+        a2.res_f32_bs, a2.res_f32_ld = _bl(x.f32)
+    else:
+        a2.res_bf16 = x16.data_ptr()
+        a2.res_bf16_bs, a2.res_bf16_ld = _bl(x16)
+    a2.out_f32 = out32.data_ptr()
+    a2.out_f32_bs, a2.out_f32_ld = _bl(out32)
+    a2.out_bf16 = out16.data_ptr()
+    a2.out_bf16_bs, a2.out_bf16_ld = _bl(out16)
+    N.call("of_rb_gate_fwd", C.byref(a2))
+    out = Act(out32, out16)
+
+    if ctx.tape is not None:
+        def backward():
+            dout = out.grad
+            out.grad = None
+            d_bs, d_ld = _bl(dout)
+            b2 = _rb_args(B, L, Cout, y2, stats2, m.block2.norm, None)
+            b2.dout_f32 = dout.data_ptr()
+            b2.dout_f32_bs, b2.dout_f32_ld = d_bs, d_ld
+            dgate = zeros((B, Cout), F32, dev)
+            b2.acc_bc = dgate.data_ptr()
+            N.call("of_rb_gate_bwd_reduce", C.byref(b2))
+            # gate MLP backward
+            dg1 = zeros((B, Wa.shape[0]), F32, dev)
+            linear_small_bwd(dgate, gatepre, 2, g1, Wb.view(Wb.shape[0], -1), st.grad(Wb), st.grad(se.layers[2].bias), dg1)
+            dpooled = zeros((B, Cout), F32, dev)
+            linear_small_bwd(dg1, g1pre, 1, pooled, Wa.view(Wa.shape[0], -1), st.grad(Wa), st.grad(se.layers[0].bias), dpooled)
+            # d logits
+            da = empty((B, L), F32, dev)
+            b2.mode = 1
+            b2.vec, b2.vec_bs = dpooled.data_ptr(), Cout
+            b2.p, b2.pooled, b2.out_rows = p.data_ptr(), pooled.data_ptr(), da.data_ptr()
+            N.call("of_rb_rowdot", C.byref(b2))
+            # GroupNorm-2 backward, pass 1
+            dxh = empty((B, L, Cout), BF16, dev)
+            dstats = zeros((B, 2), F64, dev)
+            b2.mode = 0
+            b2.gate, b2.dpooled, b2.da, b2.wk = gate.data_ptr(), dpooled.data_ptr(), da.data_ptr(), wk.data_ptr()
+            b2.dstats = dstats.data_ptr()
+            b2.dgamma, b2.dbeta = st.grad(m.block2.norm.weight).data_ptr(), st.grad(m.block2.norm.bias).data_ptr()
+            b2.dwk, b2.dbk = st.grad(se.to_k.weight).data_ptr(), st.grad(se.to_k.bias).data_ptr()
+            b2.dxhat_bf16 = dxh.data_ptr()
+            b2.dxhat_bs, b2.dxhat_ld = _bl(dxh)
+            dout16 = None
+            if has_res:
+                dout16 = empty((B, L, Cout), BF16, dev)
+                b2.dout_bf16 = dout16.data_ptr()
+                b2.dout_bf16_bs, b2.dout_bf16_ld = _bl(dout16)
+            N.call("of_rb_bwd_pass1", C.byref(b2))
+            dy2 = empty((B, L, Cout), BF16, dev)
+            b2.dy_bf16 = dy2.data_ptr()
+            b2.dy_bs, b2.dy_ld = _bl(dy2)
+            b2.dbias = st.grad(m.block2.proj.bias).data_ptr()
+            N.call("of_rb_bwd_apply", C.byref(b2))
+            # conv2 backward
+            h1a = Act(None, h1)
+            dh1 = conv3_bwd(ctx, m.block2.proj, h1a, h1, dy2, want_bf16=True, want_f32=False)
+            # GroupNorm-1 (+FiLM) backward
+            b1 = _rb_args(B, L, Cout, y1, stats1, m.block1.norm, ss)
+            b1.mode = 1
+            b1.dh_bf16 = dh1.data_ptr()
+            b1.dh_bs, b1.dh_ld = _bl(dh1)
+            dxh1 = dxh  # reuse
+            dstats1 = zeros((B, 2), F64, dev)
+            b1.dstats = dstats1.data_ptr()
+            b1.dgamma, b1.dbeta = st.grad(m.block1.norm.weight).data_ptr(), st.grad(m.block1.norm.bias).data_ptr()
+            dss = None
+            if ss is not None:
+                dss = zeros((B, 2 * Cout), F32, dev)
+                b1.dss = dss.data_ptr()
+            b1.dxhat_bf16 = dxh1.data_ptr()
+            b1.dxhat_bs, b1.dxhat_ld = _bl(dxh1)
+            N.call("of_rb_bwd_pass1", C.byref(b1))
+            dy1 = dy2  # reuse
+            b1.dy_bf16 = dy1.data_ptr()
+            b1.dy_bs, b1.dy_ld = _bl(dy1)
+            b1.dbias = st.grad(m.block1.proj.bias).data_ptr()
+            N.call("of_rb_bwd_apply", C.byref(b1))
+            # input gradient: identity residual (adopt dout) or res_conv dgrad, then conv1 dgrad accumulated in place
+            if has_res:
+                _wgrad_linear(st, m.res_conv.weight, dout16, x16)
+                _bias_grad(st, m.res_conv.bias, dout16)
+                _dgrad_into(x, dout16, st.linear_w(m.res_conv.weight), N_out=Cin, K=Cout)
+            else:
+                x.add_grad(dout)
+            conv3_bwd(ctx, m.block1.proj, x, x16, dy1)
+            if ss is not None:
+                W = m.mlp[1].weight
+                linear_small_bwd(dss, None, 0, ctx.emb_act, W, st.grad(W), st.grad(m.mlp[1].bias), ctx.d_emb_act)
+        ctx.tape.push(backward)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ TransformerBlock
+def rope_tables(ctx: Ctx, L: int, D: int, scale_base: int):
+    """cos/sin (L, D) bf16 generated exactly like attention.py:33-49 does under bf16 autocast (tables in q's dtype)."""
+    key = (L, D, scale_base)
+    hit = ctx.rope_cache.get(key)
+    if hit is None:
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, D, 2, device=ctx.device).float() / D))
+        t = torch.arange(L, dtype=BF16, device=ctx.device)
+        t *= scale_base / L
+        freqs = torch.einsum("i,j->ij", t, inv_freq.to(BF16))
+        emb = torch.cat([freqs, freqs], dim=-1)
+        hit = (emb.cos().contiguous(), emb.sin().contiguous())
+        ctx.rope_cache[key] = hit
+    return hit
+
+
+def transformer_block(ctx: Ctx, m, x: Act) -> Act:
+    """TransformerBlock.forward (reference unet.py:179-183) = Attention.forward_body (unet.py:125-141) + FeedForward."""
+    st, dev = ctx.store, ctx.device
+    at = m.attn
+    B, L, Cc = x.f32.shape
+    H, KVH, D = at.heads, at.kv_heads, at.dim_head
+    HD, KD = H * D, KVH * D
+    rows = B * L
+    x32 = x.f32
+    assert x32.stride(0) == L * x32.stride(1)
+    xn32 = empty((B, L, Cc), F32, dev)
+    xn16 = empty((B, L, Cc), BF16, dev)
+    mr = empty((rows, 2), F32, dev)
+    N.call("of_layernorm_fwd", _p(x32), x32.stride(1), rows, Cc, _p(at.norm.weight), _p(at.norm.bias), at.norm.eps,
+           _p(xn32), _p(xn16), Cc, _p(mr))
+    wqkv = st.linear_w(at.to_q.weight, at.to_kv.weight)
+    qkv = empty((B, L, HD + 2 * KD), BF16, dev)
+    R.gemm_fwd(xn16, wqkv, N_out=HD + 2 * KD, K=Cc, out_bf16=qkv)
+    cosT, sinT = rope_tables(ctx, L, D, at.rotary_emb.scale_base)
+    q_bs, q_ld = _bl(qkv)
+    N.call("of_rope_fwd", _p(qkv), q_ld, q_bs, B, L, H, KVH, D, _p(cosT), _p(sinT))
+    q, k, v = qkv[:, :, :HD], qkv[:, :, HD:HD + KD], qkv[:, :, HD + KD:]
+    o16 = empty((B, L, HD), BF16, dev)
+    lse = empty((B, H, L), F32, dev)
+    R.attn_fwd(q, k, v, o16, lse, H=H, KVH=KVH, D=D, variant=ctx.attn_variant)
+    wout = st.linear_w(at.to_out.weight)
+    x2_32 = empty((B, L, Cc), F32, dev)
+    x2_16 = empty((B, L, Cc), BF16, dev)
+    R.gemm_fwd(o16, wout, N_out=Cc, K=HD, bias=at.to_out.bias, aux_f32=xn32, out_f32=x2_32, out_bf16=x2_16)
+    ff1, ff2 = m.ff[0], m.ff[2]
+    Ci = ff1.weight.shape[0]
+    w1, w2 = st.linear_w(ff1.weight), st.linear_w(ff2.weight)
+    u16 = empty((B, L, Ci), BF16, dev) if ctx.tape is not None else None
+    s16 = empty((B, L, Ci), BF16, dev)
+    R.gemm_fwd(x2_16, w1, N_out=Ci, K=Cc, bias=ff1.bias, act=R.ACT_SILU, pre_bf16=u16, out_bf16=s16)
+    out32 = empty((B, L, Cc), F32, dev)
+    out16 = empty((B, L, Cc), BF16, dev)
+    R.gemm_fwd(s16, w2, N_out=Cc, K=Ci, bias=ff2.bias, aux_f32=x2_32, out_f32=out32, out_bf16=out16)
+    out = Act(out32, out16)
+
+    if ctx.tape is not None:
+        def backward():
+            dout = out.grad
+            out.grad = None
+            dout16 = empty((B, L, Cc), BF16, dev)
+            cast_copy(dout, dout16)
+            # FeedForward
+            dU = empty((B, L, Ci), BF16, dev)
+            R.gemm_fwd(dout16, w2, N_out=Ci, K=Cc, b_mn_major=True, aux_bf16=u16, aux_is_dsilu=True, out_bf16=dU)
+            _wgrad_linear(st, ff2.weight, dout16, s16)
+            _bias_grad(st, ff2.bias, dout16)
+            x2 = Act(None, None)
+            x2.grad = dout  # residual `ff(x) + x`
+            dx2_16 = _dgrad_into(x2, dU, w1, N_out=Cc, K=Ci, want_bf16=True)
+            _wgrad_linear(st, ff1.weight, dU, x2_16)
+            _bias_grad(st, ff1.bias, dU)
+            # to_out
+            dO = empty((B, L, HD), BF16, dev)
+            R.gemm_fwd(dx2_16, wout, N_out=HD, K=Cc, b_mn_major=True, out_bf16=dO)
+            _wgrad_linear(st, at.to_out.weight, dx2_16, o16)
+            _bias_grad(st, at.to_out.bias, dx2_16)
+            # attention core
+            delta = empty((B, H, L), F32, dev)
+            dq = zeros((B, L, HD), F32, dev)
+            dkv = zeros((B, L, 2 * KD), F32, dev)
+            R.attn_bwd(q, k, v, o16, lse, dO, delta, dq, dkv[:, :, :KD], dkv[:, :, KD:], H=H, KVH=KVH, D=D)
+            dqkv = empty((B, L, HD + 2 * KD), BF16, dev)
+            dq_bs, dq_ld = _bl(dq)
+            dkv_bs, dkv_ld = _bl(dkv)
+            o_bs, o_ld = _bl(dqkv)
+            N.call("of_rope_bwd", _p(dq), dq_ld, dq_bs, dkv[:, :, :KD].data_ptr(), dkv[:, :, KD:].data_ptr(), dkv_ld, dkv_bs,
+                   _p(dqkv), o_ld, o_bs, B, L, H, KVH, D, _p(cosT), _p(sinT))
+            # q/kv projections: d(xn) = residual grad (x2.grad) + dqkv W
+            _dgrad_into(x2, dqkv, wqkv, N_out=Cc, K=HD + 2 * KD)
+            _wgrad_linear(st, at.to_q.weight, dqkv[:, :, :HD], xn16)
+            _wgrad_linear(st, at.to_kv.weight, dqkv[:, :, HD:], xn16)
+            # LayerNorm
+            dxn = x2.grad
+            assert dxn.stride(0) == L * dxn.stride(1)
+            dx = empty((B, L, Cc), F32, dev)
+            N.call("of_layernorm_bwd", _p(dxn), dxn.stride(1), _p(x32), x32.stride(1), rows, Cc, _p(at.norm.weight), _p(mr),
+                   _p(dx), None, Cc, st.grad(at.norm.weight).data_ptr(), st.grad(at.norm.bias).data_ptr())
+            x.add_grad(dx)
+        ctx.tape.push(backward)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ samplers
+def downsample(ctx: Ctx, m, x: Act) -> Act:
+    """Downsample (unet.py:77-92): reflect-pad right by 1, conv k=3 stride 2 — as a 2-tap conv over the (B, L/2, 2C) view
+    plus a one-row fix-up for the reflected sample."""
+    st, dev = ctx.store, ctx.device
+    conv = m.conv
+    x16 = x.bf16
+    B, L, Cin = x16.shape
+    assert L % 2 == 0 and x16.is_contiguous()
+    Cout = conv.weight.shape[0]
+    Lh = L // 2
+    w = st.down_w(conv.weight)                       # [2][Cout][2Cin]
+    xv = x16.view(B, Lh, 2 * Cin)
+    y = empty((B, Lh, Cout), BF16, dev)
+    R.gemm_fwd(xv, w, N_out=Cout, K=2 * Cin, taps=2, shift0=0, shift_step=1, bias=conv.bias, out_bf16=y)
+    # reflect: x_pad[L] = x[L-2]  ->  y[Lh-1] += W2 x[L-2]
+    xrow = x16[:, L - 2:L - 1, :]
+    ylast = y[:, Lh - 1:Lh, :]
+    R.gemm_fwd(xrow, w[1], N_out=Cout, K=Cin, b_ld=2 * Cin, aux_bf16=ylast, out_bf16=ylast)
+    out = Act(None, y)
+
+    if ctx.tape is not None:
+        def backward():
+            dy = out.grad
+            out.grad = None
+            dy16 = empty((B, Lh, Cout), BF16, dev)
+            cast_copy(dy, dy16)
+            _bias_grad(st, conv.bias, dy16)
+            if conv.weight.requires_grad:
+                tmp = zeros((2, Cout, 2 * Cin), F32, dev)
+                R.gemm_wgrad(dy16, xv, tmp, M=Cout, N_out=2 * Cin, taps=2, shift0=0, shift_step=1)
+                R.gemm_wgrad(dy16[:, Lh - 1:Lh, :], xrow, tmp[1:2, :, :Cin], M=Cout, N_out=Cin)
+                g = torch.stack([tmp[0, :, :Cin], tmp[0, :, Cin:], tmp[1, :, :Cin]], dim=2)
+                st.set_grad(conv.weight, g)
+            # dgrad over the (B, Lh, 2Cin) view, then the reflected row
+            if x.grad is None:
+                x.grad = empty((B, L, Cin), F32, dev)
+                prev = None
+            else:
+                if not x.grad.is_contiguous():
+                    t = empty((B, L, Cin), F32, dev)
+                    cast_copy(x.grad, t)
+                    x.grad = t
+                prev = x.grad.view(B, Lh, 2 * Cin)
+            gv = x.grad.view(B, Lh, 2 * Cin)
+            R.gemm_fwd(dy16, w, N_out=2 * Cin, K=Cout, taps=2, shift0=0, shift_step=-1, b_mn_major=True, b_ld=2 * Cin,
+                       aux_f32=prev, out_f32=gv)
+            grow = x.grad[:, L - 2:L - 1, :]
+            R.gemm_fwd(dy16[:, Lh - 1:Lh, :], w[1], N_out=Cin, K=Cout, b_mn_major=True, b_ld=2 * Cin, aux_f32=grow, out_f32=grow)
+        ctx.tape.push(backward)
+    return out
+
+
+def upsample(ctx: Ctx, m, x: Act) -> Act:
+    """Upsample (unet.py:61-74): nearest x2 then conv k=3."""
+    st, dev = ctx.store, ctx.device
+    conv = m.conv
+    x16 = x.bf16
+    B, L, Cin = x16.shape
+    up = empty((B, 2 * L, Cin), BF16, dev)
+    xb, xl = _bl(x16)
+    N.call("of_upsample2x_fwd", _p(x16), xl, xb, B, L, Cin, _p(up), Cin, 2 * L * Cin)
+    y = conv3(ctx, up, conv)
+    out = Act(None, y)
+
+    if ctx.tape is not None:
+        def backward():
+            dy = out.grad
+            out.grad = None
+            dy16 = empty(y.shape, BF16, dev)
+            cast_copy(dy, dy16)
+            _bias_grad(st, conv.bias, dy16)
+            upa = Act(None, up)
+            conv3_bwd(ctx, conv, upa, up, dy16)
+            d = upa.grad
+            dx = empty((B, L, Cin), F32, dev)
+            N.call("of_upsample2x_bwd", _p(d), Cin, 2 * L * Cin, B, L, Cin, _p(dx), None, Cin, L * Cin)
+            x.add_grad(dx)
+        ctx.tape.push(backward)
+    return out
+
+
+def parallel_sampler(ctx: Ctx, m, x: Act) -> Act:
+    """Parallel(conv3, conv1) (unet.py:95-101,225-236): bf16 sum of the two bf16 conv outputs."""
+    st, dev = ctx.store, ctx.device
+    c3, c1 = m.fns[0], m.fns[1]
+    x16 = x.bf16
+    B, L, Cin = x16.shape
+    Cout = c3.weight.shape[0]
+    y3 = conv3(ctx, x16, c3)
+    w1 = st.linear_w(c1.weight)
+    y = empty((B, L, Cout), BF16, dev)
+    R.gemm_fwd(x16, w1, N_out=Cout, K=Cin, bias=c1.bias, aux_bf16=y3, out_bf16=y)
+    out = Act(None, y)
+
+    if ctx.tape is not None:
+        def backward():
+            dy = out.grad
+            out.grad = None
+            dy16 = empty(y.shape, BF16, dev)
+            cast_copy(dy, dy16)
+            _bias_grad(st, c3.bias, dy16)
+            _bias_grad(st, c1.bias, dy16)
+            _wgrad_linear(st, c1.weight, dy16, x16)
+            _dgrad_into(x, dy16, w1, N_out=Cin, K=Cout)
+            conv3_bwd(ctx, c3, x, x16, dy16)
+        ctx.tape.push(backward)
+    return out
+
+
+def cross_embed(ctx: Ctx, m, x16: torch.Tensor) -> Act:
+    """CrossEmbedLayer (unet.py:42-58): the three branches as one zero-padded k=15 implicit GEMM."""
+    st, dev = ctx.store, ctx.device
+    B, L, Cp = x16.shape
+    w = st.cross_w(m.convs)
+    kmax, Cout = w.shape[0], w.shape[1]
+    bias = torch.cat([c.bias.detach() for c in m.convs])
+    y = empty((B, L, Cout), BF16, dev)
+    R.gemm_fwd(x16, w, N_out=Cout, K=Cp, taps=kmax, shift0=-(kmax // 2), shift_step=1, bias=bias, out_bf16=y)
+    out = Act(None, y)
+
+    if ctx.tape is not None:
+        def backward():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            dy16 = empty(y.shape, BF16, dev)
+            cast_copy(dy, dy16)
+            tmp = zeros((kmax, Cout, Cp), F32, dev)
+            R.gemm_wgrad(dy16, x16, tmp, M=Cout, N_out=Cp, taps=kmax, shift0=-(kmax // 2), shift_step=1)
+            db = zeros((Cout,), F32, dev)
+            colsum(dy16, db)
+            r = 0
+            for c in m.convs:
+                co, ci, k = c.weight.shape
+                o = kmax // 2 - k // 2
+                if c.weight.requires_grad:
+                    st.set_grad(c.weight, tmp[o:o + k, r:r + co, :ci].permute(1, 2, 0).contiguous())
+                    st.set_grad(c.bias, db[r:r + co].clone())
+                r += co
+        ctx.tape.push(backward)
+    return out
+
+
+def concat(ctx: Ctx, a: Act, b: Act) -> Act:
+    """torch.cat([a, b], dim=channels) on the bf16 operand copies (both consumers of a concat are GEMMs)."""
+    dev = ctx.device
+    B, L, Ca = a.bf16.shape
+    Cb = b.bf16.shape[2]
+    wide = empty((B, L, Ca + Cb), BF16, dev)
+    cast_copy(a.bf16, wide[:, :, :Ca])
+    cast_copy(b.bf16, wide[:, :, Ca:])
+    out = Act(None, wide)
+
+    if ctx.tape is not None:
+        def backward():
+            g = out.grad
+            out.grad = None
+            a.add_grad(g[:, :, :Ca])
+            b.add_grad(g[:, :, Ca:])
+        ctx.tape.push(backward)
+    return out
+
+
+def unet_block(ctx: Ctx, m, x: Act):
+    """UNetBlock.forward_body (unet.py:240-252): returns (sampler(x), x)."""
+    x = residual_block(ctx, m.init_resnet, x)
+    for res, tr in zip(m.resnets, m.transformers):
+        x = residual_block(ctx, res, x)
+        x = transformer_block(ctx, tr, x)
+    kind = m.sampler_kind
+    if kind == "down":
+        y = downsample(ctx, m.sampler, x)
+    elif kind == "up":
+        y = upsample(ctx, m.sampler, x)
+    else:
+        y = parallel_sampler(ctx, m.sampler, x)
+    return y, x
