@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py — denoiser fwd+bwd samples/s on N B200 (BASELINE.json configs[1..2]): one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size L|S] [--batch B] [--frames N]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU, NCCL)
+
+A "step" = one training micro-step of the reference trainer (trainer.py:295-301): noise + timestep draw, add_noise,
+denoiser forward (cond_drop_prob 0.5), masked-MSE loss, full backward to all 1239 parameter gradients (+ gradient
+all-reduce when N > 1).  The optimizer is excluded (SURVEY.md §8d metric 1).  Default workload: CFG-L (dim_h=512,
+1.28 B params), per-GPU batch 4, 4096 frames, bf16 compute / fp32 master weights — the trainer defaults.
+
+--impl reference: the reference's own CPU implementation of the same step (the oracle port, proven bit-identical to
+/root/reference on CPU), fp32, all host threads, on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SIZES = {"L": 512, "S": 128}
+# algorithmic forward FLOPs per sample at N=4096: 3x for fwd+bwd
+FWD_TFLOP = {"L": 2.500, "S": 0.974}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops_sustained", 1394.6), d.get("hbm_gbs", 6551.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self) -> None:
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self) -> None:
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def synth_batch(batch: int, frames: int, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 6, frames, generator=g)
+    a = torch.randn(batch, 96, frames, generator=g)
+    c = torch.randn(batch, 5, generator=g)
+    return x, a, c
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference / baseline
+def cpu_reference_step_time(size: str, frames: int, steps: int, warmup: int):
+    """Oracle (port of the reference) fwd+bwd on the host cores, fp32 (mode M2), batch 1."""
+    from oracle.models import DiffusionOsuFusion as OracleModel
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = OracleModel(SIZES[size])
+    torch.nn.init.normal_(model.unet.final_conv.weight, std=0.02)
+    x, a, c = synth_batch(1, frames, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        loss = model(x, a, c)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), cores, float(loss)
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = args.ref_frames
+    sec, cores, loss = cpu_reference_step_time(args.size, frames, args.steps, min(args.warmup, 1))
+    value = 1.0 / sec
+    sample = f"batch 1 x {frames} frames per step (workload: batch {args.batch} x {args.frames} frames per GPU), fp32, oracle port of the reference"
+    line = {
+        "impl": "reference", "metric": "denoiser fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CFG-{args.size} dim_h={SIZES[args.size]} denoiser train micro-step (fwd+bwd), cond_drop_prob=0.5",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args) -> None:
+    import torch.distributed as dist
+
+    from osufusion_b200 import _native as NN
+    from osufusion_b200 import ops_raw as R
+    from osufusion_b200.graphs import GraphedTrainStep
+    from osufusion_b200.models import DiffusionOsuFusion
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, n, size = args.batch, args.frames, args.size
+    torch.manual_seed(0)
+    model = DiffusionOsuFusion(SIZES[size]).to(dev)
+    torch.nn.init.normal_(model.unet.final_conv.weight, std=0.02)
+    sync = None
+    if world > 1:
+        from osufusion_b200.ddp import GradAllReducer
+        sync = GradAllReducer(model)
+    x, a, c = synth_batch(B, n, 1234 + rank)
+    hx, ha, hc = x.pin_memory(), a.pin_memory(), c.pin_memory()
+    dx, da, dc = hx.to(dev), ha.to(dev), hc.to(dev)
+
+    NN.lib().of_reset_launch_count()
+    step = GraphedTrainStep(model, dx, da, dc, warmup=2, post_backward=(sync.all_reduce if sync else None))
+    launches_per_step = NN.lib().of_launch_count() // 3   # 2 warm-up steps + 1 captured step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    value = B * world / (ms * 1e-3)
+
+    # ---- end-to-end: host buffers in pinned memory -> H2D -> step -> D2H of the loss, every step
+    hloss = torch.empty(1).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(hx, ha, hc)                       # copies into the graph's static inputs, then replays
+        hloss.copy_(step.loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t)
+    e2e_value = B * world / (e2e_ms * 1e-3)
+    h2d = hx.numel() * 4 + ha.numel() * 4 + hc.numel() * 4
+
+    # ---- roofline of the dominant kernel family: one instrumented eager step with CUDA events around every launch
+    roof = None
+    if rank == 0:
+        tf_peak, hbm_peak, how = peaks()
+        del loss
+        model.zero_grad(set_to_none=True)
+        NN.PROFILE = []
+        l2 = model(dx, da, dc)
+        l2.backward()
+        torch.cuda.synchronize()
+        agg = {}
+        for name, flops, ev0, ev1 in NN.PROFILE:
+            d = agg.setdefault(name, [0.0, 0.0, 0])
+            d[0] += ev0.elapsed_time(ev1)
+            d[1] += flops
+            d[2] += 1
+        NN.PROFILE = None
+        del l2
+        top = max(agg.items(), key=lambda kv: kv[1][0])
+        name, (tms, fl, cnt) = top
+        ach = fl / (tms * 1e-3) / 1e12
+        roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "traffic": None, "launches": cnt, "ms_per_step": tms, "peak_source": how + " (bf16_tflops_sustained)",
+                "families_ms": {k: round(v[0], 3) for k, v in agg.items()},
+                "families_tflops": {k: round(v[1] / (v[0] * 1e-3) / 1e12, 1) for k, v in agg.items() if v[0] > 0}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores, _ = cpu_reference_step_time(size, args.ref_frames, 1, 0)
+        cpu = {"value": 1.0 / sec, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"1 step of batch 1 x {args.ref_frames} frames, fp32 oracle port on the host CPU ({sec:.1f} s)"}
+
+    if rank == 0:
+        tf_peak, _, _ = peaks()
+        step_tflop = 3 * FWD_TFLOP[size] * (n / 4096.0) * B   # linear-in-N approximation is exact only at N=4096
+        line = {
+            "metric": "denoiser fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"CFG-{size} dim_h={SIZES[size]} denoiser train micro-step (fwd+bwd, all grads), cond_drop_prob=0.5",
+                       "per_gpu_batch": B, "global_batch": B * world, "frames": n, "parallelism": f"dp{world}",
+                       "l2": "working set (2.6 GB bf16 weights + activations) >> 126 MB L2; no explicit flush",
+                       "cuda_graph": True},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "model_tflops_per_gpu": step_tflop / (ms * 1e-3), "mfu_vs_measured_peak": step_tflop / (ms * 1e-3) / tf_peak,
+            "roofline": roof, "cpu_baseline": cpu, "loss": float(step.loss),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="L", choices=["L", "S"])
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--frames", type=int, default=4096)
+    ap.add_argument("--ref-frames", type=int, default=1024, help="frames of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

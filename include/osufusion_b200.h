@@ -138,9 +138,9 @@ int of_attn_bwd(const of_attn_args* args, void* stream);
  *
  *   of_rb_apply_fwd       out_bf16 = h                                   (block1: input of the second conv)
  *   of_rb_rowdot          mode 0: out_rows[b,l] = bf16r( sum_c bf16r(h)*bf16r(vec[c]) + vec_bias )     (to_k logits)
- *                         mode 1: out_rows[b,l] = p[b,l] * ( sum_c bf16r(h)*vec[b,c] - sum_c vec[b,c]*pooled[b,c] )
- *                                 (= d logits, with vec = d pooled)
- *   of_softmax_rows       p[b,:] = bf16r(softmax_L(logits[b,:]))          in place on out_rows
+ *                         mode 1: out_rows[b,l] = sum_c bf16r(h)*vec[b,c]      (= d p, with vec = d pooled)
+ *   of_softmax_rows       p[b,:] = softmax_L(logits[b,:]) in place, fp32 (consumers round to bf16 like the autocast einsum)
+ *   of_softmax_bwd_rows   rd[b,:] <- p * (rd - sum_l p*rd)                 (softmax backward -> d logits)
  *   of_rb_pool            acc_bc[b,c] += sum_l bf16r(h[b,l,c]) * p[b,l]
  *   of_rb_gate_fwd        out = h * gate[b,c] + res   -> out_f32 and/or out_bf16
  *   of_rb_gate_bwd_reduce acc_bc[b,c] += sum_l dout_f32[b,l,c] * h[b,l,c]                              (d gate)
@@ -194,6 +194,7 @@ int of_rb_gate_bwd_reduce(const of_rb_args* a, void* stream);
 int of_rb_bwd_pass1(const of_rb_args* a, void* stream);
 int of_rb_bwd_apply(const of_rb_args* a, void* stream);
 int of_softmax_rows(float* rows, int B, int L, void* stream);
+int of_softmax_bwd_rows(const float* p, float* rd, int B, int L, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Transformer-block and glue kernels.

@@ -89,6 +89,7 @@ _SIGS = {
     "of_rb_bwd_pass1": [C.POINTER(RbArgs), P],
     "of_rb_bwd_apply": [C.POINTER(RbArgs), P],
     "of_softmax_rows": [P, I, I, P],
+    "of_softmax_bwd_rows": [P, P, I, I, P],
     "of_layernorm_fwd": [P, LL, I, I, P, P, F, P, P, LL, P, P],
     "of_layernorm_bwd": [P, LL, P, LL, I, I, P, P, P, P, LL, P, P, P],
     "of_rope_fwd": [P, LL, LL, I, I, I, I, I, P, P, P],
@@ -136,10 +137,22 @@ def check(rc: int, what: str) -> None:
         raise NativeError(f"{what} failed (rc={rc}): {lib().of_last_error().decode()}")
 
 
-def call(name: str, *args) -> None:
+# When set to a list, every entry point is bracketed by CUDA events on the launching stream and
+# (family, algorithmic_flops, start_event, end_event) is appended (bench.py roofline section).
+PROFILE = None
+
+
+def call(name: str, *args, flops: float = 0.0, family: str | None = None) -> None:
     """Invoke an entry point with the current torch CUDA stream appended; raises on a non-zero return."""
     fn = getattr(lib(), name)
-    rc = fn(*args, stream_ptr())
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args, stream_ptr())
+        e1.record()
+        PROFILE.append((family or name, flops, e0, e1))
+    else:
+        rc = fn(*args, stream_ptr())
     if rc != 0:
         raise NativeError(f"{name} failed (rc={rc}): {lib().of_last_error().decode()}")
 

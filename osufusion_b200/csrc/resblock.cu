@@ -106,15 +106,6 @@ __global__ void __launch_bounds__(256) rb_rowdot_kernel(const of_rb_args a) {
   float mean, rstd;
   gn_mean_rstd(g.stats, b, (double)g.L * (double)g.C, g.eps, mean, rstd);
   const float* vec = a.vec + (long long)b * a.vec_bs;
-  float T = 0.f;
-  if (a.mode == 1) {
-    for (int v = lane; v < vecs; v += 32) {
-      V8 d = ld_f32x8(vec + v * 8), pl = ld_f32x8(a.pooled + (long long)b * a.C + v * 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) T += d.v[j] * pl.v[j];
-    }
-    T = warp_sum(T);
-  }
   const float bias = a.vec_bias ? *a.vec_bias : 0.f;
   const int rows_per_cta = 8 * 8;  // 8 warps x 8 rows
   const int l0 = blockIdx.x * rows_per_cta;
@@ -146,13 +137,24 @@ __global__ void __launch_bounds__(256) rb_rowdot_kernel(const of_rb_args a) {
     if (lane == 0) {
       float r;
       if (a.mode == 0) r = bf16_round(acc + bias);
-      else r = a.p[(long long)b * a.L + l] * (acc - T);
+      else r = acc;
       a.out_rows[(long long)b * a.L + l] = r;
     }
   }
 }
 
-// one CTA per sample: p = bf16r(softmax(logits)) in place
+// one CTA per sample: da = p * (rd - sum_l p*rd) in place on rd   (softmax backward with the fp32 probabilities)
+__global__ void __launch_bounds__(1024) softmax_bwd_rows_kernel(const float* __restrict__ p, float* rd, int L) {
+  __shared__ float sm[32];
+  const float* pr = p + (long long)blockIdx.x * L;
+  float* r = rd + (long long)blockIdx.x * L;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s += pr[i] * r[i];
+  s = block_sum(s, sm);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] = pr[i] * (r[i] - s);
+}
+
+// one CTA per sample: p = softmax(logits) in place (fp32; consumers round to bf16 where the reference does)
 __global__ void __launch_bounds__(1024) softmax_rows_kernel(float* rows, int L) {
   __shared__ float sm[32];
   float* r = rows + (long long)blockIdx.x * L;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(1024) softmax_rows_kernel(float* rows, int L) 
   for (int i = threadIdx.x; i < L; i += blockDim.x) s += expf(r[i] - mx);
   s = block_sum(s, sm);
   const float inv = 1.0f / s;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] = bf16_round(expf(r[i] - mx) * inv);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] = expf(r[i] - mx) * inv;
 }
 
 __global__ void __launch_bounds__(kRbThreads) rb_pool_kernel(const of_rb_args a) {
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(kRbThreads) rb_pool_kernel(const of_rb_args a)
   for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
     V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
     gn_eval(k, y, xh, z, f, h);
-    const float pl = a.p[(long long)m.b * a.L + l];
+    const float pl = bf16_round(a.p[(long long)m.b * a.L + l]);  // einsum operand is cast to bf16 (autocast)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += bf16_round(h.v[j]) * pl;
   }
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(kRbThreads) rb_bwd_pass1_kernel(const of_rb_ar
       gn_eval(k, y, xh, z, f, h);
       if (a.mode == 0) {
         V8 d = ld_f32x8(a.dout_f32 + m.b * a.dout_f32_bs + (long long)l * a.dout_f32_ld + m.c0);
-        const float pl = a.p[(long long)m.b * a.L + l];
+        const float pl = bf16_round(a.p[(long long)m.b * a.L + l]);
         const float da = a.da[(long long)m.b * a.L + l];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -356,12 +358,18 @@ extern "C" int of_rb_rowdot(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_rowdot");
   if (rc) return rc;
   OF_REQUIRE(a->vec && a->out_rows, "of_rb_rowdot: null vec/out_rows");
-  if (a->mode == 1) OF_REQUIRE(a->p && a->pooled, "of_rb_rowdot(mode 1): null p/pooled");
   RB_LAUNCH(rb_rowdot_kernel, dim3((a->L + 63) / 64, a->B), 256)
 }
 extern "C" int of_softmax_rows(float* rows, int B, int L, void* stream) {
   OF_REQUIRE(rows && B >= 1 && L >= 1, "of_softmax_rows: bad args");
   softmax_rows_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rows, L);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
+extern "C" int of_softmax_bwd_rows(const float* p, float* rd, int B, int L, void* stream) {
+  OF_REQUIRE(p && rd && B >= 1 && L >= 1, "of_softmax_bwd_rows: bad args");
+  softmax_bwd_rows_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, rd, L);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

@@ -393,6 +393,7 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             b2.vec, b2.vec_bs = dpooled.data_ptr(), Cout
             b2.p, b2.pooled, b2.out_rows = p.data_ptr(), pooled.data_ptr(), da.data_ptr()
             N.call("of_rb_rowdot", C.byref(b2))
+            N.call("of_softmax_bwd_rows", _p(p), _p(da), B, L)
             # GroupNorm-2 backward, pass 1
             dxh = empty((B, L, Cout), BF16, dev)
             dstats = zeros((B, 2), F64, dev)

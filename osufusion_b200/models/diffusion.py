@@ -24,6 +24,13 @@ class DDIMScheduler:
         self.alphas_cumprod = torch.cumprod(1.0 - self.betas, dim=0)
         self.num_inference_steps = None
         self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1, dtype=torch.int64)
+        self._dev_cache = {}
+
+    def alphas_cumprod_on(self, device) -> torch.Tensor:
+        key = str(device)
+        if key not in self._dev_cache:
+            self._dev_cache[key] = self.alphas_cumprod.to(device=device, dtype=torch.float32)
+        return self._dev_cache[key]
 
     def set_timesteps(self, n: int) -> None:
         self.num_inference_steps = n
@@ -70,6 +77,6 @@ class OsuFusion(BaseOsuFusion):
             noise = torch.randn_like(x)
         if timesteps is None:
             timesteps = torch.randint(0, self.scheduler.config.num_train_timesteps, (x.shape[0],), dtype=torch.int64, device=x.device)
-        ac = self.scheduler.alphas_cumprod.to(device=x.device, dtype=torch.float32)[timesteps]
+        ac = self.scheduler.alphas_cumprod_on(x.device)[timesteps]
         ca, cb = (ac ** 0.5).contiguous(), ((1 - ac) ** 0.5).contiguous()
         return self._train_step(x, a, timesteps, c, noise, ca, cb, 0.0, 1.0, orig_len, cond_mask)

@@ -67,7 +67,7 @@ def gemm_fwd(a, b, *, N_out, K, taps=1, shift0=0, shift_step=0, b_mn_major=False
         assert stats.dtype == torch.float64
         g.stats = stats.data_ptr()
     g.block_n = block_n
-    N.check(N.lib().of_gemm(C.byref(g), N.stream_ptr()), "of_gemm")
+    N.call("of_gemm", C.byref(g), flops=2.0 * g.batch * g.rows * N_out * K * taps, family="gemm_kernel (tcgen05 GEMM/conv)")
 
 
 def gemm_wgrad(dy, x, out_f32, *, M, N_out, taps=1, shift0=0, shift_step=0, split_k=0, block_n=0):
@@ -88,7 +88,7 @@ def gemm_wgrad(dy, x, out_f32, *, M, N_out, taps=1, shift0=0, shift_step=0, spli
     g.out_f32_batch_stride, g.out_f32_ld = out_f32.stride(0), out_f32.stride(1)
     g.split_k = split_k
     g.block_n = block_n
-    N.check(N.lib().of_gemm(C.byref(g), N.stream_ptr()), "of_gemm(wgrad)")
+    N.call("of_gemm", C.byref(g), flops=2.0 * g.batch * g.rows * N_out * M * taps, family="gemm_kernel (tcgen05 GEMM/conv)")
 
 
 def _attn_common(q, k, v, H, KVH, D, variant):
@@ -111,7 +111,7 @@ def attn_fwd(q, k, v, out, lse, *, H, KVH, D, variant=0):
     g.out = out.data_ptr()
     g.out_batch_stride, g.out_ld = _bl(out)
     g.lse = N.ptr(lse)
-    N.check(N.lib().of_attn_fwd(C.byref(g), N.stream_ptr()), "of_attn_fwd")
+    N.call("of_attn_fwd", C.byref(g), flops=4.0 * g.B * H * g.L * g.L * D, family="attn_fwd_kernel (tcgen05 MQA flash)")
 
 
 def attn_bwd(q, k, v, out, lse, dout, delta, dq, dk, dv, *, H, KVH, D, variant=0):
@@ -127,4 +127,4 @@ def attn_bwd(q, k, v, out, lse, dout, delta, dq, dk, dv, *, H, KVH, D, variant=0
     g.dk, g.dv = dk.data_ptr(), dv.data_ptr()
     assert _bl(dk) == _bl(dv)
     g.dkv_batch_stride, g.dkv_ld = _bl(dk)
-    N.check(N.lib().of_attn_bwd(C.byref(g), N.stream_ptr()), "of_attn_bwd")
+    N.call("of_attn_bwd", C.byref(g), flops=10.0 * g.B * H * g.L * g.L * D, family="attn_bwd_kernel (tcgen05 MQA flash)")
