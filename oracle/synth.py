@@ -32,9 +32,9 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0) -> torch.Tenso
     fan_in = 1
     for s in shape[1:]:
         fan_in *= s
-    std = 1.0 / max(fan_in, 1) ** 0.5
+    std = 1.0 / (3.0 * max(fan_in, 1)) ** 0.5   # same second moment as torch's default kaiming-uniform(a=sqrt(5)) init
     if "final_conv" in key:
-        std = 0.02 * 4  # the reference zero-inits final_conv (unet.py:354), which makes parity vacuous: re-randomise
+        std = 0.05  # the reference zero-inits final_conv (unet.py:354), which makes parity vacuous: re-randomise
     return std * torch.randn(shape, generator=g)
 
 

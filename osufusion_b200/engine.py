@@ -126,6 +126,10 @@ class ParamStore:
         self.grads = {}
         self.refresh = True
         self.epoch = 0
+        # set by ddp.GradAllReducer: gradients then live in one flat arena (views keyed by id(param))
+        self.arena_views = None
+        self.on_backward_begin = None
+        self.on_touch = None
 
     def begin_forward(self, refresh: bool) -> None:
         self.refresh = refresh
@@ -201,19 +205,29 @@ class ParamStore:
         return self._cached(("padrows", id(w), rows), (w,), build)
 
     # ---- gradient buffers (fp32, zero-initialised, torch layout) handed back to autograd at the end of backward
-    def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
+    def existing_grad(self, p: torch.nn.Parameter):
+        """The gradient buffer of p if one exists already (arena view or earlier contribution), else None."""
+        if self.on_touch is not None:
+            self.on_touch(id(p))
         g = self.grads.get(id(p))
+        if g is None and self.arena_views is not None and id(p) in self.arena_views:
+            g = self.arena_views[id(p)]
+            self.grads[id(p)] = g
+        return g
+
+    def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
+        g = self.existing_grad(p)
         if g is None:
             g = zeros(p.shape, F32, p.device)
             self.grads[id(p)] = g
         return g
 
     def set_grad(self, p: torch.nn.Parameter, g: torch.Tensor) -> None:
-        old = self.grads.get(id(p))
+        old = self.existing_grad(p)
         if old is None:
             self.grads[id(p)] = g
         else:
-            old.add_(g)
+            old.add_(g.view(old.shape))
 
     def take_grads(self, params):
         out = [self.grads.get(id(p)) if p.requires_grad else None for p in params]
@@ -230,7 +244,7 @@ def _wgrad_conv(store: ParamStore, w: torch.nn.Parameter, dy16, x16, taps, shift
     cp = (Cin + 7) // 8 * 8
     tmp = zeros((k, Cout, cp), F32, w.device)
     R.gemm_wgrad(dy16, x16, tmp, M=Cout, N_out=cp, taps=taps, shift0=shift0, shift_step=1)
-    g = store.grads.get(id(w))
+    g = store.existing_grad(w)
     if g is None:
         g = empty(w.shape, F32, w.device)
         store.grads[id(w)] = g

@@ -219,7 +219,8 @@ class UNet(nn.Module):
             for i, (lo, hi) in enumerate(rio)])
         self._store = ParamStore()
         self.attn_variant = 0
-        self.grad_sync = None   # set by osufusion_b200.ddp.DataParallel: called as layer gradients complete
+        self.grad_sync = None    # set by osufusion_b200.ddp.GradAllReducer: called after every backward tape op
+        self.grad_finish = None  # ... and once at the end of backward (launch remaining buckets, join the comm stream)
 
     # ------------------------------------------------------------------ reference API
     def set_gradient_checkpointing(self, value: bool) -> None:
@@ -360,9 +361,16 @@ class UNet(nn.Module):
         return out16, (ctx, xf)
 
     def backward_from(self, ctx: Ctx, xf: Act, dY16: torch.Tensor, params):
+        st = ctx.store
+        if st.on_backward_begin is not None:
+            st.on_backward_begin()
+        if self.grad_sync is not None:
+            self.grad_sync(len(ctx.tape.ops) + 1)
         self.final_backward(ctx, xf, dY16)
         ctx.tape.run_backward(self.grad_sync)
-        return ctx.store.take_grads(params)
+        if self.grad_finish is not None:
+            self.grad_finish()
+        return st.take_grads(params)
 
 
 class UNetFunction(torch.autograd.Function):

@@ -1,0 +1,64 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the gradient arena / bucket scheduler (osufusion_b200/ddp.py)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.synth import TINY
+    from osufusion_b200.ddp import GradAllReducer, backward_param_order
+    from osufusion_b200.modules import UNet
+
+    torch.manual_seed(0)
+    net = UNet(6, 96, 5, **TINY)
+    order = backward_param_order(net)
+    assert len(order) == len(list(net.parameters())) and len({id(p) for p in order}) == len(order)
+    assert order[0] is net.final_conv.weight          # first gradient to complete in backward
+    red = GradAllReducer(net, bucket_bytes=1 << 20)   # ~20 buckets on the tiny config
+    assert len(red.buckets) > 4
+    st = net._store
+    n_ops = 40
+    for step in range(2):                              # step 0 learns bucket readiness, step 1 overlaps
+        st.on_backward_begin()
+        net.grad_sync(n_ops + 1)
+        per = max(1, len(order) // n_ops)
+        k = 0
+        for op in range(n_ops, -1, -1):                # emulate the backward tape: each op finalises a slice of params
+            for p in order[k:k + per] if op > 0 else order[k:]:
+                g = st.grad(p)
+                g.add_(float(rank + 1) * (1 + step))
+            k += per
+            net.grad_sync(op)
+        net.grad_finish()
+        expect = (1 + step) * sum(r + 1 for r in range(world)) / world
+        grads = st.take_grads(list(net.parameters()))
+        assert all(torch.allclose(g, torch.full_like(g, expect)) for g in grads), (rank, step)
+        if step == 1:
+            assert red.ready_at is not None and len(red._launched) == len(red.buckets)
+    out.put((rank, "ok", len(red.buckets)))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == "ok" for r in res)
