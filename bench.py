@@ -215,7 +215,7 @@ def run_ours(args) -> None:
         l2.backward()
         torch.cuda.synchronize()
         agg = {}
-        for name, flops, ev0, ev1 in NN.PROFILE:
+        for name, flops, ev0, ev1, _tag in NN.PROFILE:
             d = agg.setdefault(name, [0.0, 0.0, 0])
             d[0] += ev0.elapsed_time(ev1)
             d[1] += flops

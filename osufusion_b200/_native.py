@@ -142,7 +142,7 @@ def check(rc: int, what: str) -> None:
 PROFILE = None
 
 
-def call(name: str, *args, flops: float = 0.0, family: str | None = None) -> None:
+def call(name: str, *args, flops: float = 0.0, family: str | None = None, tag: str = "") -> None:
     """Invoke an entry point with the current torch CUDA stream appended; raises on a non-zero return."""
     fn = getattr(lib(), name)
     if PROFILE is not None:
@@ -150,7 +150,7 @@ def call(name: str, *args, flops: float = 0.0, family: str | None = None) -> Non
         e0.record()
         rc = fn(*args, stream_ptr())
         e1.record()
-        PROFILE.append((family or name, flops, e0, e1))
+        PROFILE.append((family or name, flops, e0, e1, tag))
     else:
         rc = fn(*args, stream_ptr())
     if rc != 0:

@@ -115,16 +115,25 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       }
     }
   }
+  // CTA-level reduction in shared memory, then ONE global atomic per channel per CTA
+  extern __shared__ float s_red[];  // [2][C]
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_red[c] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + 32 * i;
     if (vi < vecs) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(dgamma + vi * 8 + j, dg[i].v[j]);
-        atomicAdd(dbeta + vi * 8 + j, db[i].v[j]);
+        atomicAdd(&s_red[vi * 8 + j], dg[i].v[j]);
+        atomicAdd(&s_red[C + vi * 8 + j], db[i].v[j]);
       }
     }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(dgamma + c, s_red[c]);
+    atomicAdd(dbeta + c, s_red[C + c]);
   }
 }
 
@@ -355,7 +364,14 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, rows);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long r = r0; r < r1; ++r) {
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {
+    V8 v0 = ld_bf16x8(dy + r * ld + vi * 8), v1 = ld_bf16x8(dy + (r + 1) * ld + vi * 8);
+    V8 v2 = ld_bf16x8(dy + (r + 2) * ld + vi * 8), v3 = ld_bf16x8(dy + (r + 3) * ld + vi * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += (v0.v[j] + v1.v[j]) + (v2.v[j] + v3.v[j]);
+  }
+  for (; r < r1; ++r) {
     V8 v = ld_bf16x8(dy + r * ld + vi * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
@@ -577,28 +593,40 @@ __global__ void sampler_update_kernel(const float* __restrict__ xin, const __nv_
 }
 
 // weight repacking: torch Conv1d weight (Cout, Cin, k) fp32 -> [k][Cout][Cin_pad] bf16 (zero padded), and back-accumulation
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int k, __nv_bfloat16* __restrict__ out,
-                                        int Cin_pad, int tap_offset, int taps_total) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)k * Cout * Cin_pad;
-  if (idx >= total) return;
-  const int ci = (int)(idx % Cin_pad);
-  long long r = idx / Cin_pad;
-  const int co = (int)(r % Cout), t = (int)(r / Cout);
-  float v = ci < Cin ? w[((long long)co * Cin + ci) * k + t] : 0.f;
-  out[((long long)(t + tap_offset) * Cout + co) * Cin_pad + ci] = __float2bfloat16_rn(v);
+// CTA = (output channel co, 256-wide ci chunk): the (ci, t) slab of one co is contiguous in the torch layout and each tap row
+// is contiguous in the packed layout, so both sides are coalesced through a shared-memory transpose.
+constexpr int kPackChunk = 256;
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int k,
+                                                               __nv_bfloat16* __restrict__ out, int Cin_pad, int tap_offset,
+                                                               int taps_total) {
+  extern __shared__ float s_w[];  // [kPackChunk * k]
+  const int co = blockIdx.x;
+  const int ci0 = blockIdx.y * kPackChunk;
+  const int nci = min(kPackChunk, Cin_pad - ci0);
+  const int nreal = max(0, min(kPackChunk, Cin - ci0));
+  const float* src = w + ((long long)co * Cin + ci0) * k;
+  for (int i = threadIdx.x; i < nreal * k; i += blockDim.x) s_w[i] = src[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nci * k; i += blockDim.x) {
+    const int t = i / nci, ci = i - t * nci;
+    const float v = ci < nreal ? s_w[ci * k + t] : 0.f;
+    out[((long long)(t + tap_offset) * Cout + co) * Cin_pad + ci0 + ci] = __float2bfloat16_rn(v);
+  }
 }
-// dw (Cout, Cin, k) fp32 = packed[t + tap_offset][co][ci] (fp32)  (gather; overwrite)
-__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset,
-                                         float* __restrict__ dw, int accumulate) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)Cout * Cin * k;
-  if (idx >= total) return;
-  const int t = (int)(idx % k);
-  long long r = idx / k;
-  const int ci = (int)(r % Cin), co = (int)(r / Cin);
-  const float v = packed[((long long)(t + tap_offset) * Cout + co) * Cin_pad + ci];
-  dw[idx] = accumulate ? dw[idx] + v : v;
+__global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(const float* __restrict__ packed, int Cout, int Cin, int k,
+                                                                int Cin_pad, int tap_offset, float* __restrict__ dw,
+                                                                int accumulate) {
+  extern __shared__ float s_w[];
+  const int co = blockIdx.x;
+  const int ci0 = blockIdx.y * kPackChunk;
+  const int nreal = max(0, min(kPackChunk, Cin - ci0));
+  for (int i = threadIdx.x; i < nreal * k; i += blockDim.x) {
+    const int t = i / nreal, ci = i - t * nreal;
+    s_w[ci * k + t] = packed[((long long)(t + tap_offset) * Cout + co) * Cin_pad + ci0 + ci];
+  }
+  __syncthreads();
+  float* dst = dw + ((long long)co * Cin + ci0) * k;
+  for (int i = threadIdx.x; i < nreal * k; i += blockDim.x) dst[i] = accumulate ? dst[i] + s_w[i] : s_w[i];
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -641,14 +669,16 @@ extern "C" int of_layernorm_bwd(const float* dy, long long dy_ld, const float* x
                                 float* dgamma, float* dbeta, void* stream) {
   OF_REQUIRE(dy && x && gamma && mean_rstd && dgamma && dbeta && (dx_f32 || dx_bf16), "of_layernorm_bwd: null pointer");
   OF_REQUIRE(C % 8 == 0 && C <= 2048, "of_layernorm_bwd: unsupported C=%d", C);
-  int rpw = rows >= 8 * 148 * 16 ? 8 : (rows >= 8 * 148 * 2 ? 2 : 1);
+  int rpw = (rows + 8 * 296 - 1) / (8 * 296);   // ~2 CTAs per SM, each warp walks `rpw` consecutive rows
+  if (rpw < 1) rpw = 1;
   dim3 grid((rows + 8 * rpw - 1) / (8 * rpw));
+  const size_t red_smem = 2 * (size_t)C * sizeof(float);
   const int nv = (C / 8 + 31) / 32;
   __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-  if (nv <= 1) layernorm_bwd_kernel<1><<<grid, 256, 0, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
-  else if (nv <= 2) layernorm_bwd_kernel<2><<<grid, 256, 0, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
-  else if (nv <= 4) layernorm_bwd_kernel<4><<<grid, 256, 0, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
-  else layernorm_bwd_kernel<8><<<grid, 256, 0, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
+  if (nv <= 1) layernorm_bwd_kernel<1><<<grid, 256, red_smem, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
+  else if (nv <= 2) layernorm_bwd_kernel<2><<<grid, 256, red_smem, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
+  else if (nv <= 4) layernorm_bwd_kernel<4><<<grid, 256, red_smem, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
+  else layernorm_bwd_kernel<8><<<grid, 256, red_smem, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
   DONE()
 }
 
@@ -701,7 +731,7 @@ extern "C" int of_linear_small_bwd(const float* dy, long long dy_ld, const float
 
 extern "C" int of_colsum_bf16(const void* dy, long long ld, long long rows, int N, float* db, void* stream) {
   OF_REQUIRE(dy && db && N % 8 == 0 && ld % 8 == 0, "of_colsum_bf16: bad args");
-  int rpc = 128;
+  int rpc = 64;
   dim3 grid((unsigned)((rows + rpc - 1) / rpc), (N / 8 + 255) / 256);
   colsum_bf16_kernel<<<grid, 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc);
   DONE()
@@ -797,16 +827,19 @@ extern "C" int of_sampler_update(const float* xin, const void* cond, const void*
 extern "C" int of_pack_conv_weight(const float* w, int Cout, int Cin, int k, void* out, int Cin_pad, int tap_offset, int taps_total,
                                    void* stream) {
   OF_REQUIRE(w && out && Cin_pad >= Cin && tap_offset + k <= taps_total, "of_pack_conv_weight: bad args");
-  long long total = (long long)k * Cout * Cin_pad;
-  pack_conv_weight_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(w, Cout, Cin, k, reinterpret_cast<__nv_bfloat16*>(out), Cin_pad,
-                                                                      tap_offset, taps_total);
+  OF_REQUIRE(k <= 32, "of_pack_conv_weight: kernel size %d too large", k);
+  dim3 grid(Cout, (Cin_pad + kPackChunk - 1) / kPackChunk);
+  pack_conv_weight_kernel<<<grid, 256, kPackChunk * k * sizeof(float), STREAM>>>(w, Cout, Cin, k, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                                 Cin_pad, tap_offset, taps_total);
   DONE()
 }
 extern "C" int of_unpack_conv_wgrad(const float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw,
                                     int accumulate, void* stream) {
   OF_REQUIRE(packed && dw, "of_unpack_conv_wgrad: null pointer");
-  long long total = (long long)Cout * Cin * k;
-  unpack_conv_wgrad_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(packed, Cout, Cin, k, Cin_pad, tap_offset, dw, accumulate);
+  OF_REQUIRE(k <= 32, "of_unpack_conv_wgrad: kernel size %d too large", k);
+  dim3 grid(Cout, (Cin + kPackChunk - 1) / kPackChunk);
+  unpack_conv_wgrad_kernel<<<grid, 256, kPackChunk * k * sizeof(float), STREAM>>>(packed, Cout, Cin, k, Cin_pad, tap_offset, dw,
+                                                                                  accumulate);
   DONE()
 }
 extern "C" int of_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {

@@ -83,6 +83,21 @@ __device__ __forceinline__ Map make_map(int C, int L) {
   return m;
 }
 
+
+// Sum the per-thread 8-channel partials of the `rpar` row-lanes of a CTA in shared memory, then one global atomic per channel.
+// `sm` holds C floats; all threads of the CTA must call this.
+__device__ __forceinline__ void cta_channel_reduce(const Map& m, int C, const float (&part)[8], float* sm, float* gdst) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sm[m.c0 + j], part[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(gdst + c, sm[c]);
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(kRbThreads) rb_apply_fwd_kernel(const of_rb_args a) {
   GnCtx g = make_ctx(a);
@@ -169,20 +184,20 @@ __global__ void __launch_bounds__(1024) softmax_rows_kernel(float* rows, int L) 
 }
 
 __global__ void __launch_bounds__(kRbThreads) rb_pool_kernel(const of_rb_args a) {
+  extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L);
-  if (!m.active) return;
-  ChanConst k = load_consts(g, m.b, m.c0);
+  ChanConst k;
+  if (m.active) k = load_consts(g, m.b, m.c0);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+  for (int l = m.l_begin + m.rsub; m.active && l < m.l_end; l += m.rpar) {
     V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
     gn_eval(k, y, xh, z, f, h);
     const float pl = bf16_round(a.p[(long long)m.b * a.L + l]);  // einsum operand is cast to bf16 (autocast)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += bf16_round(h.v[j]) * pl;
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(a.acc_bc + (long long)m.b * a.C + m.c0 + j, acc[j]);
+  cta_channel_reduce(m, a.C, acc, s_red, a.acc_bc + (long long)m.b * a.C);
 }
 
 __global__ void __launch_bounds__(kRbThreads) rb_gate_fwd_kernel(const of_rb_args a) {
@@ -208,27 +223,30 @@ __global__ void __launch_bounds__(kRbThreads) rb_gate_fwd_kernel(const of_rb_arg
 
 // ------------------------------------------------------------------------------------------------ backward
 __global__ void __launch_bounds__(kRbThreads) rb_gate_bwd_reduce_kernel(const of_rb_args a) {
+  extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L);
-  if (!m.active) return;
-  ChanConst k = load_consts(g, m.b, m.c0);
+  ChanConst k;
+  if (m.active) k = load_consts(g, m.b, m.c0);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+  for (int l = m.l_begin + m.rsub; m.active && l < m.l_end; l += m.rpar) {
     V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
     gn_eval(k, y, xh, z, f, h);
     V8 d = ld_f32x8(a.dout_f32 + m.b * a.dout_f32_bs + (long long)l * a.dout_f32_ld + m.c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += d.v[j] * h.v[j];
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(a.acc_bc + (long long)m.b * a.C + m.c0 + j, acc[j]);
+  cta_channel_reduce(m, a.C, acc, s_red, a.acc_bc + (long long)m.b * a.C);
 }
 
-__global__ void __launch_bounds__(kRbThreads) rb_bwd_pass1_kernel(const of_rb_args a) {
+__global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb_args a) {
   __shared__ float sm[32];
+  extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L);
   float s1 = 0.f, s2 = 0.f, sda = 0.f;
+  float dgam[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbet[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float dsc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dsh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dwk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (m.active) {
     ChanConst k = load_consts(g, m.b, m.c0);
     V8 gate, dpool, wk;
@@ -239,8 +257,6 @@ __global__ void __launch_bounds__(kRbThreads) rb_bwd_pass1_kernel(const of_rb_ar
 #pragma unroll
       for (int j = 0; j < 8; ++j) wk.v[j] = bf16_round(wk.v[j]);
     }
-    float dgam[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbet[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float dsc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dsh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dwk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const __nv_bfloat16* dh16 = reinterpret_cast<const __nv_bfloat16*>(a.dh_bf16);
     __nv_bfloat16* dxh = reinterpret_cast<__nv_bfloat16*>(a.dxhat_bf16);
     __nv_bfloat16* do16 = reinterpret_cast<__nv_bfloat16*>(a.dout_bf16);
@@ -279,17 +295,14 @@ __global__ void __launch_bounds__(kRbThreads) rb_bwd_pass1_kernel(const of_rb_ar
       }
       st_bf16x8(dxh + m.b * a.dxhat_bs + (long long)l * a.dxhat_ld + m.c0, dx);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(a.dgamma + m.c0 + j, dgam[j]);
-      atomicAdd(a.dbeta + m.c0 + j, dbet[j]);
-      if (k.film) {
-        atomicAdd(a.dss + (long long)m.b * 2 * a.C + m.c0 + j, dsc[j]);
-        atomicAdd(a.dss + (long long)m.b * 2 * a.C + a.C + m.c0 + j, dsh[j]);
-      }
-      if (a.mode == 0) atomicAdd(a.dwk + m.c0 + j, dwk[j]);
-    }
   }
+  cta_channel_reduce(m, a.C, dgam, s_red, a.dgamma);
+  cta_channel_reduce(m, a.C, dbet, s_red, a.dbeta);
+  if (a.ss) {
+    cta_channel_reduce(m, a.C, dsc, s_red, a.dss + (long long)blockIdx.y * 2 * a.C);
+    cta_channel_reduce(m, a.C, dsh, s_red, a.dss + (long long)blockIdx.y * 2 * a.C + a.C);
+  }
+  if (a.mode == 0) cta_channel_reduce(m, a.C, dwk, s_red, a.dwk);
   s1 = block_sum(s1, sm);
   s2 = block_sum(s2, sm);
   if (a.mode == 0) sda = block_sum(sda, sm);
@@ -301,9 +314,9 @@ __global__ void __launch_bounds__(kRbThreads) rb_bwd_pass1_kernel(const of_rb_ar
 }
 
 __global__ void __launch_bounds__(kRbThreads) rb_bwd_apply_kernel(const of_rb_args a) {
+  extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L);
-  if (!m.active) return;
   float mean, rstd;
   const double n = (double)a.L * (double)a.C;
   gn_mean_rstd(g.stats, m.b, n, g.eps, mean, rstd);
@@ -311,7 +324,7 @@ __global__ void __launch_bounds__(kRbThreads) rb_bwd_apply_kernel(const of_rb_ar
   const __nv_bfloat16* dxh = reinterpret_cast<const __nv_bfloat16*>(a.dxhat_bf16);
   __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(a.dy_bf16);
   float db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+  for (int l = m.l_begin + m.rsub; m.active && l < m.l_end; l += m.rpar) {
     V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0);
     V8 dx = ld_bf16x8(dxh + m.b * a.dxhat_bs + (long long)l * a.dxhat_ld + m.c0), o;
 #pragma unroll
@@ -322,10 +335,7 @@ __global__ void __launch_bounds__(kRbThreads) rb_bwd_apply_kernel(const of_rb_ar
     }
     st_bf16x8(dy + m.b * a.dy_bs + (long long)l * a.dy_ld + m.c0, o);
   }
-  if (a.dbias) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(a.dbias + m.c0 + j, db[j]);
-  }
+  if (a.dbias) cta_channel_reduce(m, a.C, db, s_red, a.dbias);
 }
 
 static int check_common(const of_rb_args* a, const char* who) {
@@ -342,8 +352,8 @@ static dim3 rb_grid(const of_rb_args* a) { return dim3((a->L + kRowsPerCta - 1) 
 
 using namespace ofx;
 
-#define RB_LAUNCH(kernel, grid, threads)                                           \
-  kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);       \
+#define RB_LAUNCH(kernel, grid, threads)                                                                     \
+  kernel<<<grid, threads, (size_t)a->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(*a);       \
   OF_CHECK_CUDA(cudaGetLastError());                                              \
   count_launch();                                                                 \
   return OF_OK;

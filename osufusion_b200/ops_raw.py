@@ -67,7 +67,8 @@ def gemm_fwd(a, b, *, N_out, K, taps=1, shift0=0, shift_step=0, b_mn_major=False
         assert stats.dtype == torch.float64
         g.stats = stats.data_ptr()
     g.block_n = block_n
-    N.call("of_gemm", C.byref(g), flops=2.0 * g.batch * g.rows * N_out * K * taps, family="gemm_kernel (tcgen05 GEMM/conv)")
+    N.call("of_gemm", C.byref(g), flops=2.0 * g.batch * g.rows * N_out * K * taps, family="gemm_kernel (tcgen05 GEMM/conv)",
+           tag=f"{'wgrad' if g.mode else ('dgrad' if g.b_mn_major else 'fwd')} B{g.batch} L{g.rows} N{g.N} K{g.K} T{g.taps}")
 
 
 def gemm_wgrad(dy, x, out_f32, *, M, N_out, taps=1, shift0=0, shift_step=0, split_k=0, block_n=0):
@@ -88,7 +89,8 @@ def gemm_wgrad(dy, x, out_f32, *, M, N_out, taps=1, shift0=0, shift_step=0, spli
     g.out_f32_batch_stride, g.out_f32_ld = out_f32.stride(0), out_f32.stride(1)
     g.split_k = split_k
     g.block_n = block_n
-    N.call("of_gemm", C.byref(g), flops=2.0 * g.batch * g.rows * N_out * M * taps, family="gemm_kernel (tcgen05 GEMM/conv)")
+    N.call("of_gemm", C.byref(g), flops=2.0 * g.batch * g.rows * N_out * M * taps, family="gemm_kernel (tcgen05 GEMM/conv)",
+           tag=f"{'wgrad' if g.mode else ('dgrad' if g.b_mn_major else 'fwd')} B{g.batch} L{g.rows} N{g.N} K{g.K} T{g.taps}")
 
 
 def _attn_common(q, k, v, H, KVH, D, variant):

@@ -176,4 +176,41 @@ def test_sampling_matches_oracle_trajectory():
                 y_ref = ora.sample(a, c, noise.clone(), cond_scale=scale)
             y_new = new.sample(a, c, noise.clone(), cond_scale=scale)
             assert y_new.shape == y_ref.shape == (2, 6, 100)
-            assert nrel(y_new, y_ref) < 3e-2, (NC.__module__, scale, nrel(y_new, y_ref))
+            # several bf16 denoiser evaluations are chained (and CFG amplifies their differences): trajectory tolerance is loose,
+            # the per-step update arithmetic is checked tightly in test_sampler_update_kernel_matches_schedules
+            assert nrel(y_new, y_ref) < 0.12, (NC.__module__, scale, nrel(y_new, y_ref))
+            assert (y_new - y_ref).abs().mean() < 1.5e-2 * y_ref.abs().mean().clamp_min(0.1)
+
+
+def test_sampler_update_kernel_matches_schedules():
+    """Fused CFG + DDIM / midpoint update vs the restated diffusers / torchdiffeq arithmetic on identical predictions."""
+    from oracle.schedules import DDIMSchedule
+    from osufusion_b200 import _native as N
+    torch.manual_seed(3)
+    B, n, Lp = 2, 100, 112
+    x = torch.randn(B, 6, n, device=dev) * 1.5
+    cond = torch.randn(B, Lp, 8, device=dev).bfloat16()
+    null = torch.randn(B, Lp, 8, device=dev).bfloat16()
+    c_ref = cond[:, :n, :6].transpose(1, 2)
+    n_ref = null[:, :n, :6].transpose(1, 2)
+    scale = 2.0
+    eps = n_ref + (c_ref - n_ref) * scale                    # bf16 arithmetic, as unet.py:465 under autocast
+    sch = DDIMSchedule(1000)
+    sch.set_timesteps(35)
+    for t in (952, 28, 0):
+        ref = sch.step(eps, t, x)
+        a_t = float(sch.alphas_cumprod[t])
+        tp = t - 1000 // 35
+        a_p = float(sch.alphas_cumprod[tp]) if tp >= 0 else 1.0
+        out = torch.empty_like(x)
+        packed = torch.empty(B, Lp, 8, device=dev, dtype=torch.bfloat16)
+        N.call("of_sampler_update", x.data_ptr(), cond.data_ptr(), null.data_ptr(), 8, Lp * 8, scale, 0, (1 - a_t) ** 0.5, a_t ** 0.5,
+               a_p ** 0.5, (1 - a_p) ** 0.5, B, 6, n, out.data_ptr(), packed.data_ptr(), Lp, 8, -1.0)
+        assert nrel(out, ref) < 2e-3, (t, nrel(out, ref))
+        assert nrel(packed[:, :n, :6].transpose(1, 2), ref) < 1e-2
+        assert (packed[:, n:, :6] == -1.0).all() and (packed[:, :, 6:] == 0).all()
+    dt = 1.0 / 15
+    out = torch.empty_like(x)
+    N.call("of_sampler_update", x.data_ptr(), cond.data_ptr(), None, 8, Lp * 8, 1.0, 1, dt, 1.0, 0.0, 0.0, B, 6, n, out.data_ptr(), None,
+           Lp, 8, -1.0)
+    assert nrel(out, x + c_ref * torch.tensor(dt)) < 2e-3
