@@ -17,7 +17,7 @@ namespace ofx {
 int make_head_tmap(CUtensorMap* m, const void* base, int D, int heads, int L, int B, long long ld, long long bs,
                    unsigned box_rows);
 
-constexpr int kBThreads = 192;
+constexpr int kBThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax/epilogue (two per TMEM lane quarter)
 constexpr uint32_t kTile = 128 * 64 * 2;  // 16 KB
 
 struct AttnBwdParams {
@@ -42,6 +42,9 @@ __device__ __forceinline__ void red_add4(float* ptr, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Software pipeline (per Q tile i; tensor core and softmax threads overlap):
+//   MMA   : dV+=P(i)^T dO | S(i+1)=Q K^T | dK+=dS(i)^T Q, dQ(i)=dS K | dP(i+1)=dO V^T
+//   threads: A(i): S -> P (regs + smem) | C(i-1): dQ(i-1) -> global atomics | B(i): dP -> dS (smem)
 __global__ void __launch_bounds__(kBThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -57,14 +60,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;    // [2]
   uint64_t* qdo_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* sdp_empty = bars + 6;
-  uint64_t* pds_full = bars + 7;
-  uint64_t* pds_empty = bars + 8;
-  uint64_t* dq_full = bars + 9;
-  uint64_t* dq_empty = bars + 10;
-  uint64_t* acc_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* dp_full = bars + 7;
+  uint64_t* dp_empty = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* p_empty = bars + 10;
+  uint64_t* ds_full = bars + 11;
+  uint64_t* ds_empty = bars + 12;
+  uint64_t* dq_full = bars + 13;
+  uint64_t* dq_empty = bars + 14;
+  uint64_t* acc_done = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -81,12 +88,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_empty[i], 1);
     }
-    mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 4);
-    mbar_init(pds_full, 4);
-    mbar_init(pds_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 8);
+    mbar_init(dp_full, 1);
+    mbar_init(dp_empty, 8);
+    mbar_init(p_full, 8);
+    mbar_init(p_empty, 1);
+    mbar_init(ds_full, 8);
+    mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 4);
+    mbar_init(dq_empty, 8);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -121,143 +132,183 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t idesc_kv = make_idesc_bf16(128, 64, 1, 1);  // dV, dK: A = P^T / dS^T (MN-major), B MN-major
       const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);  // dQ: A = dS (K-major), B = K (MN-major)
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
+      auto issue_s = [&](int i) {
+        const uint32_t aQ = smem_u32(sQdO + (i & 1) * 2 * kTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      auto issue_dp = [&](int i) {
+        const uint32_t adO = smem_u32(sQdO + (i & 1) * 2 * kTile) + kTile;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tdP, make_smem_desc(adO + k * 32, 16, 1024), make_smem_desc(aV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(dp_full);
+      };
       mbar_wait(kv_full, 0);
+      mbar_wait(&qdo_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      issue_dp(0);
       for (int i = 0; i < n; ++i) {
         const int st = i & 1;
         const uint32_t aQ = smem_u32(sQdO + st * 2 * kTile), adO = aQ + kTile;
-        mbar_wait(&qdo_full[st], (i >> 1) & 1);
-        mbar_wait(sdp_empty, (i & 1) ^ 1);
+        // dV += P^T dO   (K = 128 q rows, 16 per step)
+        mbar_wait(p_full, i & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s,
-                      k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tdP, make_smem_desc(adO + k * 32, 16, 1024), make_smem_desc(aV + k * 32, 16, 1024), idesc_s,
-                      k > 0 ? 1u : 0u);
-        umma_commit(sdp_full);
-
-        mbar_wait(pds_full, i & 1);
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ss(tdV, make_smem_desc(aP + k * 2048, kTile, 1024), make_smem_desc(adO + k * 2048, 8192, 1024), idesc_kv,
+                      (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(p_empty);
+        // S(i+1)
+        if (i + 1 < n) {
+          mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+          mbar_wait(s_empty, i & 1);
+          tc_fence_after();
+          issue_s(i + 1);
+        }
+        // dK += dS^T Q ; dQ = dS K
+        mbar_wait(ds_full, i & 1);
         mbar_wait(dq_empty, (i & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dV += P^T dO   (K = 128 q rows, 16 per step)
-          umma_f16_ss(tdV, make_smem_desc(aP + k * 2048, 2 * kTile / 2, 1024), make_smem_desc(adO + k * 2048, 8192, 1024),
-                      idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ss(tdK, make_smem_desc(adS + k * 2048, kTile, 1024), make_smem_desc(aQ + k * 2048, 8192, 1024), idesc_kv,
+                      (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dK += dS^T Q
-          umma_f16_ss(tdK, make_smem_desc(adS + k * 2048, 2 * kTile / 2, 1024), make_smem_desc(aQ + k * 2048, 8192, 1024),
-                      idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // dQ = dS K      (K = 128 keys, 16 per step)
+        for (int k = 0; k < 8; ++k)
           umma_f16_ss(tdQ, make_smem_desc(adS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
                       make_smem_desc(aK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
         umma_commit(dq_full);
-        umma_commit(pds_empty);
+        umma_commit(ds_empty);
         umma_commit(&qdo_empty[st]);
+        // dP(i+1)
+        if (i + 1 < n) {
+          mbar_wait(dp_empty, i & 1);
+          tc_fence_after();
+          issue_dp(i + 1);
+        }
       }
       umma_commit(acc_done);
     }
     __syncwarp();
   } else {
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;     // which 64 keys (S/dP columns) / which 32 d-columns (dQ, dK, dV) this warp owns
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const long long bh = (long long)b * p.H + h;
+    const int key_base = k0 + half * 64;
+
+    auto flush_dq = [&](int i) {   // stage C: dQ(i) tile -> global fp32 atomics
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      uint32_t dq[32];
+      tmem_ld_32x32b_x32(tdQ + lane_off + half * 32, dq);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+      const int qrow = i * 128 + row;
+      if (qrow < p.L) {
+        float* dst = p.dq + (long long)b * p.dq_bs + (long long)qrow * p.dq_ld + (long long)h * p.D + half * 32;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (half * 32 + g * 4 < p.D)
+            red_add4(dst + g * 4, __uint_as_float(dq[g * 4]), __uint_as_float(dq[g * 4 + 1]), __uint_as_float(dq[g * 4 + 2]),
+                     __uint_as_float(dq[g * 4 + 3]));
+      }
+    };
+
     for (int i = 0; i < n; ++i) {
       const int qrow = i * 128 + row;
       const bool q_ok = qrow < p.L;
       const float lse2 = q_ok ? p.lse[bh * p.L + qrow] : 0.f;
       const float dlt = q_ok ? p.delta[bh * p.L + qrow] : 0.f;
-      mbar_wait(sdp_full, i & 1);
-      mbar_wait(pds_empty, (i & 1) ^ 1);
-      tc_fence_after();
+      // ---- stage A: P = exp2(S*scale*log2e - lse2)
+      uint32_t pk[32];  // 64 probabilities, packed bf16x2
+      {
+        uint32_t s[64];
+        mbar_wait(s_full, i & 1);
+        tc_fence_after();
+        uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+        uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+        tmem_ld_32x32b_x32(tS + lane_off + half * 64, s0);
+        tmem_ld_32x32b_x32(tS + lane_off + half * 64 + 32, s1);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t s[64], dp[64];
-        {
-          uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
-          uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
-          uint32_t (&d0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dp[0]);
-          uint32_t (&d1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dp[32]);
-          tmem_ld_32x32b_x32(tS + lane_off + hf * 64, s0);
-          tmem_ld_32x32b_x32(tS + lane_off + hf * 64 + 32, s1);
-          tmem_ld_32x32b_x32(tdP + lane_off + hf * 64, d0);
-          tmem_ld_32x32b_x32(tdP + lane_off + hf * 64 + 32, d1);
-          tmem_wait_ld();
-        }
-        const int key_base = k0 + hf * 64;
-        uint8_t* prow = sP + hf * kTile + row * 128;
-        uint8_t* dsrow = sdS + hf * kTile + row * 128;
-#pragma unroll
-        for (int pc = 0; pc < 8; ++pc) {
-          uint32_t pw[4], dw[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c0 = pc * 8 + e * 2;
-            float p0 = ex2b(fmaf(__uint_as_float(s[c0]), p.scale_log2, -lse2));
-            float p1 = ex2b(fmaf(__uint_as_float(s[c0 + 1]), p.scale_log2, -lse2));
-            if (!q_ok || key_base + c0 >= p.L) p0 = 0.f;
-            if (!q_ok || key_base + c0 + 1 >= p.L) p1 = 0.f;
-            float ds0 = p0 * (__uint_as_float(dp[c0]) - dlt) * p.scale;
-            float ds1 = p1 * (__uint_as_float(dp[c0 + 1]) - dlt) * p.scale;
-            pw[e] = pack_bf16x2(p0, p1);
-            dw[e] = pack_bf16x2(ds0, ds1);
-          }
-          const int off = (pc ^ (row & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + off) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        for (int e = 0; e < 32; ++e) {
+          float p0 = ex2b(fmaf(__uint_as_float(s[2 * e]), p.scale_log2, -lse2));
+          float p1 = ex2b(fmaf(__uint_as_float(s[2 * e + 1]), p.scale_log2, -lse2));
+          if (!q_ok || key_base + 2 * e >= p.L) p0 = 0.f;
+          if (!q_ok || key_base + 2 * e + 1 >= p.L) p1 = 0.f;
+          pk[e] = pack_bf16x2(p0, p1);
         }
       }
-      tc_fence_before();
+      mbar_wait(p_empty, (i & 1) ^ 1);   // dV MMA of the previous tile has finished reading sP
+      {
+        uint8_t* prow = sP + half * kTile + row * 128;
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc)
+          *reinterpret_cast<uint4*>(prow + ((pc ^ (row & 7)) << 4)) = make_uint4(pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+      }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(sdp_empty);
-        mbar_arrive(pds_full);
-      }
-      // ---- dQ tile -> global (fp32 atomics; summed over KV tiles)
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      uint32_t dq[64];
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- stage C of the previous tile (its dK/dQ MMAs ran while we computed P)
+      if (i > 0) flush_dq(i - 1);
+      // ---- stage B: dS = P o (dP - delta) * scale
       {
-        uint32_t (&q0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dq[0]);
-        uint32_t (&q1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dq[32]);
-        tmem_ld_32x32b_x32(tdQ + lane_off, q0);
-        tmem_ld_32x32b_x32(tdQ + lane_off + 32, q1);
+        uint32_t dp[64];
+        mbar_wait(dp_full, i & 1);
+        tc_fence_after();
+        uint32_t (&d0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dp[0]);
+        uint32_t (&d1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dp[32]);
+        tmem_ld_32x32b_x32(tdP + lane_off + half * 64, d0);
+        tmem_ld_32x32b_x32(tdP + lane_off + half * 64 + 32, d1);
         tmem_wait_ld();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty);
-      if (q_ok) {
-        float* dst = p.dq + (long long)b * p.dq_bs + (long long)qrow * p.dq_ld + (long long)h * p.D;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dp_empty);
 #pragma unroll
-        for (int g = 0; g < 16; ++g)
-          if (g * 4 < p.D)
-            red_add4(dst + g * 4, __uint_as_float(dq[g * 4]), __uint_as_float(dq[g * 4 + 1]),
-                     __uint_as_float(dq[g * 4 + 2]), __uint_as_float(dq[g * 4 + 3]));
+        for (int e = 0; e < 32; ++e) {
+          float2 pp = unpack_bf16x2(pk[e]);
+          float ds0 = pp.x * (__uint_as_float(dp[2 * e]) - dlt) * p.scale;
+          float ds1 = pp.y * (__uint_as_float(dp[2 * e + 1]) - dlt) * p.scale;
+          pk[e] = pack_bf16x2(ds0, ds1);
+        }
       }
+      mbar_wait(ds_empty, (i & 1) ^ 1);  // dK/dQ MMAs of the previous tile have finished reading sdS
+      {
+        uint8_t* dsrow = sdS + half * kTile + row * 128;
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc)
+          *reinterpret_cast<uint4*>(dsrow + ((pc ^ (row & 7)) << 4)) = make_uint4(pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
     }
-    // ---- dK / dV tiles -> global (fp32 atomics; summed over q heads)
+    flush_dq(n - 1);
+    // ---- dK / dV tiles -> global (fp32 atomics; summed over q heads); this warp owns d-columns [half*32, half*32+32)
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const int key = k0 + row;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      uint32_t a[64];
-      uint32_t (&a0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&a[0]);
-      uint32_t (&a1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&a[32]);
-      const uint32_t t = which == 0 ? tdV : tdK;
-      tmem_ld_32x32b_x32(t + lane_off, a0);
-      tmem_ld_32x32b_x32(t + lane_off + 32, a1);
+      uint32_t a[32];
+      tmem_ld_32x32b_x32((which == 0 ? tdV : tdK) + lane_off + half * 32, a);
       tmem_wait_ld();
       if (key < p.L) {
-        float* dst = (which == 0 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)key * p.dkv_ld + (long long)kvh * p.D;
+        float* dst = (which == 0 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)key * p.dkv_ld + (long long)kvh * p.D + half * 32;
 #pragma unroll
-        for (int g = 0; g < 16; ++g)
-          if (g * 4 < p.D)
+        for (int g = 0; g < 8; ++g)
+          if (half * 32 + g * 4 < p.D)
             red_add4(dst + g * 4, __uint_as_float(a[g * 4]), __uint_as_float(a[g * 4 + 1]), __uint_as_float(a[g * 4 + 2]),
                      __uint_as_float(a[g * 4 + 3]));
       }

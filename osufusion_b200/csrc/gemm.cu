@@ -15,7 +15,7 @@ namespace ofx {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 constexpr int kMaxStages = 8;
 constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
 constexpr uint32_t kTmemCols = 512;
@@ -110,7 +110,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);
+      mbar_init(&tmem_empty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -200,8 +200,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue warps (2..9)
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;   // the two warps of a quarter take alternate 32-column chunks
     const int r = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -221,7 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         __nv_bfloat16* o16 = p.out_bf16 ? p.out_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
         __nv_bfloat16* pre16 = p.pre_bf16 ? p.pre_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
         float* o32 = p.out_f32 ? p.out_f32 + brow * p.out_f32_bs + (long long)m * p.out_f32_ld : nullptr;
-        for (int c = 0; c < p.BN / 32; ++c) {
+        for (int c = chalf; c < p.BN / 32; c += 2) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c * 32, v);
           tmem_wait_ld();
@@ -305,7 +306,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // WGRAD: atomically accumulate fp32 into out_f32[tap][m][n]
         const bool row_ok = (m < p.K) && k_nonempty;
         float* o32 = p.out_f32 + (long long)tc.tap * p.out_f32_bs + (long long)m * p.out_f32_ld;
-        for (int c = 0; c < p.BN / 32; ++c) {
+        for (int c = chalf; c < p.BN / 32; c += 2) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c * 32, v);
           tmem_wait_ld();

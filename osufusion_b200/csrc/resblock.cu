@@ -11,7 +11,6 @@
 namespace ofx {
 
 constexpr int kRbThreads = 256;
-constexpr int kRowsPerCta = 64;
 
 struct GnCtx {
   int B, L, C;
@@ -69,7 +68,7 @@ struct Map {
   int vecs, rpar, vi, rsub, c0, b, l_begin, l_end;
   bool active;
 };
-__device__ __forceinline__ Map make_map(int C, int L) {
+__device__ __forceinline__ Map make_map(int C, int L, int rows_per_cta) {
   Map m;
   m.vecs = C >> 3;
   m.rpar = kRbThreads / m.vecs;
@@ -78,11 +77,33 @@ __device__ __forceinline__ Map make_map(int C, int L) {
   m.active = m.rsub < m.rpar;
   m.c0 = m.vi * 8;
   m.b = blockIdx.y;
-  m.l_begin = blockIdx.x * kRowsPerCta;
-  m.l_end = min(m.l_begin + kRowsPerCta, L);
+  m.l_begin = blockIdx.x * rows_per_cta;
+  m.l_end = min(m.l_begin + rows_per_cta, L);
   return m;
 }
 
+
+// Up to 5 per-channel partial arrays reduced across the CTA with 3 barriers in total: sm holds n*C floats.
+struct RedSlot {
+  const float* part;  // this thread's 8 partials
+  float* gdst;        // global [C] destination (nullptr = skip)
+};
+__device__ __forceinline__ void cta_channel_reduce_multi(const Map& m, int C, const RedSlot* slots, int n, float* sm) {
+  for (int c = threadIdx.x; c < n * C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  if (m.active) {
+    for (int s = 0; s < n; ++s) {
+      if (slots[s].gdst == nullptr) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sm[s * C + m.c0 + j], slots[s].part[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n * C; c += blockDim.x) {
+    const int s = c / C;
+    if (slots[s].gdst != nullptr) atomicAdd(slots[s].gdst + (c - s * C), sm[c]);
+  }
+}
 
 // Sum the per-thread 8-channel partials of the `rpar` row-lanes of a CTA in shared memory, then one global atomic per channel.
 // `sm` holds C floats; all threads of the CTA must call this.
@@ -99,9 +120,9 @@ __device__ __forceinline__ void cta_channel_reduce(const Map& m, int C, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(kRbThreads) rb_apply_fwd_kernel(const of_rb_args a) {
+__global__ void __launch_bounds__(kRbThreads) rb_apply_fwd_kernel(const of_rb_args a, const int rpc) {
   GnCtx g = make_ctx(a);
-  Map m = make_map(a.C, a.L);
+  Map m = make_map(a.C, a.L, rpc);
   if (!m.active) return;
   ChanConst k = load_consts(g, m.b, m.c0);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
@@ -112,8 +133,9 @@ __global__ void __launch_bounds__(kRbThreads) rb_apply_fwd_kernel(const of_rb_ar
   }
 }
 
-// warp per row: dot(h_row, vec)
-__global__ void __launch_bounds__(256) rb_rowdot_kernel(const of_rb_args a) {
+// warp per row: dot(h_row, vec); lane owns 16-byte vectors lane + 32*i (i < NV) and keeps their constants in registers
+template <int NV>
+__global__ void __launch_bounds__(256) rb_rowdot_kernel(const of_rb_args a, const int rows_per_warp) {
   GnCtx g = make_ctx(a);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -122,39 +144,37 @@ __global__ void __launch_bounds__(256) rb_rowdot_kernel(const of_rb_args a) {
   gn_mean_rstd(g.stats, b, (double)g.L * (double)g.C, g.eps, mean, rstd);
   const float* vec = a.vec + (long long)b * a.vec_bs;
   const float bias = a.vec_bias ? *a.vec_bias : 0.f;
-  const int rows_per_cta = 8 * 8;  // 8 warps x 8 rows
-  const int l0 = blockIdx.x * rows_per_cta;
-  for (int rr = warp; rr < rows_per_cta; rr += 8) {
+  ChanConst k[NV];
+  V8 w[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+      k[i] = load_consts(g, b, vi * 8);
+      w[i] = ld_f32x8(vec + vi * 8);
+      if (a.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[i].v[j] = bf16_round(w[i].v[j]);
+      }
+    }
+  }
+  const int l0 = (blockIdx.x * 8 + warp) * rows_per_warp;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
     const int l = l0 + rr;
     if (l >= a.L) break;
     float acc = 0.f;
-    for (int v = lane; v < vecs; v += 32) {
-      const int c0 = v * 8;
-      ChanConst k;
-      k.gamma = ld_f32x8(g.gamma + c0);
-      k.beta = ld_f32x8(g.beta + c0);
-      k.film = g.ss != nullptr;
-      if (k.film) {
-        V8 sc = ld_f32x8(g.ss + (long long)b * 2 * g.C + c0);
-        k.shift = ld_f32x8(g.ss + (long long)b * 2 * g.C + g.C + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) k.sp1.v[j] = bf16_round(sc.v[j] + 1.0f);
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < vecs) {
+        V8 y = ld_bf16x8(g.y + b * g.y_bs + (long long)l * g.y_ld + vi * 8), xh, z, f, h;
+        gn_eval(k[i], y, xh, z, f, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += bf16_round(h.v[j]) * w[i].v[j];
       }
-      k.mean = mean;
-      k.rstd = rstd;
-      V8 y = ld_bf16x8(g.y + b * g.y_bs + (long long)l * g.y_ld + c0), xh, z, f, h;
-      gn_eval(k, y, xh, z, f, h);
-      V8 w = ld_f32x8(vec + c0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc += bf16_round(h.v[j]) * (a.mode == 0 ? bf16_round(w.v[j]) : w.v[j]);
     }
     acc = warp_sum(acc);
-    if (lane == 0) {
-      float r;
-      if (a.mode == 0) r = bf16_round(acc + bias);
-      else r = acc;
-      a.out_rows[(long long)b * a.L + l] = r;
-    }
+    if (lane == 0) a.out_rows[(long long)b * a.L + l] = (a.mode == 0) ? bf16_round(acc + bias) : acc;
   }
 }
 
@@ -183,10 +203,10 @@ __global__ void __launch_bounds__(1024) softmax_rows_kernel(float* rows, int L) 
   for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] = expf(r[i] - mx) * inv;
 }
 
-__global__ void __launch_bounds__(kRbThreads) rb_pool_kernel(const of_rb_args a) {
+__global__ void __launch_bounds__(kRbThreads) rb_pool_kernel(const of_rb_args a, const int rpc) {
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
-  Map m = make_map(a.C, a.L);
+  Map m = make_map(a.C, a.L, rpc);
   ChanConst k;
   if (m.active) k = load_consts(g, m.b, m.c0);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -200,9 +220,9 @@ __global__ void __launch_bounds__(kRbThreads) rb_pool_kernel(const of_rb_args a)
   cta_channel_reduce(m, a.C, acc, s_red, a.acc_bc + (long long)m.b * a.C);
 }
 
-__global__ void __launch_bounds__(kRbThreads) rb_gate_fwd_kernel(const of_rb_args a) {
+__global__ void __launch_bounds__(kRbThreads) rb_gate_fwd_kernel(const of_rb_args a, const int rpc) {
   GnCtx g = make_ctx(a);
-  Map m = make_map(a.C, a.L);
+  Map m = make_map(a.C, a.L, rpc);
   if (!m.active) return;
   ChanConst k = load_consts(g, m.b, m.c0);
   V8 gate = ld_f32x8(a.gate + (long long)m.b * a.C + m.c0);
@@ -222,10 +242,10 @@ __global__ void __launch_bounds__(kRbThreads) rb_gate_fwd_kernel(const of_rb_arg
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(kRbThreads) rb_gate_bwd_reduce_kernel(const of_rb_args a) {
+__global__ void __launch_bounds__(kRbThreads) rb_gate_bwd_reduce_kernel(const of_rb_args a, const int rpc) {
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
-  Map m = make_map(a.C, a.L);
+  Map m = make_map(a.C, a.L, rpc);
   ChanConst k;
   if (m.active) k = load_consts(g, m.b, m.c0);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -239,11 +259,11 @@ __global__ void __launch_bounds__(kRbThreads) rb_gate_bwd_reduce_kernel(const of
   cta_channel_reduce(m, a.C, acc, s_red, a.acc_bc + (long long)m.b * a.C);
 }
 
-__global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb_args a) {
+__global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb_args a, const int rpc) {
   __shared__ float sm[32];
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
-  Map m = make_map(a.C, a.L);
+  Map m = make_map(a.C, a.L, rpc);
   float s1 = 0.f, s2 = 0.f, sda = 0.f;
   float dgam[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbet[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float dsc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dsh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dwk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -279,7 +299,9 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float df = dh.v[j] * dsilu_acc(f.v[j]);
+        // silu'(f) = s*(1 + f*(1-s)) with s = h/f reused from the forward recompute (s = sigmoid(f))
+        const float sg = 1.0f / (1.0f + expf(-f.v[j]));
+        float df = dh.v[j] * (sg * (1.0f + f.v[j] * (1.0f - sg)));
         float dz = df;
         if (k.film) {
           dsc[j] += df * z.v[j];
@@ -296,13 +318,12 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
       st_bf16x8(dxh + m.b * a.dxhat_bs + (long long)l * a.dxhat_ld + m.c0, dx);
     }
   }
-  cta_channel_reduce(m, a.C, dgam, s_red, a.dgamma);
-  cta_channel_reduce(m, a.C, dbet, s_red, a.dbeta);
-  if (a.ss) {
-    cta_channel_reduce(m, a.C, dsc, s_red, a.dss + (long long)blockIdx.y * 2 * a.C);
-    cta_channel_reduce(m, a.C, dsh, s_red, a.dss + (long long)blockIdx.y * 2 * a.C + a.C);
-  }
-  if (a.mode == 0) cta_channel_reduce(m, a.C, dwk, s_red, a.dwk);
+  RedSlot slots[5] = {{dgam, a.dgamma},
+                      {dbet, a.dbeta},
+                      {dsc, a.ss ? a.dss + (long long)blockIdx.y * 2 * a.C : nullptr},
+                      {dsh, a.ss ? a.dss + (long long)blockIdx.y * 2 * a.C + a.C : nullptr},
+                      {dwk, a.mode == 0 ? a.dwk : nullptr}};
+  cta_channel_reduce_multi(m, a.C, slots, 5, s_red);
   s1 = block_sum(s1, sm);
   s2 = block_sum(s2, sm);
   if (a.mode == 0) sda = block_sum(sda, sm);
@@ -313,10 +334,10 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
   }
 }
 
-__global__ void __launch_bounds__(kRbThreads) rb_bwd_apply_kernel(const of_rb_args a) {
+__global__ void __launch_bounds__(kRbThreads) rb_bwd_apply_kernel(const of_rb_args a, const int rpc) {
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
-  Map m = make_map(a.C, a.L);
+  Map m = make_map(a.C, a.L, rpc);
   float mean, rstd;
   const double n = (double)a.L * (double)a.C;
   gn_mean_rstd(g.stats, m.b, n, g.eps, mean, rstd);
@@ -346,14 +367,24 @@ static int check_common(const of_rb_args* a, const char* who) {
   OF_REQUIRE(a->y_ld % 8 == 0, "%s: y_ld %% 8", who);
   return OF_OK;
 }
-static dim3 rb_grid(const of_rb_args* a) { return dim3((a->L + kRowsPerCta - 1) / kRowsPerCta, a->B); }
+// rows per CTA: enough CTAs for ~4 per SM, at least 2 rows per row-lane, at most 64 rows
+static int rb_rows_per_cta(const of_rb_args* a) {
+  const int rpar = kRbThreads / (a->C / 8) > 0 ? kRbThreads / (a->C / 8) : 1;
+  long long want = ((long long)a->B * a->L + 4 * device_sm_count() - 1) / (4 * device_sm_count());
+  int r = (int)want;
+  if (r < 2 * rpar) r = 2 * rpar;
+  if (r > 64) r = 64;
+  return r;
+}
+static dim3 rb_grid(const of_rb_args* a, int rpc) { return dim3((a->L + rpc - 1) / rpc, a->B); }
 
 }  // namespace ofx
 
 using namespace ofx;
 
-#define RB_LAUNCH(kernel, grid, threads)                                                                     \
-  kernel<<<grid, threads, (size_t)a->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(*a);       \
+#define RB_LAUNCH(kernel)                                                                                                    \
+  const int rpc = rb_rows_per_cta(a);                                                                                        \
+  kernel<<<rb_grid(a, rpc), kRbThreads, 5 * (size_t)a->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(*a, rpc); \
   OF_CHECK_CUDA(cudaGetLastError());                                              \
   count_launch();                                                                 \
   return OF_OK;
@@ -362,13 +393,23 @@ extern "C" int of_rb_apply_fwd(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_apply_fwd");
   if (rc) return rc;
   OF_REQUIRE(a->out_bf16 && a->out_bf16_ld % 8 == 0, "of_rb_apply_fwd: bad out_bf16");
-  RB_LAUNCH(rb_apply_fwd_kernel, rb_grid(a), kRbThreads)
+  RB_LAUNCH(rb_apply_fwd_kernel)
 }
 extern "C" int of_rb_rowdot(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_rowdot");
   if (rc) return rc;
   OF_REQUIRE(a->vec && a->out_rows, "of_rb_rowdot: null vec/out_rows");
-  RB_LAUNCH(rb_rowdot_kernel, dim3((a->L + 63) / 64, a->B), 256)
+  const int nv = (a->C / 8 + 31) / 32;
+  const int rows_per_warp = a->L >= 2048 ? 4 : 1;
+  dim3 grid((a->L + 8 * rows_per_warp - 1) / (8 * rows_per_warp), a->B);
+  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (nv <= 1) rb_rowdot_kernel<1><<<grid, 256, 0, st_>>>(*a, rows_per_warp);
+  else if (nv <= 2) rb_rowdot_kernel<2><<<grid, 256, 0, st_>>>(*a, rows_per_warp);
+  else if (nv <= 4) rb_rowdot_kernel<4><<<grid, 256, 0, st_>>>(*a, rows_per_warp);
+  else rb_rowdot_kernel<8><<<grid, 256, 0, st_>>>(*a, rows_per_warp);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
 }
 extern "C" int of_softmax_rows(float* rows, int B, int L, void* stream) {
   OF_REQUIRE(rows && B >= 1 && L >= 1, "of_softmax_rows: bad args");
@@ -388,19 +429,19 @@ extern "C" int of_rb_pool(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_pool");
   if (rc) return rc;
   OF_REQUIRE(a->p && a->acc_bc, "of_rb_pool: null p/acc_bc");
-  RB_LAUNCH(rb_pool_kernel, rb_grid(a), kRbThreads)
+  RB_LAUNCH(rb_pool_kernel)
 }
 extern "C" int of_rb_gate_fwd(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_gate_fwd");
   if (rc) return rc;
   OF_REQUIRE(a->gate && (a->res_f32 || a->res_bf16) && (a->out_f32 || a->out_bf16), "of_rb_gate_fwd: null gate/res/out");
-  RB_LAUNCH(rb_gate_fwd_kernel, rb_grid(a), kRbThreads)
+  RB_LAUNCH(rb_gate_fwd_kernel)
 }
 extern "C" int of_rb_gate_bwd_reduce(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_gate_bwd_reduce");
   if (rc) return rc;
   OF_REQUIRE(a->dout_f32 && a->acc_bc, "of_rb_gate_bwd_reduce: null dout/acc");
-  RB_LAUNCH(rb_gate_bwd_reduce_kernel, rb_grid(a), kRbThreads)
+  RB_LAUNCH(rb_gate_bwd_reduce_kernel)
 }
 extern "C" int of_rb_bwd_pass1(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_bwd_pass1");
@@ -411,11 +452,11 @@ extern "C" int of_rb_bwd_pass1(const of_rb_args* a, void* stream) {
     OF_REQUIRE(a->dout_f32 && a->gate && a->dpooled && a->p && a->da && a->wk && a->dwk, "of_rb_bwd_pass1(mode 0): null inputs");
   else
     OF_REQUIRE(a->dh_bf16, "of_rb_bwd_pass1(mode 1): null dh");
-  RB_LAUNCH(rb_bwd_pass1_kernel, rb_grid(a), kRbThreads)
+  RB_LAUNCH(rb_bwd_pass1_kernel)
 }
 extern "C" int of_rb_bwd_apply(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_bwd_apply");
   if (rc) return rc;
   OF_REQUIRE(a->dxhat_bf16 && a->dstats && a->dy_bf16, "of_rb_bwd_apply: null pointers");
-  RB_LAUNCH(rb_bwd_apply_kernel, rb_grid(a), kRbThreads)
+  RB_LAUNCH(rb_bwd_apply_kernel)
 }
