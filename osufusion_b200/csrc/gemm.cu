@@ -225,9 +225,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int c = chalf; c < p.BN / 32; c += 2) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c * 32, v);
-          tmem_wait_ld();
           const int nb = tc.n0 + c * 32;
-          if (row_ok && nb < p.N) {
+          const bool chunk_ok = row_ok && nb < p.N;
+          // Issue every global load of this chunk BEFORE waiting on the TMEM load, so their latency overlaps instead of being
+          // paid once per 8-column group.
+          float4 bz[8], ax[8];
+          uint4 ah[4];
+          if (chunk_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = nb + g * 8;
+              const bool ok = n < p.N;
+              if (p.bias && ok) {
+                bz[2 * g] = *reinterpret_cast<const float4*>(p.bias + n);
+                bz[2 * g + 1] = *reinterpret_cast<const float4*>(p.bias + n + 4);
+              } else {
+                bz[2 * g] = bz[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (aux32 && ok) {
+                ax[2 * g] = *reinterpret_cast<const float4*>(aux32 + n);
+                ax[2 * g + 1] = *reinterpret_cast<const float4*>(aux32 + n + 4);
+              } else {
+                ax[2 * g] = ax[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (aux16 && ok) ah[g] = *reinterpret_cast<const uint4*>(aux16 + n);
+              else ah[g] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          tmem_wait_ld();
+          if (chunk_ok) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const int n = nb + g * 8;
@@ -235,33 +261,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 float f[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = k_nonempty ? __uint_as_float(v[g * 8 + j]) : 0.f;
-                if (p.bias) {
-                  float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
-                  float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (aux32) {
-                  float4 a0 = *reinterpret_cast<const float4*>(aux32 + n);
-                  float4 a1 = *reinterpret_cast<const float4*>(aux32 + n + 4);
-                  f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
-                  f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
-                }
+                f[0] += bz[2 * g].x + ax[2 * g].x; f[1] += bz[2 * g].y + ax[2 * g].y;
+                f[2] += bz[2 * g].z + ax[2 * g].z; f[3] += bz[2 * g].w + ax[2 * g].w;
+                f[4] += bz[2 * g + 1].x + ax[2 * g + 1].x; f[5] += bz[2 * g + 1].y + ax[2 * g + 1].y;
+                f[6] += bz[2 * g + 1].z + ax[2 * g + 1].z; f[7] += bz[2 * g + 1].w + ax[2 * g + 1].w;
                 float x16[8];
-                if (aux16) {
-                  uint4 u = *reinterpret_cast<const uint4*>(aux16 + n);
-                  float2 t0 = unpack_bf16x2(u.x), t1 = unpack_bf16x2(u.y), t2 = unpack_bf16x2(u.z),
-                         t3 = unpack_bf16x2(u.w);
+                {
+                  float2 t0 = unpack_bf16x2(ah[g].x), t1 = unpack_bf16x2(ah[g].y), t2 = unpack_bf16x2(ah[g].z),
+                         t3 = unpack_bf16x2(ah[g].w);
                   x16[0] = t0.x; x16[1] = t0.y; x16[2] = t1.x; x16[3] = t1.y;
                   x16[4] = t2.x; x16[5] = t2.y; x16[6] = t3.x; x16[7] = t3.y;
-                  if (!p.aux_is_dsilu) {
+                }
+                if (aux16 && !p.aux_is_dsilu) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] += x16[j];
-                  }
+                  for (int j = 0; j < 8; ++j) f[j] += x16[j];
                 }
                 if (pre16) {
-                  st_global_v4(pre16 + n, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                               pack_bf16x2(f[6], f[7]));
+                  *reinterpret_cast<uint4*>(pre16 + n) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                                    pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
                 }
                 if (p.act == OF_ACT_SILU) {
 #pragma unroll
@@ -272,8 +289,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   for (int j = 0; j < 8; ++j) f[j] *= dsilu_f(x16[j]);
                 }
                 if (o16) {
-                  st_global_v4(o16 + n, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                               pack_bf16x2(f[6], f[7]));
+                  *reinterpret_cast<uint4*>(o16 + n) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
                 }
                 if (o32) {
                   *reinterpret_cast<float4*>(o32 + n) = make_float4(f[0], f[1], f[2], f[3]);
