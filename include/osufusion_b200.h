@@ -202,7 +202,8 @@ int of_softmax_bwd_rows(const float* p, float* rd, int B, int L, void* stream);
  *                        fp32 normed tensor (the residual of unet.py:141) and its bf16 copy for the q/kv GEMM.
  * of_rope_fwd/bwd      : RotaryPositionEmbedding.forward + apply_rotary_pos_emb/rotate_half (attention.py:52-58,
  *                        utils.py:25-32) applied in place to the q and k slots of the fused qkv buffer; the cos/sin
- *                        tables (L, D) are generated by the host exactly as the reference does (attention.py:33-49).
+ *                        tables (L, D) are generated by the host exactly as the reference does (attention.py:33-49): bf16 when
+ *                        q is bf16 (autocast), fp32 (table_f32=1, fp32 arithmetic) when a DoRA-adapted to_q promotes q to fp32.
  *                        bwd also converts the fp32 attention gradients to the bf16 (B, L, (H+2KVH)*D) layout.
  * of_linear_small_*    : nn.Linear with M <= 16 rows: time_mlp / cond_mlp (unet.py:356-366), FiLM heads
  *                        (residual.py:104-111), GlobalContext.layers 1x1 convs on the pooled (B,C,1) vector
@@ -228,11 +229,11 @@ int of_layernorm_fwd(const float* x, long long x_ld, int rows, int C, const floa
 int of_layernorm_bwd(const float* dy, long long dy_ld, const float* x, long long x_ld, int rows, int C, const float* gamma,
                      const float* mean_rstd, float* dx_f32, void* dx_bf16, long long dx_ld, float* dgamma, float* dbeta,
                      void* stream);
-int of_rope_fwd(void* qkv, long long ld, long long bs, int B, int L, int H, int KVH, int D, const void* cos_bf16,
-                const void* sin_bf16, void* stream);
+int of_rope_fwd(void* qkv, long long ld, long long bs, int B, int L, int H, int KVH, int D, const void* cos_tab,
+                const void* sin_tab, int table_f32, void* stream);
 int of_rope_bwd(const float* dq, long long dq_ld, long long dq_bs, const float* dk, const float* dv, long long dkv_ld,
                 long long dkv_bs, void* dqkv_bf16, long long out_ld, long long out_bs, int B, int L, int H, int KVH, int D,
-                const void* cos_bf16, const void* sin_bf16, void* stream);
+                const void* cos_tab, const void* sin_tab, int table_f32, void* stream);
 int of_linear_small_fwd(const float* x, long long x_ld, int M, int N, int K, const float* W, long long w_ld, const float* bias,
                         int act, int round_bf16, float* y, long long y_ld, float* ypre, void* stream);
 int of_linear_small_bwd(const float* dy, long long dy_ld, const float* ypre, int act, const float* x, long long x_ld, int M,
@@ -263,6 +264,20 @@ int of_pack_conv_weight(const float* w, int Cout, int Cin, int k, void* out, int
 int of_unpack_conv_wgrad(const float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw, int accumulate,
                          void* stream);
 int of_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LoRA / DoRA adapters.  Replace `LoraConv1d.forward` + `DoraConv1dLayer.forward` (lora_layers.py:59-92,292-328: base conv,
+ * a SECOND base conv scaled by (s-1), lora_B(lora_A(x))) and peft 0.12.0's DoRA nn.Linear path by one GEMM on the effective
+ * weight W_eff = s * (W + scaling * B A), s = magnitude / ||W + scaling B A||_2 (norm detached, lora_layers.py:76-79).
+ *   of_dora_merge : W (Cout,Cin,k) fp32, A (r,Cin,k), B (Cout,r), mag (Cout) or NULL (plain LoRA)  ->
+ *                   packed bf16 [k][Cout][Cin_pad] GEMM operand (tap stride given), n2_ws[Cout] = ||.||^2, s_out[Cout] (optional)
+ *   of_dora_grad  : dW_packed = d loss / d W_eff (fp32, same packed layout, from of_gemm WGRAD) -> dA, dB, dmag (accumulated)
+ * ------------------------------------------------------------------------------------------------ */
+int of_dora_merge(const float* W, const float* A, const float* B, const float* mag, float scaling, int Cout, int Cin, int k, int r,
+                  float* n2_ws, void* packed_bf16, int Cin_pad, long long tap_stride, float* s_out, void* stream);
+int of_dora_grad(const float* W, const float* A, const float* B, const float* mag, float scaling, int Cout, int Cin, int k, int r,
+                 const float* n2, const float* dW_packed, int Cin_pad, long long tap_stride, float* dA, float* dB, float* dmag,
+                 void* stream);
 
 #ifdef __cplusplus
 }

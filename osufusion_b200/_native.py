@@ -92,8 +92,8 @@ _SIGS = {
     "of_softmax_bwd_rows": [P, P, I, I, P],
     "of_layernorm_fwd": [P, LL, I, I, P, P, F, P, P, LL, P, P],
     "of_layernorm_bwd": [P, LL, P, LL, I, I, P, P, P, P, LL, P, P, P],
-    "of_rope_fwd": [P, LL, LL, I, I, I, I, I, P, P, P],
-    "of_rope_bwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, P, P, P],
+    "of_rope_fwd": [P, LL, LL, I, I, I, I, I, P, P, I, P],
+    "of_rope_bwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, P, P, I, P],
     "of_linear_small_fwd": [P, LL, I, I, I, P, LL, P, I, I, P, LL, P, P],
     "of_linear_small_bwd": [P, LL, P, I, P, LL, I, I, I, P, LL, I, P, P, P, LL, P],
     "of_colsum_bf16": [P, LL, LL, I, P, P],
@@ -110,6 +110,8 @@ _SIGS = {
     "of_pack_conv_weight": [P, I, I, I, P, I, I, I, P],
     "of_unpack_conv_wgrad": [P, I, I, I, I, I, P, I, P],
     "of_cast_f32_bf16": [P, P, LL, P],
+    "of_dora_merge": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P],
+    "of_dora_grad": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P, P, P],
 }
 EXPORTS = ["of_last_error", "of_version", "of_launch_count", "of_reset_launch_count", *_SIGS.keys()]
 

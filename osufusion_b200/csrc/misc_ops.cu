@@ -140,8 +140,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // =================================================================================================== RoPE
 // qkv (B, L, (H+2*KVH)*D) bf16; rotate the H q-slots and KVH k-slots in place, bf16 arithmetic as the reference
 // (x*cos, rotate_half(x)*sin and their sum are each rounded to bf16: utils.py:25-32 under autocast).
+__device__ __forceinline__ V8 ld_tab(const __nv_bfloat16* p) { return ld_bf16x8(p); }
+__device__ __forceinline__ V8 ld_tab(const float* p) { return ld_f32x8(p); }
+
+// TAB = __nv_bfloat16: tables in q's autocast dtype (attention.py:37-41) and bf16 intermediate rounding.
+// TAB = float: q is fp32 in the reference (DoRA-adapted to_q promotes its output to fp32), so tables and arithmetic are fp32.
+template <typename TAB>
 __global__ void rope_fwd_kernel(__nv_bfloat16* qkv, long long ld, long long bs, int B, int L, int slots, int D,
-                                const __nv_bfloat16* __restrict__ cosT, const __nv_bfloat16* __restrict__ sinT) {
+                                const TAB* __restrict__ cosT, const TAB* __restrict__ sinT) {
   const int tps = D >> 4;  // threads per slot (each handles 8 + 8 paired channels)
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * L * slots * tps;
@@ -154,23 +160,29 @@ __global__ void rope_fwd_kernel(__nv_bfloat16* qkv, long long ld, long long bs, 
   const int half = D >> 1;
   __nv_bfloat16* base = qkv + b * bs + (long long)l * ld + (long long)slot * D;
   V8 x1 = ld_bf16x8(base + tp * 8), x2 = ld_bf16x8(base + half + tp * 8);
-  V8 c1 = ld_bf16x8(cosT + (long long)l * D + tp * 8), c2 = ld_bf16x8(cosT + (long long)l * D + half + tp * 8);
-  V8 s1 = ld_bf16x8(sinT + (long long)l * D + tp * 8), s2 = ld_bf16x8(sinT + (long long)l * D + half + tp * 8);
+  V8 c1 = ld_tab(cosT + (long long)l * D + tp * 8), c2 = ld_tab(cosT + (long long)l * D + half + tp * 8);
+  V8 s1 = ld_tab(sinT + (long long)l * D + tp * 8), s2 = ld_tab(sinT + (long long)l * D + half + tp * 8);
   V8 o1, o2;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    o1.v[j] = bf16_round(x1.v[j] * c1.v[j]) + bf16_round(-x2.v[j] * s1.v[j]);
-    o2.v[j] = bf16_round(x2.v[j] * c2.v[j]) + bf16_round(x1.v[j] * s2.v[j]);
+    if (sizeof(TAB) == 2) {
+      o1.v[j] = bf16_round(x1.v[j] * c1.v[j]) + bf16_round(-x2.v[j] * s1.v[j]);
+      o2.v[j] = bf16_round(x2.v[j] * c2.v[j]) + bf16_round(x1.v[j] * s2.v[j]);
+    } else {
+      o1.v[j] = x1.v[j] * c1.v[j] - x2.v[j] * s1.v[j];
+      o2.v[j] = x2.v[j] * c2.v[j] + x1.v[j] * s2.v[j];
+    }
   }
   st_bf16x8(base + tp * 8, o1);
   st_bf16x8(base + half + tp * 8, o2);
 }
 
 // dq32 (B,L,H*D), dk32/dv32 (B,L,KVH*D) fp32 -> dqkv16 (B,L,(H+2KVH)*D) bf16, undoing the rotation on q and k slots.
+template <typename TAB>
 __global__ void rope_bwd_kernel(const float* __restrict__ dq, long long dq_ld, long long dq_bs, const float* __restrict__ dk,
                                 const float* __restrict__ dv, long long dkv_ld, long long dkv_bs, __nv_bfloat16* out,
                                 long long out_ld, long long out_bs, int B, int L, int H, int KVH, int D,
-                                const __nv_bfloat16* __restrict__ cosT, const __nv_bfloat16* __restrict__ sinT) {
+                                const TAB* __restrict__ cosT, const TAB* __restrict__ sinT) {
   const int tps = D >> 4;
   const int slots = H + 2 * KVH;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,8 +200,8 @@ __global__ void rope_bwd_kernel(const float* __restrict__ dq, long long dq_ld, l
   else src = dv + b * dkv_bs + (long long)l * dkv_ld + (long long)(slot - H - KVH) * D;
   V8 g1 = ld_f32x8(src + tp * 8), g2 = ld_f32x8(src + half + tp * 8), o1, o2;
   if (slot < H + KVH) {
-    V8 c1 = ld_bf16x8(cosT + (long long)l * D + tp * 8), c2 = ld_bf16x8(cosT + (long long)l * D + half + tp * 8);
-    V8 s1 = ld_bf16x8(sinT + (long long)l * D + tp * 8), s2 = ld_bf16x8(sinT + (long long)l * D + half + tp * 8);
+    V8 c1 = ld_tab(cosT + (long long)l * D + tp * 8), c2 = ld_tab(cosT + (long long)l * D + half + tp * 8);
+    V8 s1 = ld_tab(sinT + (long long)l * D + tp * 8), s2 = ld_tab(sinT + (long long)l * D + half + tp * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // y1 = x1*c1 - x2*s1 ; y2 = x2*c2 + x1*s2  =>  dx1 = g1*c1 + g2*s2 ; dx2 = g2*c2 - g1*s1
@@ -682,27 +694,37 @@ extern "C" int of_layernorm_bwd(const float* dy, long long dy_ld, const float* x
   DONE()
 }
 
-extern "C" int of_rope_fwd(void* qkv, long long ld, long long bs, int B, int L, int H, int KVH, int D, const void* cos_bf16,
-                           const void* sin_bf16, void* stream) {
-  OF_REQUIRE(qkv && cos_bf16 && sin_bf16, "of_rope_fwd: null pointer");
+extern "C" int of_rope_fwd(void* qkv, long long ld, long long bs, int B, int L, int H, int KVH, int D, const void* cos_tab,
+                           const void* sin_tab, int table_f32, void* stream) {
+  OF_REQUIRE(qkv && cos_tab && sin_tab, "of_rope_fwd: null pointer");
   OF_REQUIRE(D % 16 == 0 && ld % 8 == 0, "of_rope_fwd: D=%d must be a multiple of 16", D);
   long long total = (long long)B * L * (H + KVH) * (D / 16);
-  rope_fwd_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<__nv_bfloat16*>(qkv), ld, bs, B, L, H + KVH, D,
-                                                              reinterpret_cast<const __nv_bfloat16*>(cos_bf16),
-                                                              reinterpret_cast<const __nv_bfloat16*>(sin_bf16));
+  if (table_f32)
+    rope_fwd_kernel<float><<<blocks_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<__nv_bfloat16*>(qkv), ld, bs, B, L, H + KVH, D,
+                                                                       reinterpret_cast<const float*>(cos_tab),
+                                                                       reinterpret_cast<const float*>(sin_tab));
+  else
+    rope_fwd_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, STREAM>>>(
+        reinterpret_cast<__nv_bfloat16*>(qkv), ld, bs, B, L, H + KVH, D, reinterpret_cast<const __nv_bfloat16*>(cos_tab),
+        reinterpret_cast<const __nv_bfloat16*>(sin_tab));
   DONE()
 }
 
 extern "C" int of_rope_bwd(const float* dq, long long dq_ld, long long dq_bs, const float* dk, const float* dv, long long dkv_ld,
                            long long dkv_bs, void* dqkv_bf16, long long out_ld, long long out_bs, int B, int L, int H, int KVH,
-                           int D, const void* cos_bf16, const void* sin_bf16, void* stream) {
-  OF_REQUIRE(dq && dk && dv && dqkv_bf16 && cos_bf16 && sin_bf16, "of_rope_bwd: null pointer");
+                           int D, const void* cos_tab, const void* sin_tab, int table_f32, void* stream) {
+  OF_REQUIRE(dq && dk && dv && dqkv_bf16 && cos_tab && sin_tab, "of_rope_bwd: null pointer");
   OF_REQUIRE(D % 16 == 0, "of_rope_bwd: D=%d must be a multiple of 16", D);
   long long total = (long long)B * L * (H + 2 * KVH) * (D / 16);
-  rope_bwd_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs,
-                                                              reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), out_ld, out_bs, B, L, H,
-                                                              KVH, D, reinterpret_cast<const __nv_bfloat16*>(cos_bf16),
-                                                              reinterpret_cast<const __nv_bfloat16*>(sin_bf16));
+  if (table_f32)
+    rope_bwd_kernel<float><<<blocks_for(total, 256), 256, 0, STREAM>>>(dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs,
+                                                                       reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), out_ld, out_bs, B, L,
+                                                                       H, KVH, D, reinterpret_cast<const float*>(cos_tab),
+                                                                       reinterpret_cast<const float*>(sin_tab));
+  else
+    rope_bwd_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, STREAM>>>(
+        dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), out_ld, out_bs, B, L, H, KVH, D,
+        reinterpret_cast<const __nv_bfloat16*>(cos_tab), reinterpret_cast<const __nv_bfloat16*>(sin_tab));
   DONE()
 }
 

@@ -69,7 +69,8 @@ class GradAllReducer:
         self.unet, self.group, self.overlap = unet, group, overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         params = [p for p in backward_param_order(unet) if p.requires_grad]
-        total = sum(p.numel() for p in params)
+        ALIGN = 32                      # floats: every gradient view starts 128-byte aligned (kernels use 16-byte vector atomics)
+        total = sum((p.numel() + ALIGN - 1) // ALIGN * ALIGN for p in params)
         dev = params[0].device
         self.arena = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views = {}
@@ -79,7 +80,7 @@ class GradAllReducer:
         for p in params:
             self.views[id(p)] = self.arena[off:off + p.numel()].view(p.shape)
             b_ids.append(id(p))
-            off += p.numel()
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
             if (off - b_start) * 4 >= bucket_bytes:
                 self.buckets.append((b_start, off, b_ids))
                 b_start, b_ids = off, []

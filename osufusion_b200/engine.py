@@ -113,6 +113,15 @@ def colsum(dy16: torch.Tensor, out: torch.Tensor) -> None:
         N.call("of_colsum_bf16", _p(dy16), ld, B * L, Nn, _p(out))
 
 
+def _base(m):
+    """The nn.Conv1d / nn.Linear holding the (possibly frozen) base weight: adapters wrap it as `.base_layer` (peft naming)."""
+    return getattr(m, "base_layer", m)
+
+
+def _adapter(m):
+    return m if hasattr(m, "base_layer") else None
+
+
 # ------------------------------------------------------------------------------------------------ parameter staging
 class ParamStore:
     """bf16 GEMM-operand copies of the fp32 master parameters and the fp32 gradient buffers the kernels accumulate into.
@@ -204,6 +213,66 @@ class ParamStore:
             return out
         return self._cached(("padrows", id(w), rows), (w,), build)
 
+    # ---- LoRA / DoRA: effective weights W_eff = s * (W + scaling * B A) merged straight into the GEMM operand layout
+    def _dora_merge_into(self, ad, out_rows: torch.Tensor, cin_pad: int, tap_stride: int):
+        base = ad.base_layer
+        W = base.weight
+        Cout, Cin = W.shape[0], W.shape[1]
+        k = W.shape[2] if W.dim() == 3 else 1
+        A, Bm, mag = ad.lora_A["default"].weight, ad.lora_B["default"].weight, ad.magnitude()
+        n2 = empty((Cout,), F32, W.device)
+        N.call("of_dora_merge", _p(W), _p(A), _p(Bm), _p(mag), float(ad.scaling), Cout, Cin, k, ad.r, _p(n2), out_rows.data_ptr(),
+               cin_pad, tap_stride, None)
+        return n2
+
+    def conv_w_mod(self, conv) -> torch.Tensor:
+        """GEMM operand of a (possibly adapted) Conv1d: [k][Cout][Cin_pad] bf16."""
+        ad = _adapter(conv)
+        if ad is None:
+            return self.conv_w(conv.weight)
+        W = ad.base_layer.weight
+        ps = (W, ad.lora_A["default"].weight, ad.lora_B["default"].weight) + ((ad.magnitude(),) if ad.use_dora else ())
+
+        def build():
+            Cout, Cin, k = W.shape
+            cp = (Cin + 7) // 8 * 8
+            out = zeros((k, Cout, cp), BF16, W.device) if cp != Cin else empty((k, Cout, cp), BF16, W.device)
+            n2 = self._dora_merge_into(ad, out, cp, Cout * cp)
+            return out, n2
+        return self._cached(("dconv", id(W)), ps, build)[0]
+
+    def dora_n2(self, mod):
+        W = mod.base_layer.weight
+        hit = self.cache.get(("dconv", id(W))) or self.cache.get(("dlin", id(W)))
+        return hit[1][1]
+
+    def linear_w_mods(self, *mods) -> torch.Tensor:
+        """[sum N_i][K] bf16 row-concatenation of (possibly adapted) Linear weights."""
+        if all(_adapter(m) is None for m in mods):
+            return self.linear_w(*[m.weight for m in mods])
+        ps = []
+        for m in mods:
+            ad = _adapter(m)
+            ps += [_base(m).weight] + ([ad.lora_A["default"].weight, ad.lora_B["default"].weight] if ad is not None else [])
+            if ad is not None and ad.use_dora:
+                ps.append(ad.magnitude())
+
+        def build():
+            K = _base(mods[0]).weight.shape[1]
+            out = empty((sum(_base(m).weight.shape[0] for m in mods), K), BF16, _base(mods[0]).weight.device)
+            r = 0
+            for m in mods:
+                w = _base(m).weight
+                ad = _adapter(m)
+                if ad is None:
+                    N.call("of_cast_f32_bf16", _p(w), out[r:].data_ptr(), w.numel())
+                else:
+                    n2 = self._dora_merge_into(ad, out[r:], K, w.shape[0] * K)
+                    self.cache[("dlin", id(w))] = (None, (None, n2), self.epoch)
+                r += w.shape[0]
+            return out
+        return self._cached(("linm",) + tuple(id(_base(m).weight) for m in mods), tuple(ps), build)
+
     # ---- gradient buffers (fp32, zero-initialised, torch layout) handed back to autograd at the end of backward
     def existing_grad(self, p: torch.nn.Parameter):
         """The gradient buffer of p if one exists already (arena view or earlier contribution), else None."""
@@ -214,6 +283,12 @@ class ParamStore:
             g = self.arena_views[id(p)]
             self.grads[id(p)] = g
         return g
+
+    def grad_opt(self, p):
+        """Gradient buffer of p, or None when p is absent / frozen (kernels skip NULL outputs)."""
+        if p is None or not p.requires_grad:
+            return None
+        return self.grad(p)
 
     def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
         g = self.existing_grad(p)
@@ -236,6 +311,38 @@ class ParamStore:
 
 
 # ------------------------------------------------------------------------------------------------ GEMM-shaped layers
+def _dora_backward(store: ParamStore, ad, dW_packed: torch.Tensor, cin_pad: int, tap_stride: int) -> None:
+    base = ad.base_layer
+    W = base.weight
+    Cout, Cin = W.shape[0], W.shape[1]
+    k = W.shape[2] if W.dim() == 3 else 1
+    A, Bm, mag = ad.lora_A["default"].weight, ad.lora_B["default"].weight, ad.magnitude()
+    n2 = store.dora_n2(ad) if mag is not None else None
+    N.call("of_dora_grad", _p(W), _p(A), _p(Bm), _p(mag), float(ad.scaling), Cout, Cin, k, ad.r, _p(n2), _p(dW_packed), cin_pad,
+           tap_stride, store.grad(A).data_ptr(), store.grad(Bm).data_ptr(), _p(store.grad(mag)) if mag is not None else None)
+
+
+def _wgrad_conv_mod(store: ParamStore, conv, dy16, x16, taps, shift0):
+    ad = _adapter(conv)
+    if ad is None:
+        return _wgrad_conv(store, conv.weight, dy16, x16, taps, shift0)
+    Cout, Cin, k = ad.base_layer.weight.shape
+    cp = (Cin + 7) // 8 * 8
+    tmp = zeros((k, Cout, cp), F32, dy16.device)
+    R.gemm_wgrad(dy16, x16, tmp, M=Cout, N_out=cp, taps=taps, shift0=shift0, shift_step=1)
+    _dora_backward(store, ad, tmp, cp, Cout * cp)
+
+
+def _wgrad_linear_mod(store: ParamStore, lin, dy16, x16):
+    ad = _adapter(lin)
+    if ad is None:
+        return _wgrad_linear(store, lin.weight, dy16, x16)
+    Nn, K = ad.base_layer.weight.shape
+    tmp = zeros((1, Nn, K), F32, dy16.device)
+    R.gemm_wgrad(dy16, x16, tmp, M=Nn, N_out=K)
+    _dora_backward(store, ad, tmp, K, Nn * K)
+
+
 def _wgrad_conv(store: ParamStore, w: torch.nn.Parameter, dy16, x16, taps, shift0):
     """Conv1d weight gradient: packed [k][Cout][Cin_pad] fp32 accumulation, then back to the (Cout, Cin, k) layout."""
     if not w.requires_grad:
@@ -298,18 +405,19 @@ class Ctx:
 def conv3(ctx: Ctx, x16, conv, *, stats=None, out=None):
     """nn.Conv1d(k=3, padding=1) as implicit GEMM; returns bf16 (B, L, Cout)."""
     B, L, _ = x16.shape
-    Cout, Cin, k = conv.weight.shape
-    w = ctx.store.conv_w(conv.weight)
+    base = _base(conv)
+    Cout, Cin, k = base.weight.shape
+    w = ctx.store.conv_w_mod(conv)
     y = out if out is not None else empty((B, L, Cout), BF16, ctx.device)
-    R.gemm_fwd(x16, w, N_out=Cout, K=w.shape[2], taps=k, shift0=-(k // 2), shift_step=1, bias=conv.bias, out_bf16=y, stats=stats)
+    R.gemm_fwd(x16, w, N_out=Cout, K=w.shape[2], taps=k, shift0=-(k // 2), shift_step=1, bias=base.bias, out_bf16=y, stats=stats)
     return y
 
 
 def conv3_bwd(ctx: Ctx, conv, x: Act, x16, dy16, need_dx=True, want_bf16=False, want_f32=True):
-    Cout, Cin, k = conv.weight.shape
-    _wgrad_conv(ctx.store, conv.weight, dy16, x16, taps=k, shift0=-(k // 2))
+    Cout, Cin, k = _base(conv).weight.shape
+    _wgrad_conv_mod(ctx.store, conv, dy16, x16, taps=k, shift0=-(k // 2))
     if need_dx:
-        w = ctx.store.conv_w(conv.weight)
+        w = ctx.store.conv_w_mod(conv)
         return _dgrad_into(x, dy16, w, N_out=Cin, K=Cout, taps=k, shift0=k // 2, shift_step=-1, b_ld=w.shape[2],
                            want_bf16=want_bf16, want_f32=want_f32)
     return None
@@ -332,7 +440,7 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
     st, dev = ctx.store, ctx.device
     x16 = x.bf16
     B, L, Cin = x16.shape
-    Cout = m.block1.proj.weight.shape[0]
+    Cout = _base(m.block1.proj).weight.shape[0]
     ss = None
     if m.mlp is not None:
         ss, _ = linear_small_fwd(ctx.emb_act, m.mlp[1].weight, m.mlp[1].bias)
@@ -398,9 +506,9 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             N.call("of_rb_gate_bwd_reduce", C.byref(b2))
             # gate MLP backward
             dg1 = zeros((B, Wa.shape[0]), F32, dev)
-            linear_small_bwd(dgate, gatepre, 2, g1, Wb.view(Wb.shape[0], -1), st.grad(Wb), st.grad(se.layers[2].bias), dg1)
+            linear_small_bwd(dgate, gatepre, 2, g1, Wb.view(Wb.shape[0], -1), st.grad_opt(Wb), st.grad_opt(se.layers[2].bias), dg1)
             dpooled = zeros((B, Cout), F32, dev)
-            linear_small_bwd(dg1, g1pre, 1, pooled, Wa.view(Wa.shape[0], -1), st.grad(Wa), st.grad(se.layers[0].bias), dpooled)
+            linear_small_bwd(dg1, g1pre, 1, pooled, Wa.view(Wa.shape[0], -1), st.grad_opt(Wa), st.grad_opt(se.layers[0].bias), dpooled)
             # d logits
             da = empty((B, L), F32, dev)
             b2.mode = 1
@@ -427,7 +535,7 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             dy2 = empty((B, L, Cout), BF16, dev)
             b2.dy_bf16 = dy2.data_ptr()
             b2.dy_bs, b2.dy_ld = _bl(dy2)
-            b2.dbias = st.grad(m.block2.proj.bias).data_ptr()
+            b2.dbias = _p(st.grad_opt(_base(m.block2.proj).bias))
             N.call("of_rb_bwd_apply", C.byref(b2))
             # conv2 backward
             h1a = Act(None, h1)
@@ -451,7 +559,7 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             dy1 = dy2  # reuse
             b1.dy_bf16 = dy1.data_ptr()
             b1.dy_bs, b1.dy_ld = _bl(dy1)
-            b1.dbias = st.grad(m.block1.proj.bias).data_ptr()
+            b1.dbias = _p(st.grad_opt(_base(m.block1.proj).bias))
             N.call("of_rb_bwd_apply", C.byref(b1))
             # input gradient: identity residual (adopt dout) or res_conv dgrad, then conv1 dgrad accumulated in place
             if has_res:
@@ -463,21 +571,23 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             conv3_bwd(ctx, m.block1.proj, x, x16, dy1)
             if ss is not None:
                 W = m.mlp[1].weight
-                linear_small_bwd(dss, None, 0, ctx.emb_act, W, st.grad(W), st.grad(m.mlp[1].bias), ctx.d_emb_act)
+                linear_small_bwd(dss, None, 0, ctx.emb_act, W, st.grad_opt(W), st.grad_opt(m.mlp[1].bias), ctx.d_emb_act)
         ctx.tape.push(backward)
     return out
 
 
 # ------------------------------------------------------------------------------------------------ TransformerBlock
-def rope_tables(ctx: Ctx, L: int, D: int, scale_base: int):
-    """cos/sin (L, D) bf16 generated exactly like attention.py:33-49 does under bf16 autocast (tables in q's dtype)."""
-    key = (L, D, scale_base)
+def rope_tables(ctx: Ctx, L: int, D: int, scale_base: int, f32: bool = False):
+    """cos/sin (L, D) generated exactly like attention.py:33-49: in q's dtype — bf16 under autocast, fp32 when a DoRA-adapted
+    to_q has promoted q to fp32 (peft: `(mag/norm - 1) * F.linear(x, W)` is fp32 x bf16 -> fp32)."""
+    dt = F32 if f32 else BF16
+    key = (L, D, scale_base, f32)
     hit = ctx.rope_cache.get(key)
     if hit is None:
         inv_freq = 1.0 / (10000 ** (torch.arange(0, D, 2, device=ctx.device).float() / D))
-        t = torch.arange(L, dtype=BF16, device=ctx.device)
+        t = torch.arange(L, dtype=dt, device=ctx.device)
         t *= scale_base / L
-        freqs = torch.einsum("i,j->ij", t, inv_freq.to(BF16))
+        freqs = torch.einsum("i,j->ij", t, inv_freq.to(dt))
         emb = torch.cat([freqs, freqs], dim=-1)
         hit = (emb.cos().contiguous(), emb.sin().contiguous())
         ctx.rope_cache[key] = hit
@@ -499,12 +609,14 @@ def transformer_block(ctx: Ctx, m, x: Act) -> Act:
     mr = empty((rows, 2), F32, dev)
     N.call("of_layernorm_fwd", _p(x32), x32.stride(1), rows, Cc, _p(at.norm.weight), _p(at.norm.bias), at.norm.eps,
            _p(xn32), _p(xn16), Cc, _p(mr))
-    wqkv = st.linear_w(at.to_q.weight, at.to_kv.weight)
+    wqkv = st.linear_w_mods(at.to_q, at.to_kv)
     qkv = empty((B, L, HD + 2 * KD), BF16, dev)
     R.gemm_fwd(xn16, wqkv, N_out=HD + 2 * KD, K=Cc, out_bf16=qkv)
-    cosT, sinT = rope_tables(ctx, L, D, at.rotary_emb.scale_base)
+    ad_q = _adapter(at.to_q)
+    rope_f32 = ad_q is not None and ad_q.use_dora
+    cosT, sinT = rope_tables(ctx, L, D, at.rotary_emb.scale_base, rope_f32)
     q_bs, q_ld = _bl(qkv)
-    N.call("of_rope_fwd", _p(qkv), q_ld, q_bs, B, L, H, KVH, D, _p(cosT), _p(sinT))
+    N.call("of_rope_fwd", _p(qkv), q_ld, q_bs, B, L, H, KVH, D, _p(cosT), _p(sinT), int(rope_f32))
     q, k, v = qkv[:, :, :HD], qkv[:, :, HD:HD + KD], qkv[:, :, HD + KD:]
     o16 = empty((B, L, HD), BF16, dev)
     lse = empty((B, H, L), F32, dev)
@@ -555,11 +667,11 @@ def transformer_block(ctx: Ctx, m, x: Act) -> Act:
             dkv_bs, dkv_ld = _bl(dkv)
             o_bs, o_ld = _bl(dqkv)
             N.call("of_rope_bwd", _p(dq), dq_ld, dq_bs, dkv[:, :, :KD].data_ptr(), dkv[:, :, KD:].data_ptr(), dkv_ld, dkv_bs,
-                   _p(dqkv), o_ld, o_bs, B, L, H, KVH, D, _p(cosT), _p(sinT))
+                   _p(dqkv), o_ld, o_bs, B, L, H, KVH, D, _p(cosT), _p(sinT), int(rope_f32))
             # q/kv projections: d(xn) = residual grad (x2.grad) + dqkv W
             _dgrad_into(x2, dqkv, wqkv, N_out=Cc, K=HD + 2 * KD)
-            _wgrad_linear(st, at.to_q.weight, dqkv[:, :, :HD], xn16)
-            _wgrad_linear(st, at.to_kv.weight, dqkv[:, :, HD:], xn16)
+            _wgrad_linear_mod(st, at.to_q, dqkv[:, :, :HD], xn16)
+            _wgrad_linear_mod(st, at.to_kv, dqkv[:, :, HD:], xn16)
             # LayerNorm
             dxn = x2.grad
             assert dxn.stride(0) == L * dxn.stride(1)
