@@ -205,23 +205,22 @@ def run_ours(args) -> None:
     h2d = hx.numel() * 4 + ha.numel() * 4 + hc.numel() * 4
 
     # ---- roofline of the dominant kernel family: one instrumented eager step with CUDA events around every launch
+    # (every rank runs it so that the gradient all-reduces stay matched; rank 0 reports)
     roof = None
+    del loss
+    model.zero_grad(set_to_none=True)
+    NN.PROFILE = []
+    l2 = model(dx, da, dc)
+    l2.backward()
+    torch.cuda.synchronize()
     if rank == 0:
         tf_peak, hbm_peak, how = peaks()
-        del loss
-        model.zero_grad(set_to_none=True)
-        NN.PROFILE = []
-        l2 = model(dx, da, dc)
-        l2.backward()
-        torch.cuda.synchronize()
         agg = {}
         for name, flops, ev0, ev1, _tag in NN.PROFILE:
             d = agg.setdefault(name, [0.0, 0.0, 0])
             d[0] += ev0.elapsed_time(ev1)
             d[1] += flops
             d[2] += 1
-        NN.PROFILE = None
-        del l2
         top = max(agg.items(), key=lambda kv: kv[1][0])
         name, (tms, fl, cnt) = top
         ach = fl / (tms * 1e-3) / 1e12
@@ -230,6 +229,8 @@ def run_ours(args) -> None:
                 "families_ms": {k: round(v[0], 3) for k, v in agg.items()},
                 "families_tflops": {k: round(v[1] / (v[0] * 1e-3) / 1e12, 1) for k, v in agg.items() if v[0] > 0}}
 
+    NN.PROFILE = None
+    del l2
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cores, _ = cpu_reference_step_time(size, args.ref_frames, 1, 0)
@@ -251,8 +252,90 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step * args.steps),
             "model_tflops_per_gpu": step_tflop / (ms * 1e-3), "mfu_vs_measured_peak": step_tflop / (ms * 1e-3) / tf_peak,
-            "roofline": roof, "cpu_baseline": cpu, "loss": float(step.loss),
+            "roofline": roof, "cpu_baseline": cpu, "loss": float(step.loss.detach()),
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ sampling (metric 2)
+def run_sampling(args) -> None:
+    """End-to-end sampling beatmap-frames/s (BASELINE.json configs[3]): complete DDIM loop (35 steps, CFG -> 70 denoiser
+    evaluations), batch-sharded across ranks with no collective."""
+    import torch.distributed as dist
+
+    from osufusion_b200 import _native as NN
+    from osufusion_b200.models import DiffusionOsuFusion
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, n, size = args.batch, args.frames, args.size
+    torch.manual_seed(0)
+    model = DiffusionOsuFusion(SIZES[size]).to(dev).eval()
+    torch.nn.init.normal_(model.unet.final_conv.weight, std=0.02)
+    x, a, c = synth_batch(B, n, 1234 + rank)
+    ha, hc, hx = a.pin_memory(), c.pin_memory(), x.pin_memory()
+    hout = torch.empty(B, 6, n).pin_memory()
+
+    def one_song():
+        da, dc, dx = ha.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), hx.to(dev, non_blocking=True)
+        y = model.sample(da, dc, dx, cond_scale=args.cond_scale)
+        hout.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        one_song()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    NN.lib().of_reset_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        one_song()
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms, wall_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall_ms = float(t[0]), float(t[1])
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        tf_peak, _, how = peaks()
+        fwd = {("S", 32768): 53.97, ("L", 32768): 66.18, ("S", 4096): 0.974, ("L", 4096): 2.5, ("S", 65536): 213.5}.get((size, n))
+        evals = model.sampling_timesteps * (2 if args.cond_scale != 1.0 else 1)
+        line = {
+            "metric": "sampling beatmap-frames/s", "value": B * world * n / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"CFG-{size} dim_h={SIZES[size]} full DDIM sampling loop, {model.sampling_timesteps} steps, "
+                                   f"cond_scale={args.cond_scale} ({evals} denoiser evaluations), audio encoder cached",
+                       "songs_per_gpu": B, "frames": n, "parallelism": f"replicas x{world} (no collective)",
+                       "l2": "per-evaluation working set >> 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": B * world * n / (wall_ms * 1e-3), "unit": "frames/s", "ms_per_step": wall_ms,
+                    "h2d_bytes_per_step": (ha.numel() + hc.numel() + hx.numel()) * 4, "d2h_bytes_per_step": hout.numel() * 4},
+            "gpu_launches": int(NN.lib().of_launch_count()),
+        }
+        if fwd is not None:
+            tfl = evals * fwd * B / (ms * 1e-3)
+            line["algorithmic_tflops_per_gpu"] = tfl
+            line["roofline"] = {"kernel": "attn_fwd_kernel + gemm_kernel (whole sampler)", "bound": "tensor", "achieved": tfl,
+                                "peak": tf_peak, "unit": "TFLOP/s", "frac": tfl / tf_peak, "traffic": None,
+                                "note": f"algorithmic FLOPs = {evals} x F_fwd (reference's count; the cached audio encoder removes work)",
+                                "peak_source": how}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -269,9 +352,13 @@ def main() -> None:
     ap.add_argument("--frames", type=int, default=4096)
     ap.add_argument("--ref-frames", type=int, default=1024, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "sample"], help="train: fwd+bwd samples/s; sample: frames/s")
+    ap.add_argument("--cond-scale", type=float, default=2.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "sample":
+        run_sampling(args)
     else:
         run_ours(args)
 

@@ -225,6 +225,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int i = 0; i < n; ++i) {
       const int qrow = i * 128 + row;
       const bool q_ok = qrow < p.L;
+      const bool tile_full = (i * 128 + 128 <= p.L) && (k0 + 128 <= p.L);
       const float lse2 = q_ok ? p.lse[bh * p.L + qrow] : 0.f;
       const float dlt = q_ok ? p.delta[bh * p.L + qrow] : 0.f;
       // ---- stage A: P = exp2(S*scale*log2e - lse2)
@@ -241,13 +242,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
+        if (tile_full) {   // whole 128x128 tile valid: no per-element masking on the hot path
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float p0 = ex2b(fmaf(__uint_as_float(s[2 * e]), p.scale_log2, -lse2));
-          float p1 = ex2b(fmaf(__uint_as_float(s[2 * e + 1]), p.scale_log2, -lse2));
-          if (!q_ok || key_base + 2 * e >= p.L) p0 = 0.f;
-          if (!q_ok || key_base + 2 * e + 1 >= p.L) p1 = 0.f;
-          pk[e] = pack_bf16x2(p0, p1);
+          for (int e = 0; e < 32; ++e) {
+            const float p0 = ex2b(fmaf(__uint_as_float(s[2 * e]), p.scale_log2, -lse2));
+            const float p1 = ex2b(fmaf(__uint_as_float(s[2 * e + 1]), p.scale_log2, -lse2));
+            pk[e] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float p0 = ex2b(fmaf(__uint_as_float(s[2 * e]), p.scale_log2, -lse2));
+            float p1 = ex2b(fmaf(__uint_as_float(s[2 * e + 1]), p.scale_log2, -lse2));
+            if (!q_ok || key_base + 2 * e >= p.L) p0 = 0.f;
+            if (!q_ok || key_base + 2 * e + 1 >= p.L) p1 = 0.f;
+            pk[e] = pack_bf16x2(p0, p1);
+          }
         }
       }
       mbar_wait(p_empty, (i & 1) ^ 1);   // dV MMA of the previous tile has finished reading sP

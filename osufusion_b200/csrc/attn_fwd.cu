@@ -16,7 +16,7 @@
 
 namespace ofx {
 
-constexpr int kAThreads = 192;
+constexpr int kAThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..5 softmax group 0, warps 6..9 softmax group 1
 constexpr int kKvStages = 3;
 constexpr uint32_t kTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
 
@@ -36,26 +36,30 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Ping-pong schedule: one CTA owns TWO 128-row Q tiles (same batch / head); each tile has its own softmax warpgroup and its own
+// S / P / O regions in tensor memory, both share the K/V ring.  While group 0 runs its softmax on S0(j) the tensor core computes
+// S1(j) and P1 V(j-1), and vice versa, so mbarrier / TMEM latencies of one group are hidden behind the other.
+//   TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
 __global__ void __launch_bounds__(kAThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                  // 16 KB
-  uint8_t* sKV = sQ + kTileBytes;                      // kKvStages x (K 16 KB + V 16 KB)
-  uint8_t* sP = sKV + kKvStages * 2 * kTileBytes;      // 32 KB (only used when !p_in_tmem)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
+  uint8_t* sQ = smem;                                  // 2 x 16 KB
+  uint8_t* sKV = sQ + 2 * kTileBytes;                  // kKvStages x (K 16 KB + V 16 KB)
+  uint8_t* sP = sKV + kKvStages * 2 * kTileBytes;      // 2 x 32 KB (only used when !p_in_tmem)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;               // [kKvStages]
   uint64_t* kv_empty = kv_full + kKvStages;   // [kKvStages]
-  uint64_t* s_full = kv_empty + kKvStages;    // [2]
+  uint64_t* s_full = kv_empty + kKvStages;    // [2] per group
   uint64_t* s_empty = s_full + 2;             // [2]
-  uint64_t* p_full = s_empty + 2;
-  uint64_t* pv_done = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* p_full = s_empty + 2;             // [2]
+  uint64_t* pv_done = p_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
   const int n = p.n_kv_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -70,9 +74,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
     }
-    mbar_init(p_full, 4);
-    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -83,14 +87,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem;            // 2 x 128 cols
-  const uint32_t tO = tmem + 256;      // 64 cols
-  const uint32_t tP = tmem + 320;      // 64 cols (bf16x2 packed)
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
+      mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
       tma_load_4d(sQ, &tmap_q, q_full, 0, h, q0, b);
+      tma_load_4d(sQ + kTileBytes, &tmap_q, q_full, 0, h, q0 + 128, b);
       const int kvh = h % p.KVH;
       for (int j = 0; j < n; ++j) {
         const int st = j % kKvStages, use = j / kKvStages;
@@ -106,83 +108,95 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t aQ = smem_u32(sQ);
-      auto issue_s = [&](int j) {
-        const int st = j % kKvStages;
-        const uint32_t aK = smem_u32(sKV + st * 2 * kTileBytes);
+      auto issue_s = [&](int w, int j) {   // S_w(j) = Q_w K_j^T ; S buffer of group w must be free (s_empty) and K_j loaded
+        const uint32_t aQ = smem_u32(sQ + w * kTileBytes);
+        const uint32_t aK = smem_u32(sKV + (j % kKvStages) * 2 * kTileBytes);
+        mbar_wait(&s_empty[w], (j & 1) ^ 1);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tS + (j & 1) * 128, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024),
-                      idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
+          umma_f16_ss(tmem + w * 128, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s,
+                      k > 0 ? 1u : 0u);
+        umma_commit(&s_full[w]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < n; ++j) {
-        if (j + 1 < n) {
-          const int j1 = j + 1;
-          mbar_wait(&kv_full[j1 % kKvStages], (j1 / kKvStages) & 1);
-          mbar_wait(&s_empty[j1 & 1], ((j1 >> 1) & 1) ^ 1);
-          tc_fence_after();
-          issue_s(j1);
-        }
-        mbar_wait(p_full, j & 1);
+      auto issue_pv = [&](int w, int j) {  // O_w += P_w(j) V_j
+        const uint32_t aV = smem_u32(sKV + (j % kKvStages) * 2 * kTileBytes + kTileBytes);
+        const uint32_t tO = tmem + 256 + w * 64, tP = tmem + 384 + w * 64;
+        mbar_wait(&p_full[w], j & 1);
         tc_fence_after();
-        const int st = j % kKvStages;
-        const uint32_t aV = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
         if (p.p_in_tmem) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         } else {
-          const uint32_t aP = smem_u32(sP);
+          const uint32_t aP = smem_u32(sP + w * 2 * kTileBytes);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_f16_ss(tO, make_smem_desc(aP + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
                         make_smem_desc(aV + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(pv_done);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&pv_done[w]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < n; ++j) {
+        const bool more = j + 1 < n;
+        if (more) mbar_wait(&kv_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
+        issue_pv(0, j);
+        if (more) issue_s(0, j + 1);
+        issue_pv(1, j);
+        umma_commit(&kv_empty[j % kKvStages]);   // K_j and V_j are no longer needed by either group
+        if (more) issue_s(1, j + 1);
       }
     }
     __syncwarp();
   } else {
+    const int w = (warp - 2) >> 2;        // softmax group = Q tile index
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const uint32_t tS = tmem + w * 128, tO = tmem + 256 + w * 64, tP = tmem + 384 + w * 64;
+    uint8_t* sPw = sP + w * 2 * kTileBytes;
     float m_run = -INFINITY, m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < n; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t (&sc)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[c * 32]);
-        tmem_ld_32x32b_x32(tS + lane_off + (j & 1) * 128 + c * 32, sc);
-      }
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[j & 1]);
-
       const int kv_valid = p.L - j * 128;  // keys of this tile that exist
+      // ---- pass 1: row maximum (S stays in tensor memory; 32 columns in registers at a time)
       float mx = -INFINITY;
-      if (kv_valid >= 128) {
+      if (kv_valid >= 128) {   // full tile: no key masking on the hot path (the ALU pipe is the busiest one in this kernel)
+        // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is reduced
+        uint32_t sb[2][32];
+        tmem_ld_32x32b_x32(tS + lane_off, sb[0]);
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+        for (int c = 0; c < 4; ++c) {
+          tmem_wait_ld();
+          if (c + 1 < 4) tmem_ld_32x32b_x32(tS + lane_off + (c + 1) * 32, sb[(c + 1) & 1]);
+          const uint32_t (&s)[32] = sb[c & 1];
+          float m0 = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1])), m1 = fmaxf(__uint_as_float(s[2]), __uint_as_float(s[3]));
+#pragma unroll
+          for (int i = 4; i < 32; i += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          float v = (i < kv_valid) ? __uint_as_float(s[i]) : -INFINITY;
-          s[i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
+          tmem_ld_32x32b_x32(tS + lane_off + c * 32, s);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
         }
       }
       m_run = fmaxf(m_run, mx * p.scale_log2);
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
+        mbar_wait(&pv_done[w], (j - 1) & 1);   // previous P V finished: O may be rescaled, P may be overwritten
         tc_fence_after();
         const bool need = (m_run - m_used) > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
@@ -206,46 +220,64 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       } else {
         m_used = m_run;
       }
+      // ---- pass 2: P = exp2(S*scale - m), row sum, bf16 P back to tensor memory (or swizzled shared memory)
       float sum = 0.f;
-      uint32_t pk[64];
+      uint32_t s2[2][32];
+      tmem_ld_32x32b_x32(tS + lane_off, s2[0]);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
-        float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
-        sum += p0 + p1;
-        pk[i] = pack_bf16x2(p0, p1);
-      }
-      l += sum;
-      if (p.p_in_tmem) {
+      for (int c = 0; c < 4; ++c) {
+        tmem_wait_ld();
+        if (c + 1 < 4) tmem_ld_32x32b_x32(tS + lane_off + (c + 1) * 32, s2[(c + 1) & 1]);
+        const uint32_t (&s)[32] = s2[c & 1];
+        uint32_t pk[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&pc)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[c * 16]);
-          tmem_st_32x32b_x16(tP + lane_off + c * 16, pc);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-      } else {
-        // K-major A tile, two 64-key chunks, 128B rows with the hardware 128B swizzle (16B piece ^= row & 7)
+        if (kv_valid >= 128) {
+          float sa = 0.f, sb = 0.f;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint8_t* rowp = sP + c * kTileBytes + row * 128;
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
+            const float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
+            sa += p0;
+            sb += p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          sum += sa + sb;
+        } else {
 #pragma unroll
-          for (int pc = 0; pc < 8; ++pc) {
-            uint4 v = make_uint4(pk[c * 32 + pc * 4], pk[c * 32 + pc * 4 + 1], pk[c * 32 + pc * 4 + 2],
-                                 pk[c * 32 + pc * 4 + 3]);
-            *reinterpret_cast<uint4*>(rowp + ((pc ^ (row & 7)) << 4)) = v;
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
+            float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
+            if (c * 32 + 2 * i >= kv_valid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
+            sum += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
           }
         }
-        fence_proxy_async();
+        if (p.p_in_tmem) {
+          tmem_st_32x32b_x16(tP + lane_off + c * 16, pk);
+        } else {
+          uint8_t* rowp = sPw + (c >> 1) * kTileBytes + row * 128;
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc)
+            *reinterpret_cast<uint4*>(rowp + ((((c & 1) * 4 + pc) ^ (row & 7)) << 4)) =
+                make_uint4(pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+        }
       }
+      l += sum;
+      if (p.p_in_tmem) tmem_wait_st();
+      else fence_proxy_async();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) {
+        mbar_arrive(&s_empty[w]);
+        mbar_arrive(&p_full[w]);
+      }
     }
     // ---- epilogue
-    mbar_wait(pv_done, (n - 1) & 1);
+    mbar_wait(&pv_done[w], (n - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
-    const int qrow = q0 + row;
+    const int qrow = q0 + w * 128 + row;
     uint32_t o[64];
     {
       uint32_t (&o0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
@@ -314,13 +346,13 @@ extern "C" int of_attn_fwd(const of_attn_args* a, void* stream_) {
   p.out_ld = a->out_ld;
   p.out_bs = a->out_batch_stride;
   p.lse = a->lse;
-  size_t smem_bytes = 1024 + kTileBytes * (1 + 2 * kKvStages + 2) + 256;
+  size_t smem_bytes = 1024 + kTileBytes * (2 + 2 * kKvStages + 4) + 256;
   static bool attr_set = false;
   if (!attr_set) {
     OF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((a->L + 127) / 128, a->H, a->B);
+  dim3 grid((a->L + 255) / 256, a->H, a->B);
   attn_fwd_kernel<<<grid, kAThreads, smem_bytes, stream>>>(tq, tk, tv, p);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -8,6 +8,8 @@
 // main loop of tile i+1 through the double-buffered TMEM accumulator.
 //
 // Reference ops replaced: see include/osufusion_b200.h (of_gemm).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -48,14 +50,15 @@ struct TileCoord {
   int b, m0, n0, tap, k_begin, k_end;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
+// Cluster mode: `tile` enumerates PAIRS of M-adjacent tiles (m_tiles is counted in pairs by the host); `rank` picks the tile.
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int rank = 0, int mc = 0) {
   TileCoord tc;
   if (p.mode == OF_GEMM_FWD) {
     int n_blk = tile % p.n_tiles;
     int rest = tile / p.n_tiles;
     int m_blk = rest % p.m_tiles;
     tc.b = rest / p.m_tiles;
-    tc.m0 = m_blk * kBM;
+    tc.m0 = (mc ? 2 * m_blk + rank : m_blk) * kBM;
     tc.n0 = n_blk * p.BN;
     tc.tap = 0;
     tc.k_begin = 0;
@@ -68,7 +71,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile)
     int m_blk = rest % p.m_tiles;
     tc.tap = rest / p.m_tiles;
     tc.b = 0;
-    tc.m0 = m_blk * kBM;
+    tc.m0 = (mc ? 2 * m_blk + rank : m_blk) * kBM;
     tc.n0 = n_blk * p.BN;
     tc.k_begin = split * p.k_iters_per_split;
     tc.k_end = min(tc.k_begin + p.k_iters_per_split, p.k_iters_total);
@@ -84,6 +87,9 @@ __device__ __forceinline__ void red_add_v4(float* ptr, float a, float b, float c
                : "memory");
 }
 
+// kMC: launched as clusters of 2 CTAs that own two M-adjacent tiles with the same N tile; each CTA fetches half of the shared
+// B (weight / X) tile and TMA-multicasts it to both, cutting L2->SM operand traffic per CTA from A+B to A+B/2.
+template <bool kMC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmKParams p) {
@@ -106,7 +112,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < p.num_stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kMC ? 2 : 1);   // cluster: both CTAs' MMA warps release a stage (it receives multicast data)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -120,8 +126,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (kMC) cluster_sync_all();   // peer barriers must be initialised before any multicast can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  const int crank = kMC ? (int)cluster_ctarank() : 0;
+  const int tile_first = kMC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kMC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   const bool a_mn = (p.mode == OF_GEMM_WGRAD);
   const bool b_mn = (p.mode == OF_GEMM_WGRAD) || (p.b_mn != 0);
@@ -131,8 +141,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        TileCoord tc = decode_tile(p, tile);
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+        TileCoord tc = decode_tile(p, tile, crank, kMC);
         for (int it = tc.k_begin; it < tc.k_end; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + (size_t)stage * p.stage_bytes;
@@ -143,10 +153,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             int kc = it - t * p.k_chunks;
             tma_load_3d(sa, &tmap_a, &full_bar[stage], kc * kBK, tc.m0 + p.shift0 + t * p.shift_step, tc.b);
             if (!b_mn) {
-              tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * kBK, tc.n0, t);
+              if (kMC) {   // this CTA's half of the B rows (box = BN/2 rows), multicast to both CTAs
+                const int hr = p.BN / 2;
+                tma_load_3d_mc(sb + crank * hr * 128, &tmap_b, &full_bar[stage], kc * kBK, tc.n0 + crank * hr, t, 3);
+              } else {
+                tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * kBK, tc.n0, t);
+              }
             } else {
-              for (int j = 0; j < p.BN / 64; ++j)
-                tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, kc * kBK, t);
+              const int nch = p.BN / 64;
+              if (kMC) {
+                for (int j = crank * (nch / 2); j < (crank + 1) * (nch / 2); ++j)
+                  tma_load_3d_mc(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, kc * kBK, t, 3);
+              } else {
+                for (int j = 0; j < nch; ++j)
+                  tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, kc * kBK, t);
+              }
             }
           } else {
             int b = it / p.k_chunks;
@@ -154,8 +175,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int j = 0; j < 2; ++j)
               tma_load_3d(sa + j * 8192, &tmap_a, &full_bar[stage], tc.m0 + j * 64, lc * kBK, b);
             int shift = p.shift0 + tc.tap * p.shift_step;
-            for (int j = 0; j < p.BN / 64; ++j)
-              tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, lc * kBK + shift, b);
+            const int nch = p.BN / 64;
+            if (kMC) {
+              for (int j = crank * (nch / 2); j < (crank + 1) * (nch / 2); ++j)
+                tma_load_3d_mc(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, lc * kBK + shift, b, 3);
+            } else {
+              for (int j = 0; j < nch; ++j)
+                tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, lc * kBK + shift, b);
+            }
           }
           if (++stage == p.num_stages) {
             stage = 0;
@@ -172,8 +199,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        TileCoord tc = decode_tile(p, tile);
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+        TileCoord tc = decode_tile(p, tile, crank, kMC);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
@@ -188,7 +215,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             uint64_t db = b_mn ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
             umma_f16_ss(tmem_d, da, db, idesc, (it > tc.k_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (kMC) umma_commit_mc(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -206,8 +234,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int r = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      TileCoord tc = decode_tile(p, tile);
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+      TileCoord tc = decode_tile(p, tile, crank, kMC);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int m = tc.m0 + r;
@@ -350,6 +378,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (kMC) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it / arrive on its barriers
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
@@ -407,8 +436,15 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
 
+  // cluster-of-2 multicast of the B tile: needs two M tiles to pair and a B tile that splits into two swizzle-aligned halves
+  const int m_tiles_real = wgrad ? ceil_div(a->K, kBM) : ceil_div(a->rows, kBM);
+  bool use_mc = (m_tiles_real >= 2) && (b_mn ? ((BN / 64) % 2 == 0) : (BN % 16 == 0 && BN >= 64));
+  {
+    const char* e = getenv("OF_GEMM_NO_MULTICAST");
+    if (e && e[0] == '1') use_mc = false;
+  }
   if (!wgrad) {
-    p.m_tiles = ceil_div(a->rows, kBM);
+    p.m_tiles = use_mc ? ceil_div(m_tiles_real, 2) : m_tiles_real;
     p.n_tiles = ceil_div(a->N, BN);
     p.num_tiles = a->batch * p.m_tiles * p.n_tiles;
     p.k_chunks = ceil_div(a->K, kBK);
@@ -418,14 +454,14 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
   } else {
     OF_REQUIRE(a->out_f32 != nullptr, "of_gemm(wgrad): out_f32 required");
     OF_REQUIRE(a->K % 8 == 0, "of_gemm(wgrad): M=%d must be a multiple of 8", a->K);
-    p.m_tiles = ceil_div(a->K, kBM);
+    p.m_tiles = use_mc ? ceil_div(m_tiles_real, 2) : m_tiles_real;
     p.n_tiles = ceil_div(a->N, BN);
     p.k_chunks = ceil_div(a->rows, kBK);
     p.k_iters_total = a->batch * p.k_chunks;
     int base_tiles = a->taps * p.m_tiles * p.n_tiles;
     int split = a->split_k;
     if (split <= 0) {
-      split = ceil_div(2 * device_sm_count(), base_tiles);
+      split = ceil_div((use_mc ? 1 : 2) * device_sm_count(), base_tiles);
       int max_split = ceil_div(p.k_iters_total, 4);  // at least 4 k-iterations per split
       if (split > max_split) split = max_split;
       if (split < 1) split = 1;
@@ -476,7 +512,7 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
       unsigned long long ts = a->taps > 1 ? (unsigned long long)a->b_tap_stride : (unsigned long long)a->N * a->b_ld;
       unsigned long long bd[3] = {(unsigned long long)a->K, (unsigned long long)a->N, (unsigned long long)a->taps};
       unsigned long long bstr[2] = {(unsigned long long)a->b_ld * 2ull, ts * 2ull};
-      unsigned bbox[3] = {64, (unsigned)BN, 1};
+      unsigned bbox[3] = {64, (unsigned)(use_mc ? BN / 2 : BN), 1};
       if ((rc = make_tmap_bf16(&tb, a->b, 3, bd, bstr, bbox)) != OF_OK) return rc;
     } else {
       unsigned long long ts = a->taps > 1 ? (unsigned long long)a->b_tap_stride : (unsigned long long)a->K * a->b_ld;
@@ -500,11 +536,30 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
   size_t smem_bytes = (size_t)p.num_stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    OF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    OF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
-  gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  if (!use_mc) {
+    int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
+    gemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  } else {
+    int pairs = device_sm_count() / 2;
+    if (p.num_tiles < pairs) pairs = p.num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, ta, tb, p));
+  }
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

@@ -220,6 +220,7 @@ __global__ void rope_bwd_kernel(const float* __restrict__ dq, long long dq_ld, l
 // =================================================================================================== small-M linear
 constexpr int kMaxM = 16;
 // one warp per output feature n; weights fp32 (master) rounded to bf16 on the fly when round_bf16 != 0.
+template <int MM>
 __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __restrict__ x, long long x_ld, int M, int N, int K,
                                                                const float* __restrict__ W, long long w_ld,
                                                                const float* __restrict__ bias, int act, int round_bf16,
@@ -228,16 +229,17 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + warp;
   if (n >= N) return;
-  float acc[kMaxM];
+  float acc[MM];
 #pragma unroll
-  for (int m = 0; m < kMaxM; ++m) acc[m] = 0.f;
+  for (int m = 0; m < MM; ++m) acc[m] = 0.f;
   const float* w = W + (long long)n * w_ld;
   if ((K & 3) == 0 && (w_ld & 3) == 0 && (x_ld & 3) == 0) {
+#pragma unroll 2
     for (int k = lane * 4; k < K; k += 128) {
       float4 wv = *reinterpret_cast<const float4*>(w + k);
       if (round_bf16) { wv.x = bf16_round(wv.x); wv.y = bf16_round(wv.y); wv.z = bf16_round(wv.z); wv.w = bf16_round(wv.w); }
 #pragma unroll
-      for (int m = 0; m < kMaxM; ++m) {
+      for (int m = 0; m < MM; ++m) {
         if (m < M) {
           float4 xv = *reinterpret_cast<const float4*>(x + (long long)m * x_ld + k);
           if (round_bf16) { xv.x = bf16_round(xv.x); xv.y = bf16_round(xv.y); xv.z = bf16_round(xv.z); xv.w = bf16_round(xv.w); }
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
       float wv = w[k];
       if (round_bf16) wv = bf16_round(wv);
 #pragma unroll
-      for (int m = 0; m < kMaxM; ++m) {
+      for (int m = 0; m < MM; ++m) {
         if (m < M) {
           float xv = x[(long long)m * x_ld + k];
           if (round_bf16) xv = bf16_round(xv);
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
     }
   }
 #pragma unroll
-  for (int m = 0; m < kMaxM; ++m) {
+  for (int m = 0; m < MM; ++m) {
     if (m < M) {
       float v = warp_sum(acc[m]);
       if (lane == 0) {
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
 // dpre[m,n] = dy[m,n] * act'(ypre[m,n]);  dW[n,k] += sum_m dpre*x ; db[n] += sum_m dpre ; dx[m,k] += sum_n dpre*W (atomic)
 // grid: (ceil(K/ (256*4 or 256)), ceil(N/NCHUNK)); thread owns 4 (or 1) consecutive k.
 constexpr int kNChunk = 16;
+template <int MM>
 __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __restrict__ dy, long long dy_ld,
                                                                const float* __restrict__ ypre, int act,
                                                                const float* __restrict__ x, long long x_ld, int M, int N, int K,
@@ -311,10 +314,10 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
   const int kw = vec4 ? 4 : 1;
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) * kw;
   if (k >= K) return;
-  float xa[kMaxM][4];
-  float dxa[kMaxM][4];
+  float xa[MM][4];
+  float dxa[MM][4];
 #pragma unroll
-  for (int m = 0; m < kMaxM; ++m) {
+  for (int m = 0; m < MM; ++m) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       dxa[m][e] = 0.f;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
       }
     }
 #pragma unroll
-    for (int m = 0; m < kMaxM; ++m) {
+    for (int m = 0; m < MM; ++m) {
       if (m < M) {
         const float d = sdpre[j][m];
 #pragma unroll
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
   }
   if (dx) {
 #pragma unroll
-    for (int m = 0; m < kMaxM; ++m) {
+    for (int m = 0; m < MM; ++m) {
       if (m < M) {
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -367,29 +370,40 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
 }
 
 // =================================================================================================== column sum (bias grads)
-// db[n] += sum_rows bf16 dy[row, n]
+// db[n] += sum_rows bf16 dy[row, n].  256 threads = vecs 16-byte column vectors x rpar row-lanes; shared-memory combine.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, long long rows,
                                                           int N, float* __restrict__ db, int rows_per_cta) {
-  const int vecs = N >> 3;
-  const int vi = blockIdx.y * 256 + threadIdx.x;
-  if (vi >= vecs) return;
+  extern __shared__ float s_cs[];  // [min(vecs,256) * 8]
+  const int vecs_total = N >> 3;
+  const int v0 = blockIdx.y * 256;
+  const int vecs = min(256, vecs_total - v0);
+  const int rpar = 256 / vecs;
+  const int vi = threadIdx.x % vecs, rsub = threadIdx.x / vecs;
+  const bool active = rsub < rpar;
+  for (int c = threadIdx.x; c < vecs * 8; c += blockDim.x) s_cs[c] = 0.f;
+  __syncthreads();
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, rows);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long r = r0;
-  for (; r + 3 < r1; r += 4) {
-    V8 v0 = ld_bf16x8(dy + r * ld + vi * 8), v1 = ld_bf16x8(dy + (r + 1) * ld + vi * 8);
-    V8 v2 = ld_bf16x8(dy + (r + 2) * ld + vi * 8), v3 = ld_bf16x8(dy + (r + 3) * ld + vi * 8);
+  if (active) {
+    const __nv_bfloat16* base = dy + (long long)(v0 + vi) * 8;
+    long long r = r0 + rsub;
+    for (; r + 3 * rpar < r1; r += 4 * rpar) {
+      V8 a0 = ld_bf16x8(base + r * ld), a1 = ld_bf16x8(base + (r + rpar) * ld);
+      V8 a2 = ld_bf16x8(base + (r + 2 * rpar) * ld), a3 = ld_bf16x8(base + (r + 3 * rpar) * ld);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += (v0.v[j] + v1.v[j]) + (v2.v[j] + v3.v[j]);
+      for (int j = 0; j < 8; ++j) acc[j] += (a0.v[j] + a1.v[j]) + (a2.v[j] + a3.v[j]);
+    }
+    for (; r < r1; r += rpar) {
+      V8 a0 = ld_bf16x8(base + r * ld);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a0.v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_cs[vi * 8 + j], acc[j]);
   }
-  for (; r < r1; ++r) {
-    V8 v = ld_bf16x8(dy + r * ld + vi * 8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(db + vi * 8 + j, acc[j]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < vecs * 8; c += blockDim.x) atomicAdd(db + (long long)v0 * 8 + c, s_cs[c]);
 }
 
 // =================================================================================================== layout / elementwise
@@ -733,7 +747,9 @@ extern "C" int of_linear_small_fwd(const float* x, long long x_ld, int M, int N,
                                    void* stream) {
   OF_REQUIRE(x && W && y, "of_linear_small_fwd: null pointer");
   OF_REQUIRE(M >= 1 && M <= kMaxM, "of_linear_small_fwd: M=%d out of range (1..%d)", M, kMaxM);
-  linear_small_fwd_kernel<<<(N + 7) / 8, 256, 0, STREAM>>>(x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre);
+  if (M <= 4) linear_small_fwd_kernel<4><<<(N + 7) / 8, 256, 0, STREAM>>>(x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre);
+  else if (M <= 8) linear_small_fwd_kernel<8><<<(N + 7) / 8, 256, 0, STREAM>>>(x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre);
+  else linear_small_fwd_kernel<16><<<(N + 7) / 8, 256, 0, STREAM>>>(x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre);
   DONE()
 }
 
@@ -746,16 +762,20 @@ extern "C" int of_linear_small_bwd(const float* dy, long long dy_ld, const float
   const bool vec4 = ((K & 3) == 0) && ((w_ld & 3) == 0) && ((x_ld & 3) == 0) && (!dx || (dx_ld & 3) == 0);
   const int kw = vec4 ? 4 : 1;
   dim3 grid((K + 256 * kw - 1) / (256 * kw), (N + kNChunk - 1) / kNChunk);
-  linear_small_bwd_kernel<<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx,
-                                                    dx ? dx_ld : 4);
+  const long long dxl = dx ? dx_ld : 4;
+  if (M <= 4) linear_small_bwd_kernel<4><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl);
+  else if (M <= 8) linear_small_bwd_kernel<8><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl);
+  else linear_small_bwd_kernel<16><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl);
   DONE()
 }
 
 extern "C" int of_colsum_bf16(const void* dy, long long ld, long long rows, int N, float* db, void* stream) {
   OF_REQUIRE(dy && db && N % 8 == 0 && ld % 8 == 0, "of_colsum_bf16: bad args");
-  int rpc = 64;
+  int rpc = (int)((rows + 2 * device_sm_count() - 1) / (2 * device_sm_count()));
+  if (rpc < 16) rpc = 16;
+  if (rpc > 256) rpc = 256;
   dim3 grid((unsigned)((rows + rpc - 1) / rpc), (N / 8 + 255) / 256);
-  colsum_bf16_kernel<<<grid, 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc);
+  colsum_bf16_kernel<<<grid, 256, 256 * 8 * sizeof(float), STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc);
   DONE()
 }
 

@@ -133,48 +133,41 @@ __global__ void __launch_bounds__(kRbThreads) rb_apply_fwd_kernel(const of_rb_ar
   }
 }
 
-// warp per row: dot(h_row, vec); lane owns 16-byte vectors lane + 32*i (i < NV) and keeps their constants in registers
-template <int NV>
-__global__ void __launch_bounds__(256) rb_rowdot_kernel(const of_rb_args a, const int rows_per_warp) {
+// Row-wise dot products dot(h[b,l,:], vec): channel-owner mapping (constants loaded once per thread), per-row partials
+// combined through shared memory (one shuffle-reduced atomic per warp when a warp lies inside one row).
+__global__ void __launch_bounds__(kRbThreads) rb_rowdot_kernel(const of_rb_args a, const int rpc) {
+  extern __shared__ float s_red[];   // [rpc] row accumulators
   GnCtx g = make_ctx(a);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int vecs = a.C >> 3;
-  float mean, rstd;
-  gn_mean_rstd(g.stats, b, (double)g.L * (double)g.C, g.eps, mean, rstd);
-  const float* vec = a.vec + (long long)b * a.vec_bs;
-  const float bias = a.vec_bias ? *a.vec_bias : 0.f;
-  ChanConst k[NV];
-  V8 w[NV];
+  Map m = make_map(a.C, a.L, rpc);
+  for (int i = threadIdx.x; i < rpc; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  if (m.active) {
+    ChanConst k = load_consts(g, m.b, m.c0);
+    V8 w = ld_f32x8(a.vec + (long long)m.b * a.vec_bs + m.c0);
+    if (a.mode == 0) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < vecs) {
-      k[i] = load_consts(g, b, vi * 8);
-      w[i] = ld_f32x8(vec + vi * 8);
-      if (a.mode == 0) {
+      for (int j = 0; j < 8; ++j) w.v[j] = bf16_round(w.v[j]);
+    }
+    const bool warp_in_row = (m.vecs & 31) == 0;
+    for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
+      V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
+      gn_eval(k, y, xh, z, f, h);
+      float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[i].v[j] = bf16_round(w[i].v[j]);
+      for (int j = 0; j < 8; ++j) acc += bf16_round(h.v[j]) * w.v[j];
+      if (warp_in_row) {
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_red[l - m.l_begin], acc);
+      } else {
+        atomicAdd(&s_red[l - m.l_begin], acc);
       }
     }
   }
-  const int l0 = (blockIdx.x * 8 + warp) * rows_per_warp;
-  for (int rr = 0; rr < rows_per_warp; ++rr) {
-    const int l = l0 + rr;
-    if (l >= a.L) break;
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < vecs) {
-        V8 y = ld_bf16x8(g.y + b * g.y_bs + (long long)l * g.y_ld + vi * 8), xh, z, f, h;
-        gn_eval(k[i], y, xh, z, f, h);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc += bf16_round(h.v[j]) * w[i].v[j];
-      }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) a.out_rows[(long long)b * a.L + l] = (a.mode == 0) ? bf16_round(acc + bias) : acc;
+  __syncthreads();
+  const float bias = a.vec_bias ? *a.vec_bias : 0.f;
+  for (int i = threadIdx.x; i < rpc; i += blockDim.x) {
+    const int l = blockIdx.x * rpc + i;
+    if (l < a.L) a.out_rows[(long long)blockIdx.y * a.L + l] = (a.mode == 0) ? bf16_round(s_red[i] + bias) : s_red[i];
   }
 }
 
@@ -259,6 +252,7 @@ __global__ void __launch_bounds__(kRbThreads) rb_gate_bwd_reduce_kernel(const of
   cta_channel_reduce(m, a.C, acc, s_red, a.acc_bc + (long long)m.b * a.C);
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb_args a, const int rpc) {
   __shared__ float sm[32];
   extern __shared__ float s_red[];
@@ -270,7 +264,7 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
   if (m.active) {
     ChanConst k = load_consts(g, m.b, m.c0);
     V8 gate, dpool, wk;
-    if (a.mode == 0) {
+    if (MODE == 0) {
       gate = ld_f32x8(a.gate + (long long)m.b * a.C + m.c0);
       dpool = ld_f32x8(a.dpooled + (long long)m.b * a.C + m.c0);
       wk = ld_f32x8(a.wk + m.c0);
@@ -283,7 +277,7 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
     for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
       V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h, dh, dx;
       gn_eval(k, y, xh, z, f, h);
-      if (a.mode == 0) {
+      if (MODE == 0) {
         V8 d = ld_f32x8(a.dout_f32 + m.b * a.dout_f32_bs + (long long)l * a.dout_f32_ld + m.c0);
         const float pl = bf16_round(a.p[(long long)m.b * a.L + l]);
         const float da = a.da[(long long)m.b * a.L + l];
@@ -303,7 +297,7 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
         const float sg = 1.0f / (1.0f + expf(-f.v[j]));
         float df = dh.v[j] * (sg * (1.0f + f.v[j] * (1.0f - sg)));
         float dz = df;
-        if (k.film) {
+        if (MODE == 1 && k.film) {
           dsc[j] += df * z.v[j];
           dsh[j] += df;
           dz = df * k.sp1.v[j];
@@ -318,19 +312,35 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
       st_bf16x8(dxh + m.b * a.dxhat_bs + (long long)l * a.dxhat_ld + m.c0, dx);
     }
   }
-  RedSlot slots[5] = {{dgam, a.dgamma},
-                      {dbet, a.dbeta},
-                      {dsc, a.ss ? a.dss + (long long)blockIdx.y * 2 * a.C : nullptr},
-                      {dsh, a.ss ? a.dss + (long long)blockIdx.y * 2 * a.C + a.C : nullptr},
-                      {dwk, a.mode == 0 ? a.dwk : nullptr}};
-  cta_channel_reduce_multi(m, a.C, slots, 5, s_red);
+  // CTA-level combine of the per-channel partials in shared memory (accumulators stay in registers: no indirection)
+  float* dst[5] = {a.dgamma, a.dbeta, (MODE == 1 && a.ss) ? a.dss + (long long)blockIdx.y * 2 * a.C : nullptr,
+                   (MODE == 1 && a.ss) ? a.dss + (long long)blockIdx.y * 2 * a.C + a.C : nullptr, MODE == 0 ? a.dwk : nullptr};
+  for (int c = threadIdx.x; c < 5 * a.C; c += blockDim.x) s_red[c] = 0.f;
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_red[0 * a.C + m.c0 + j], dgam[j]);
+      atomicAdd(&s_red[1 * a.C + m.c0 + j], dbet[j]);
+      if (MODE == 1 && a.ss) {
+        atomicAdd(&s_red[2 * a.C + m.c0 + j], dsc[j]);
+        atomicAdd(&s_red[3 * a.C + m.c0 + j], dsh[j]);
+      }
+      if (MODE == 0) atomicAdd(&s_red[4 * a.C + m.c0 + j], dwk[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 5 * a.C; c += blockDim.x) {
+    const int sl = c / a.C;
+    if (dst[sl] != nullptr) atomicAdd(dst[sl] + (c - sl * a.C), s_red[c]);
+  }
   s1 = block_sum(s1, sm);
   s2 = block_sum(s2, sm);
-  if (a.mode == 0) sda = block_sum(sda, sm);
+  if (MODE == 0) sda = block_sum(sda, sm);
   if (threadIdx.x == 0) {
     atomicAdd(a.dstats + 2 * blockIdx.y, (double)s1);
     atomicAdd(a.dstats + 2 * blockIdx.y + 1, (double)s2);
-    if (a.mode == 0 && a.dbk) atomicAdd(a.dbk, sda);
+    if (MODE == 0 && a.dbk) atomicAdd(a.dbk, sda);
   }
 }
 
@@ -399,14 +409,9 @@ extern "C" int of_rb_rowdot(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_rowdot");
   if (rc) return rc;
   OF_REQUIRE(a->vec && a->out_rows, "of_rb_rowdot: null vec/out_rows");
-  const int nv = (a->C / 8 + 31) / 32;
-  const int rows_per_warp = a->L >= 2048 ? 4 : 1;
-  dim3 grid((a->L + 8 * rows_per_warp - 1) / (8 * rows_per_warp), a->B);
-  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
-  if (nv <= 1) rb_rowdot_kernel<1><<<grid, 256, 0, st_>>>(*a, rows_per_warp);
-  else if (nv <= 2) rb_rowdot_kernel<2><<<grid, 256, 0, st_>>>(*a, rows_per_warp);
-  else if (nv <= 4) rb_rowdot_kernel<4><<<grid, 256, 0, st_>>>(*a, rows_per_warp);
-  else rb_rowdot_kernel<8><<<grid, 256, 0, st_>>>(*a, rows_per_warp);
+  const int rpc = rb_rows_per_cta(a);
+  rb_rowdot_kernel<<<rb_grid(a, rpc), kRbThreads, (size_t)(rpc > 5 * a->C ? rpc : 5 * a->C) * sizeof(float),
+                     reinterpret_cast<cudaStream_t>(stream)>>>(*a, rpc);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;
@@ -452,7 +457,11 @@ extern "C" int of_rb_bwd_pass1(const of_rb_args* a, void* stream) {
     OF_REQUIRE(a->dout_f32 && a->gate && a->dpooled && a->p && a->da && a->wk && a->dwk, "of_rb_bwd_pass1(mode 0): null inputs");
   else
     OF_REQUIRE(a->dh_bf16, "of_rb_bwd_pass1(mode 1): null dh");
-  RB_LAUNCH(rb_bwd_pass1_kernel)
+  if (a->mode == 0) {
+    OF_REQUIRE(a->ss == nullptr, "of_rb_bwd_pass1(mode 0): FiLM is not supported on block2");
+    RB_LAUNCH(rb_bwd_pass1_kernel<0>)
+  }
+  RB_LAUNCH(rb_bwd_pass1_kernel<1>)
 }
 extern "C" int of_rb_bwd_apply(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_bwd_apply");
