@@ -4,12 +4,13 @@
 // scale 1/sqrt(D)) together with the GQA `repeat` of k,v (unet.py:135-137), which is never materialised here: every
 // q head reads the single shared KV head through its own TMA descriptor coordinates.
 //
-// One CTA = 128 query rows of one (batch, head); KV tiles of 128 keys stream through a TMA ring.
-//   warp 0 : TMA producer (Q once; K/V ring)
-//   warp 1 : MMA issuer: S_j = Q K_j^T (SS, M128 N128 K64) into a double-buffered TMEM S; O += P_j V_j
-//            (P from TMEM [TS mode] or from 128B-swizzled smem, V consumed MN-major straight from its row-major tile)
-//   warps 2-5: one thread per query row: online softmax in registers (exp2, lazy rescale of the TMEM O accumulator),
-//            P written back as bf16, final O/l and log-sum-exp written to global.
+// One CTA = TWO 128-row Q tiles of one (batch, head) ("ping-pong"); KV tiles of 128 keys stream through a shared TMA ring.
+//   warp 0    : TMA producer (both Q tiles once; K/V ring, 3 stages)
+//   warp 1    : MMA issuer: S_w(j) = Q_w K_j^T (SS, M128 N128 K64) into the S region of group w; O_w += P_w(j) V_j
+//               (P from TMEM [TS mode] or from 128B-swizzled smem, V consumed MN-major straight from its row-major tile)
+//   warps 2-5 : softmax group 0, warps 6-9: softmax group 1 — one thread per query row, two passes over S in tensor memory
+//               (row max, then exp2 / row sum / bf16 P), lazy rescale of the TMEM O accumulator, final O/l and log-sum-exp.
+//   While one group runs its softmax the tensor core works for the other, hiding mbarrier / TMEM round trips.
 // Head dim D <= 64 (zero-padded to 64 by TMA out-of-bounds fill); any L (key tail masked).
 #include "host_common.h"
 #include "ptx.cuh"
