@@ -255,8 +255,19 @@ def run_ours(args) -> None:
             "roofline": roof, "cpu_baseline": cpu, "loss": float(step.loss.detach()),
         }
         print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world: int) -> None:
+    """Multi-rank exit: tearing the NCCL communicator down while CUDA graphs that captured its collectives are still alive can
+    block for minutes, so ranks synchronise, flush and leave without destroy_process_group()."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------ sampling (metric 2)
@@ -337,8 +348,7 @@ def run_sampling(args) -> None:
                                 "note": f"algorithmic FLOPs = {evals} x F_fwd (reference's count; the cached audio encoder removes work)",
                                 "peak_source": how}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 def main() -> None:

@@ -112,39 +112,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();   // warp-uniform loop; the elected lane issues the TMA instructions
+    if (leader) {
       mbar_arrive_expect_tx(kv_full, 2 * kTile);
       tma_load_4d(sK, &tmap_k, kv_full, 0, kvh, k0, b);
       tma_load_4d(sV, &tmap_v, kv_full, 0, kvh, k0, b);
-      for (int i = 0; i < n; ++i) {
-        const int st = i & 1, use = i >> 1;
-        mbar_wait(&qdo_empty[st], (use & 1) ^ 1);
-        uint8_t* sq = sQdO + st * 2 * kTile;
+    }
+    for (int i = 0; i < n; ++i) {
+      const int st = i & 1, use = i >> 1;
+      mbar_wait(&qdo_empty[st], (use & 1) ^ 1);
+      uint8_t* sq = sQdO + st * 2 * kTile;
+      if (leader) {
         mbar_arrive_expect_tx(&qdo_full[st], 2 * kTile);
         tma_load_4d(sq, &tmap_q, &qdo_full[st], 0, h, i * 128, b);
         tma_load_4d(sq + kTile, &tmap_do, &qdo_full[st], 0, h, i * 128, b);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform MMA loop: only tcgen05.mma / commit are predicated on the elected lane (operands stay in uniform registers)
+    const bool leader = elect_one();
+    {
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_kv = make_idesc_bf16(128, 64, 1, 1);  // dV, dK: A = P^T / dS^T (MN-major), B MN-major
       const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);  // dQ: A = dS (K-major), B = K (MN-major)
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
       auto issue_s = [&](int i) {
         const uint32_t aQ = smem_u32(sQdO + (i & 1) * 2 * kTile);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tS, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
       };
       auto issue_dp = [&](int i) {
         const uint32_t adO = smem_u32(sQdO + (i & 1) * 2 * kTile) + kTile;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tdP, make_smem_desc(adO + k * 32, 16, 1024), make_smem_desc(aV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(dp_full);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tdP, make_smem_desc(adO + k * 32, 16, 1024), make_smem_desc(aV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(dp_full);
+        }
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
       mbar_wait(&qdo_full[0], 0);
@@ -157,11 +168,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // dV += P^T dO   (K = 128 q rows, 16 per step)
         mbar_wait(p_full, i & 1);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_f16_ss(tdV, make_smem_desc(aP + k * 2048, kTile, 1024), make_smem_desc(adO + k * 2048, 8192, 1024), idesc_kv,
-                      (i > 0 || k > 0) ? 1u : 0u);
-        umma_commit(p_empty);
+          for (int k = 0; k < 8; ++k)
+            umma_f16_ss(tdV, make_smem_desc(aP + k * 2048, kTile, 1024), make_smem_desc(adO + k * 2048, 8192, 1024), idesc_kv,
+                        (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(p_empty);
+        }
+        __syncwarp();
         // S(i+1)
         if (i + 1 < n) {
           mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
@@ -173,17 +187,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(ds_full, i & 1);
         mbar_wait(dq_empty, (i & 1) ^ 1);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_f16_ss(tdK, make_smem_desc(adS + k * 2048, kTile, 1024), make_smem_desc(aQ + k * 2048, 8192, 1024), idesc_kv,
-                      (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            umma_f16_ss(tdK, make_smem_desc(adS + k * 2048, kTile, 1024), make_smem_desc(aQ + k * 2048, 8192, 1024), idesc_kv,
+                        (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_f16_ss(tdQ, make_smem_desc(adS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(aK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
-        umma_commit(dq_full);
-        umma_commit(ds_empty);
-        umma_commit(&qdo_empty[st]);
+          for (int k = 0; k < 8; ++k)
+            umma_f16_ss(tdQ, make_smem_desc(adS + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                        make_smem_desc(aK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
+          umma_commit(dq_full);
+          umma_commit(ds_empty);
+          umma_commit(&qdo_empty[st]);
+        }
+        __syncwarp();
         // dP(i+1)
         if (i + 1 < n) {
           mbar_wait(dp_empty, i & 1);
@@ -191,7 +208,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           issue_dp(i + 1);
         }
       }
-      umma_commit(acc_done);
+      if (leader) umma_commit(acc_done);
     }
     __syncwarp();
   } else {

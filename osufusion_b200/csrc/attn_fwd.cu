@@ -18,8 +18,10 @@
 namespace ofx {
 
 constexpr int kAThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..5 softmax group 0, warps 6..9 softmax group 1
-constexpr int kKvStages = 3;
-constexpr uint32_t kTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
+constexpr int kKvStages = 6;
+constexpr int kKvTile = 64;                        // keys per KV tile
+constexpr uint32_t kTileBytes = 128 * 64 * 2;      // 16 KB: 128 rows x 64 bf16 (Q tile)
+constexpr uint32_t kKvBytes = kKvTile * 64 * 2;    // 8 KB: 64 keys x 64 bf16 (K or V tile)
 
 struct AttnFwdParams {
   int B, H, KVH, L, D;
@@ -37,27 +39,26 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// Ping-pong schedule: one CTA owns TWO 128-row Q tiles (same batch / head); each tile has its own softmax warpgroup and its own
-// S / P / O regions in tensor memory, both share the K/V ring.  While group 0 runs its softmax on S0(j) the tensor core computes
-// S1(j) and P1 V(j-1), and vice versa, so mbarrier / TMEM latencies of one group are hidden behind the other.
-//   TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
+// One CTA owns TWO 128-row Q tiles (same batch / head), one softmax warpgroup each; K/V stream in 64-key tiles.  With the small
+// KV tile, S and P are DOUBLE-buffered per group inside the 512 TMEM columns, so S_w(j+1), S_w(j+2) are computed while group w
+// still works on tile j and the softmax threads never wait for the tensor core (nor the tensor core for them):
+//   TMEM columns: S[w][b] = w*128 + b*64 (0..255) | O[w] = 256 + w*64 | P[w][b] = 384 + w*64 + b*32 (bf16x2 packed)
 __global__ void __launch_bounds__(kAThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 2 x 16 KB
-  uint8_t* sKV = sQ + 2 * kTileBytes;                  // kKvStages x (K 16 KB + V 16 KB)
-  uint8_t* sP = sKV + kKvStages * 2 * kTileBytes;      // 2 x 32 KB (only used when !p_in_tmem)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
+  uint8_t* sKV = sQ + 2 * kTileBytes;                  // kKvStages x (K 8 KB + V 8 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kKvStages * 2 * kKvBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;               // [kKvStages]
   uint64_t* kv_empty = kv_full + kKvStages;   // [kKvStages]
-  uint64_t* s_full = kv_empty + kKvStages;    // [2] per group
-  uint64_t* s_empty = s_full + 2;             // [2]
-  uint64_t* p_full = s_empty + 2;             // [2]
-  uint64_t* pv_done = p_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* s_full = kv_empty + kKvStages;    // [group][buf] = [4]
+  uint64_t* s_empty = s_full + 4;             // [4]
+  uint64_t* p_full = s_empty + 4;             // [4]
+  uint64_t* p_empty = p_full + 4;             // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
@@ -72,11 +73,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 4);
       mbar_init(&p_full[i], 4);
-      mbar_init(&pv_done[i], 1);
+      mbar_init(&p_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -90,66 +91,77 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    const int kvh = h % p.KVH;
+    if (leader) {
       mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
       tma_load_4d(sQ, &tmap_q, q_full, 0, h, q0, b);
       tma_load_4d(sQ + kTileBytes, &tmap_q, q_full, 0, h, q0 + 128, b);
-      const int kvh = h % p.KVH;
-      for (int j = 0; j < n; ++j) {
-        const int st = j % kKvStages, use = j / kKvStages;
-        mbar_wait(&kv_empty[st], (use & 1) ^ 1);
-        uint8_t* sk = sKV + st * 2 * kTileBytes;
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kTileBytes);
-        tma_load_4d(sk, &tmap_k, &kv_full[st], 0, kvh, j * 128, b);
-        tma_load_4d(sk + kTileBytes, &tmap_v, &kv_full[st], 0, kvh, j * 128, b);
-      }
     }
-    __syncwarp();
+    for (int j = 0; j < n; ++j) {
+      const int st = j % kKvStages, use = j / kKvStages;
+      mbar_wait(&kv_empty[st], (use & 1) ^ 1);
+      uint8_t* sk = sKV + st * 2 * kKvBytes;
+      if (leader) {
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kKvBytes);
+        tma_load_4d(sk, &tmap_k, &kv_full[st], 0, kvh, j * kKvTile, b);
+        tma_load_4d(sk + kKvBytes, &tmap_v, &kv_full[st], 0, kvh, j * kKvTile, b);
+      }
+      __syncwarp();
+    }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    // The whole warp runs the loop convergently (mbarrier waits, address arithmetic stay warp-uniform, so the tensor-core
+    // operands live in uniform registers); only the tcgen05.mma / commit instructions are predicated on one elected lane.
+    // (Issuing from a divergent `if (lane == 0)` region makes ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY waterfall loop,
+    // ~100 cycles per MMA — enough to starve the softmax groups.)
+    const bool leader = elect_one();
+    {
+      const uint32_t idesc_s = make_idesc_bf16(128, kKvTile, 0, 0);
       const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
-      auto issue_s = [&](int w, int j) {   // S_w(j) = Q_w K_j^T ; S buffer of group w must be free (s_empty) and K_j loaded
+      auto issue_s = [&](int w, int j) {   // S_w(j) = Q_w K_j^T into buffer j&1 (must have been drained by the softmax group)
+        const int bf = j & 1;
         const uint32_t aQ = smem_u32(sQ + w * kTileBytes);
-        const uint32_t aK = smem_u32(sKV + (j % kKvStages) * 2 * kTileBytes);
-        mbar_wait(&s_empty[w], (j & 1) ^ 1);
+        const uint32_t aK = smem_u32(sKV + (j % kKvStages) * 2 * kKvBytes);
+        mbar_wait(&s_empty[w * 2 + bf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem + w * 128, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s,
-                      k > 0 ? 1u : 0u);
-        umma_commit(&s_full[w]);
-      };
-      auto issue_pv = [&](int w, int j) {  // O_w += P_w(j) V_j
-        const uint32_t aV = smem_u32(sKV + (j % kKvStages) * 2 * kTileBytes + kTileBytes);
-        const uint32_t tO = tmem + 256 + w * 64, tP = tmem + 384 + w * 64;
-        mbar_wait(&p_full[w], j & 1);
-        tc_fence_after();
-        if (p.p_in_tmem) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        } else {
-          const uint32_t aP = smem_u32(sP + w * 2 * kTileBytes);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_f16_ss(tO, make_smem_desc(aP + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                        make_smem_desc(aV + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem + w * 128 + bf * 64, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024),
+                        idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[w * 2 + bf]);
         }
-        umma_commit(&pv_done[w]);
+        __syncwarp();
+      };
+      auto issue_pv = [&](int w, int j) {  // O_w += P_w(j) V_j   (P from tensor memory, V MN-major from its row-major tile)
+        const int bf = j & 1;
+        const uint32_t aV = smem_u32(sKV + (j % kKvStages) * 2 * kKvBytes + kKvBytes);
+        const uint32_t tO = tmem + 256 + w * 64, tP = tmem + 384 + w * 64 + bf * 32;
+        mbar_wait(&p_full[w * 2 + bf], (j >> 1) & 1);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < kKvTile / 16; ++k)
+            umma_f16_ts(tO, tP + k * 8, make_smem_desc(aV + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&p_empty[w * 2 + bf]);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      issue_s(0, 0);
-      issue_s(1, 0);
+      for (int j = 0; j < 2 && j < n; ++j) {
+        mbar_wait(&kv_full[j % kKvStages], 0);
+        issue_s(0, j);
+        issue_s(1, j);
+      }
       for (int j = 0; j < n; ++j) {
-        const bool more = j + 1 < n;
-        if (more) mbar_wait(&kv_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
+        const bool more = j + 2 < n;
+        if (more) mbar_wait(&kv_full[(j + 2) % kKvStages], ((j + 2) / kKvStages) & 1);
         issue_pv(0, j);
-        if (more) issue_s(0, j + 1);
+        if (more) issue_s(0, j + 2);
         issue_pv(1, j);
-        umma_commit(&kv_empty[j % kKvStages]);   // K_j and V_j are no longer needed by either group
-        if (more) issue_s(1, j + 1);
+        if (leader) umma_commit(&kv_empty[j % kKvStages]);   // K_j and V_j are no longer needed by either group
+        __syncwarp();
+        if (more) issue_s(1, j + 2);
       }
     }
     __syncwarp();
@@ -158,49 +170,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    const uint32_t tS = tmem + w * 128, tO = tmem + 256 + w * 64, tP = tmem + 384 + w * 64;
-    uint8_t* sPw = sP + w * 2 * kTileBytes;
+    const uint32_t tO = tmem + 256 + w * 64;
     float m_run = -INFINITY, m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < n; ++j) {
-      mbar_wait(&s_full[w], j & 1);
+      const int bf = j & 1;
+      const uint32_t tS = tmem + w * 128 + bf * 64, tP = tmem + 384 + w * 64 + bf * 32;
+      mbar_wait(&s_full[w * 2 + bf], (j >> 1) & 1);
       tc_fence_after();
-      const int kv_valid = p.L - j * 128;  // keys of this tile that exist
-      // ---- pass 1: row maximum (S stays in tensor memory; 32 columns in registers at a time)
-      float mx = -INFINITY;
-      if (kv_valid >= 128) {   // full tile: no key masking on the hot path (the ALU pipe is the busiest one in this kernel)
-        // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is reduced
-        uint32_t sb[2][32];
-        tmem_ld_32x32b_x32(tS + lane_off, sb[0]);
+      uint32_t s[64];
+      {
+        uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+        uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+        tmem_ld_32x32b_x32(tS + lane_off, s0);
+        tmem_ld_32x32b_x32(tS + lane_off + 32, s1);
+        tmem_wait_ld();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[w * 2 + bf]);   // S is in registers: the buffer can take S(j+2)
+      const int kv_valid = p.L - j * kKvTile;
+      const bool full = kv_valid >= kKvTile;
+      float mx;
+      if (full) {
+        float m0 = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1])), m1 = fmaxf(__uint_as_float(s[2]), __uint_as_float(s[3]));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_wait_ld();
-          if (c + 1 < 4) tmem_ld_32x32b_x32(tS + lane_off + (c + 1) * 32, sb[(c + 1) & 1]);
-          const uint32_t (&s)[32] = sb[c & 1];
-          float m0 = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1])), m1 = fmaxf(__uint_as_float(s[2]), __uint_as_float(s[3]));
-#pragma unroll
-          for (int i = 4; i < 32; i += 4) {
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
-          }
-          mx = fmaxf(mx, fmaxf(m0, m1));
+        for (int i = 4; i < 64; i += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
         }
+        mx = fmaxf(m0, m1);
       } else {
+        mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t s[32];
-          tmem_ld_32x32b_x32(tS + lane_off + c * 32, s);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
-        }
+        for (int i = 0; i < 64; ++i)
+          if (i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
       }
       m_run = fmaxf(m_run, mx * p.scale_log2);
       if (j > 0) {
-        mbar_wait(&pv_done[w], (j - 1) & 1);   // previous P V finished: O may be rescaled, P may be overwritten
-        tc_fence_after();
         const bool need = (m_run - m_used) > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
+          // rare: rescale the O accumulator; every PV issued so far must have completed (they complete in order)
+          mbar_wait(&p_empty[w * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          tc_fence_after();
           const float f = ex2(m_used - m_run);
           m_used = m_run;
           l *= f;
@@ -221,61 +232,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       } else {
         m_used = m_run;
       }
-      // ---- pass 2: P = exp2(S*scale - m), row sum, bf16 P back to tensor memory (or swizzled shared memory)
-      float sum = 0.f;
-      uint32_t s2[2][32];
-      tmem_ld_32x32b_x32(tS + lane_off, s2[0]);
+      uint32_t pk[32];
+      if (full) {
+        float sa = 0.f, sb = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_wait_ld();
-        if (c + 1 < 4) tmem_ld_32x32b_x32(tS + lane_off + (c + 1) * 32, s2[(c + 1) & 1]);
-        const uint32_t (&s)[32] = s2[c & 1];
-        uint32_t pk[16];
-#pragma unroll
-        if (kv_valid >= 128) {
-          float sa = 0.f, sb = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
-            const float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
-            sa += p0;
-            sb += p1;
-            pk[i] = pack_bf16x2(p0, p1);
-          }
-          sum += sa + sb;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
-            float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
-            if (c * 32 + 2 * i >= kv_valid) p0 = 0.f;
-            if (c * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
-            sum += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
-          }
+        for (int i = 0; i < 32; ++i) {
+          const float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
+          const float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
+          sa += p0;
+          sb += p1;
+          pk[i] = pack_bf16x2(p0, p1);
         }
-        if (p.p_in_tmem) {
-          tmem_st_32x32b_x16(tP + lane_off + c * 16, pk);
-        } else {
-          uint8_t* rowp = sPw + (c >> 1) * kTileBytes + row * 128;
+        l += sa + sb;
+      } else {
+        float sum = 0.f;
 #pragma unroll
-          for (int pc = 0; pc < 4; ++pc)
-            *reinterpret_cast<uint4*>(rowp + ((((c & 1) * 4 + pc) ^ (row & 7)) << 4)) =
-                make_uint4(pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+        for (int i = 0; i < 32; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
+          float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
+          if (2 * i >= kv_valid) p0 = 0.f;
+          if (2 * i + 1 >= kv_valid) p1 = 0.f;
+          sum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
         }
+        l += sum;
       }
-      l += sum;
-      if (p.p_in_tmem) tmem_wait_st();
-      else fence_proxy_async();
+      mbar_wait(&p_empty[w * 2 + bf], ((j >> 1) & 1) ^ 1);   // P V of tile j-2 has finished reading this P buffer
+      tc_fence_after();
+      {
+        uint32_t (&p0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[0]);
+        uint32_t (&p1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[16]);
+        tmem_st_32x32b_x16(tP + lane_off, p0);
+        tmem_st_32x32b_x16(tP + lane_off + 16, p1);
+      }
+      tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[w]);
-        mbar_arrive(&p_full[w]);
-      }
+      if (lane == 0) mbar_arrive(&p_full[w * 2 + bf]);
     }
-    // ---- epilogue
-    mbar_wait(&pv_done[w], (n - 1) & 1);
+    // ---- epilogue: wait for the last P V of this group
+    mbar_wait(&p_empty[w * 2 + ((n - 1) & 1)], ((n - 1) >> 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const int qrow = q0 + w * 128 + row;
@@ -336,18 +332,18 @@ extern "C" int of_attn_fwd(const of_attn_args* a, void* stream_) {
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_head_tmap(&tq, a->q, a->D, a->H, a->L, a->B, a->q_ld, a->q_batch_stride, 128)) != OF_OK) return rc;
-  if ((rc = make_head_tmap(&tk, a->k, a->D, a->KVH, a->L, a->B, a->kv_ld, a->kv_batch_stride, 128)) != OF_OK) return rc;
-  if ((rc = make_head_tmap(&tv, a->v, a->D, a->KVH, a->L, a->B, a->kv_ld, a->kv_batch_stride, 128)) != OF_OK) return rc;
+  if ((rc = make_head_tmap(&tk, a->k, a->D, a->KVH, a->L, a->B, a->kv_ld, a->kv_batch_stride, kKvTile)) != OF_OK) return rc;
+  if ((rc = make_head_tmap(&tv, a->v, a->D, a->KVH, a->L, a->B, a->kv_ld, a->kv_batch_stride, kKvTile)) != OF_OK) return rc;
   AttnFwdParams p;
   p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.L = a->L; p.D = a->D;
-  p.n_kv_tiles = (a->L + 127) / 128;
+  p.n_kv_tiles = (a->L + kKvTile - 1) / kKvTile;
   p.scale_log2 = (a->scale > 0.f ? a->scale : 1.0f / sqrtf((float)a->D)) * 1.4426950408889634f;
   p.p_in_tmem = a->variant == 1 ? 0 : 1;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->out_ld;
   p.out_bs = a->out_batch_stride;
   p.lse = a->lse;
-  size_t smem_bytes = 1024 + kTileBytes * (2 + 2 * kKvStages + 4) + 256;
+  size_t smem_bytes = 1024 + 2 * kTileBytes + kKvStages * 2 * kKvBytes + 512;
   static bool attr_set = false;
   if (!attr_set) {
     OF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -138,7 +138,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp runs the loop convergently; only the TMA / expect_tx instructions are predicated on the elected lane, so
+    //  coordinates and descriptors stay in uniform registers instead of going through per-instruction ELECT waterfall loops)
+    const bool leader = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
@@ -147,6 +150,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + kABytes;
+          if (leader) {
           mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
           if (p.mode == OF_GEMM_FWD) {
             int t = it / p.k_chunks;
@@ -184,6 +188,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + j * 64, lc * kBK + shift, b);
             }
           }
+          }
+          __syncwarp();
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -192,8 +198,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
+    const bool leader = elect_one();
+    {
       const uint32_t idesc = make_idesc_bf16(kBM, p.BN, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
@@ -209,20 +216,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tc_fence_after();
           uint32_t sa = smem_u32(ring + (size_t)stage * p.stage_bytes);
           uint32_t sb = sa + kABytes;
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            uint64_t da = a_mn ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-            uint64_t db = b_mn ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16_ss(tmem_d, da, db, idesc, (it > tc.k_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              uint64_t da = a_mn ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+              uint64_t db = b_mn ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+              umma_f16_ss(tmem_d, da, db, idesc, (it > tc.k_begin || k > 0) ? 1u : 0u);
+            }
+            if (kMC) umma_commit_mc(&empty_bar[stage], 3);
+            else umma_commit(&empty_bar[stage]);
           }
-          if (kMC) umma_commit_mc(&empty_bar[stage], 3);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if (leader) umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
