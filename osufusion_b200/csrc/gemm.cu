@@ -103,11 +103,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages; // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* stat_sm = reinterpret_cast<float*>(tmem_base_slot + 2);   // [2] per-tile GroupNorm partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    stat_sm[0] = 0.f;
+    stat_sm[1] = 0.f;
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < p.num_stages; ++i) {
@@ -347,17 +350,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
         }
-        if (p.stats) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-          }
-          if (lane == 0) {
-            atomicAdd(p.stats + 2 * tc.b, (double)s1);
-            atomicAdd(p.stats + 2 * tc.b + 1, (double)s2);
-          }
-        }
       } else {
         // WGRAD: atomically accumulate fp32 into out_f32[tap][m][n]
         const bool row_ok = (m < p.K) && k_nonempty;
@@ -381,7 +373,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // accumulator drained: the MMA warp may start the next tile into it
+      if (p.mode == OF_GEMM_FWD) {
+      if (p.stats) {
+        // one pair of global double atomics per TILE: the 8 epilogue warps first combine in shared memory
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+          atomicAdd(&stat_sm[0], s1);
+          atomicAdd(&stat_sm[1], s2);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          atomicAdd(p.stats + 2 * tc.b, (double)stat_sm[0]);
+          atomicAdd(p.stats + 2 * tc.b + 1, (double)stat_sm[1]);
+          stat_sm[0] = 0.f;
+          stat_sm[1] = 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
