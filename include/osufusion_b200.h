@@ -279,6 +279,45 @@ int of_dora_grad(const float* W, const float* A, const float* B, const float* ma
                  const float* n2, const float* dW_packed, int Cin_pad, long long tap_stride, float* dA, float* dB, float* dmag,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Grouped ("multi-tensor") kernels: one launch over many parameter tensors.  Descriptor tables are arrays in DEVICE memory
+ * built once per model by the host.
+ *   of_film_fwd  : every FiLM head `ResidualBlock.mlp[1]` (nn.Linear(2*dim_emb, 2*C), residual.py:104-111) at once:
+ *                  out[out_off_g + m*N_g + n] = bf16(bias_g[n] + sum_k bf16(W_g[n,k]) * x[m,k]);  x (M, K) fp32 already holds
+ *                  bf16-rounded values (SiLU(cat(t, c)) under autocast).  Bytes: sum_g N_g*K*4 read once.
+ *   of_film_bwd  : dW_g[n,k] = sum_m dss[m,n] x[m,k] and dbias_g[n] = sum_m dss[m,n] are WRITTEN (not accumulated; NULL =
+ *                  frozen), d_emb[m,k] += sum_g sum_n dss[m,n] bf16(W_g[n,k]) (atomic).  chunks = (group, first row) pairs, each
+ *                  covering at most of_film_chunk_rows() rows of one head.  Bytes: weights read once + gradients written once.
+ *   of_pack_weights : fp32 (Cout, Cin, k) master weights -> bf16 [k][Cout][cin_pad] GEMM operands (k == 1: plain cast) for a
+ *                  whole list of tensors; segment i owns CTAs [cta_begin_i, cta_begin_{i+1}), of_pack_seg_ctas() CTAs each
+ *                  (-1: unsupported kernel size, use of_pack_conv_weight).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* W;      /* (N, K) fp32 */
+  const float* bias;   /* (N) or NULL */
+  float* dW;           /* (N, K) fp32 or NULL */
+  float* dbias;        /* (N) or NULL */
+  long long out_off;   /* offset (floats) of this head's (M, N) block in out / dss: M * row_start */
+  int N;
+  int row_start;       /* first row of this head in the concatenated row space */
+} of_film_group;
+
+typedef struct {
+  const float* src;
+  void* dst;
+  int Cout, Cin, k, cin_pad;
+  int cta_begin;
+  int _pad;
+} of_pack_seg;
+
+int of_film_fwd(const of_film_group* groups_dev, int num_groups, int total_rows, const float* x, int M, int K, float* out,
+                void* stream);
+int of_film_bwd(const of_film_group* groups_dev, const int* chunks_dev, int num_chunks, const float* dss, const float* x, int M,
+                int K, float* d_emb, void* stream);
+int of_film_chunk_rows(void);
+int of_pack_weights(const of_pack_seg* segs_dev, int num_segs, int total_ctas, void* stream);
+int of_pack_seg_ctas(int Cout, int Cin, int k, int cin_pad);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,14 @@ class RbArgs(C.Structure):
     ]
 
 
+class FilmGroup(C.Structure):
+    _fields_ = [("W", P), ("bias", P), ("dW", P), ("dbias", P), ("out_off", LL), ("N", I), ("row_start", I)]
+
+
+class PackSeg(C.Structure):
+    _fields_ = [("src", P), ("dst", P), ("Cout", I), ("Cin", I), ("k", I), ("cin_pad", I), ("cta_begin", I), ("_pad", I)]
+
+
 # name -> argtypes (the trailing stream pointer included); mirrors include/osufusion_b200.h
 _SIGS = {
     "of_gemm": [C.POINTER(GemmArgs), P],
@@ -110,10 +118,14 @@ _SIGS = {
     "of_pack_conv_weight": [P, I, I, I, P, I, I, I, P],
     "of_unpack_conv_wgrad": [P, I, I, I, I, I, P, I, P],
     "of_cast_f32_bf16": [P, P, LL, P],
+    "of_film_fwd": [P, I, I, P, I, I, P, P],
+    "of_film_bwd": [P, P, I, P, P, I, I, P, P],
+    "of_pack_weights": [P, I, I, P],
     "of_dora_merge": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P],
     "of_dora_grad": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P, P, P],
 }
-EXPORTS = ["of_last_error", "of_version", "of_launch_count", "of_reset_launch_count", *_SIGS.keys()]
+_PLAIN = {"of_film_chunk_rows": [], "of_pack_seg_ctas": [I, I, I, I]}    # host-side helpers: no stream argument, return a value
+EXPORTS = ["of_last_error", "of_version", "of_launch_count", "of_reset_launch_count", *_SIGS.keys(), *_PLAIN.keys()]
 
 
 def lib() -> C.CDLL:
@@ -128,6 +140,10 @@ def lib() -> C.CDLL:
         _lib.of_last_error.restype = C.c_char_p
         _lib.of_launch_count.restype = C.c_longlong
         for name, sig in _SIGS.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = sig
+            fn.restype = C.c_int
+        for name, sig in _PLAIN.items():
             fn = getattr(_lib, name)
             fn.argtypes = sig
             fn.restype = C.c_int

@@ -31,38 +31,64 @@ __device__ __forceinline__ GnCtx make_ctx(const of_rb_args& a) {
   return g;
 }
 
-// Per-thread constants for its 8 channels.
+// Per-thread constants for its 8 channels, folded so that the per-element work is two FMAs:
+//   xhat = y*rstd + nmr            (nmr = -mean*rstd)
+//   z    = y*A + Bc                (A = rstd*gamma, Bc = beta - mean*rstd*gamma: the same folding torch's GroupNorm kernel uses)
+template <bool FILM>
 struct ChanConst {
-  V8 gamma, beta, sp1, shift;
-  float mean, rstd;
-  bool film;
+  V8 A, Bc, sp1, shift;   // sp1/shift are dead (never materialised) when FILM is false
+  float rstd, nmr;
 };
 
-__device__ __forceinline__ ChanConst load_consts(const GnCtx& g, int b, int c0) {
-  ChanConst k;
-  k.gamma = ld_f32x8(g.gamma + c0);
-  k.beta = ld_f32x8(g.beta + c0);
-  k.film = g.ss != nullptr;
-  if (k.film) {
+template <bool FILM>
+__device__ __forceinline__ ChanConst<FILM> load_consts(const GnCtx& g, int b, int c0) {
+  ChanConst<FILM> k;
+  V8 gamma = ld_f32x8(g.gamma + c0);
+  V8 beta = ld_f32x8(g.beta + c0);
+  if (FILM) {
     V8 sc = ld_f32x8(g.ss + (long long)b * 2 * g.C + c0);
     k.shift = ld_f32x8(g.ss + (long long)b * 2 * g.C + g.C + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) k.sp1.v[j] = bf16_round(sc.v[j] + 1.0f);  // reference: bf16 `scale + 1` under autocast
   }
-  gn_mean_rstd(g.stats, b, (double)g.L * (double)g.C, g.eps, k.mean, k.rstd);
+  float mean;
+  gn_mean_rstd(g.stats, b, (double)g.L * (double)g.C, g.eps, mean, k.rstd);
+  k.nmr = -mean * k.rstd;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    k.A.v[j] = k.rstd * gamma.v[j];
+    k.Bc.v[j] = fmaf(k.nmr, gamma.v[j], beta.v[j]);
+  }
   return k;
 }
 
-// xhat, z = xhat*gamma+beta, f = FiLM(z), h = silu(f) for one 8-channel vector.
-__device__ __forceinline__ void gn_eval(const ChanConst& k, const V8& y, V8& xhat, V8& z, V8& f, V8& h) {
+// sigmoid via MUFU.EX2 + MUFU.RCP (relative error ~1e-6: far below the bf16 rounding of every tensor these kernels emit)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// z = GroupNorm(y), f = FiLM(z), h = silu(f) = f*sg for one 8-channel vector (sg = sigmoid(f), reused by the backward kernels).
+template <bool FILM>
+__device__ __forceinline__ void gn_eval(const ChanConst<FILM>& k, const V8& y, V8& z, V8& f, V8& h, V8& sg) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    xhat.v[j] = (y.v[j] - k.mean) * k.rstd;
-    z.v[j] = xhat.v[j] * k.gamma.v[j] + k.beta.v[j];
-    f.v[j] = k.film ? (z.v[j] * k.sp1.v[j] + k.shift.v[j]) : z.v[j];
-    h.v[j] = silu_acc(f.v[j]);
+    z.v[j] = fmaf(y.v[j], k.A.v[j], k.Bc.v[j]);
+    f.v[j] = FILM ? fmaf(z.v[j], k.sp1.v[j], k.shift.v[j]) : z.v[j];
+    sg.v[j] = sigmoid_fast(f.v[j]);
+    h.v[j] = f.v[j] * sg.v[j];
   }
 }
+template <bool FILM>
+__device__ __forceinline__ V8 gn_h(const ChanConst<FILM>& k, const V8& y) {
+  V8 z, f, h, sg;
+  gn_eval(k, y, z, f, h, sg);
+  return h;
+}
+__device__ __forceinline__ V8 cvt_bf16x8(const uint4& u) {
+  V8 r;
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 
 struct Map {
   int vecs, rpar, vi, rsub, c0, b, l_begin, l_end;
@@ -71,7 +97,7 @@ struct Map {
 __device__ __forceinline__ Map make_map(int C, int L, int rows_per_cta) {
   Map m;
   m.vecs = C >> 3;
-  m.rpar = kRbThreads / m.vecs;
+  m.rpar = blockDim.x / m.vecs;   // the host sizes the CTA as vecs * rpar threads
   m.vi = threadIdx.x % m.vecs;
   m.rsub = threadIdx.x / m.vecs;
   m.active = m.rsub < m.rpar;
@@ -120,46 +146,68 @@ __device__ __forceinline__ void cta_channel_reduce(const Map& m, int C, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(kRbThreads) rb_apply_fwd_kernel(const of_rb_args a, const int rpc) {
+// All kernels walk their rows in batches of R: the 16-byte loads of a whole batch are issued before any arithmetic, so a
+// thread keeps R (or 2-3 R) independent requests in flight instead of paying one memory latency per row.
+#define RB_FOR_BATCH(R) for (int l0 = m.l_begin + m.rsub; l0 < m.l_end; l0 += (R) * m.rpar)
+#define RB_ROW(r) (l0 + (r) * m.rpar)
+
+template <bool FILM>
+__global__ void __launch_bounds__(kRbThreads, 3) rb_apply_fwd_kernel(const of_rb_args a, const int rpc) {
+  constexpr int R = 8;
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L, rpc);
   if (!m.active) return;
-  ChanConst k = load_consts(g, m.b, m.c0);
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
-  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
-    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
-    gn_eval(k, y, xh, z, f, h);
-    st_bf16x8(out + m.b * a.out_bf16_bs + (long long)l * a.out_bf16_ld + m.c0, h);
+  ChanConst<FILM> k = load_consts<FILM>(g, m.b, m.c0);
+  const __nv_bfloat16* yb = g.y + m.b * g.y_bs + m.c0;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out_bf16) + m.b * a.out_bf16_bs + m.c0;
+  RB_FOR_BATCH(R) {
+    uint4 raw[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (RB_ROW(r) < m.l_end) raw[r] = ldg16(yb + (long long)RB_ROW(r) * g.y_ld);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (RB_ROW(r) < m.l_end) st_bf16x8(out + (long long)RB_ROW(r) * a.out_bf16_ld, gn_h(k, cvt_bf16x8(raw[r])));
   }
 }
 
 // Row-wise dot products dot(h[b,l,:], vec): channel-owner mapping (constants loaded once per thread), per-row partials
 // combined through shared memory (one shuffle-reduced atomic per warp when a warp lies inside one row).
-__global__ void __launch_bounds__(kRbThreads) rb_rowdot_kernel(const of_rb_args a, const int rpc) {
+__global__ void __launch_bounds__(kRbThreads, 3) rb_rowdot_kernel(const of_rb_args a, const int rpc) {
+  constexpr int R = 8;
   extern __shared__ float s_red[];   // [rpc] row accumulators
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L, rpc);
   for (int i = threadIdx.x; i < rpc; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
   if (m.active) {
-    ChanConst k = load_consts(g, m.b, m.c0);
+    ChanConst<false> k = load_consts<false>(g, m.b, m.c0);
     V8 w = ld_f32x8(a.vec + (long long)m.b * a.vec_bs + m.c0);
     if (a.mode == 0) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) w.v[j] = bf16_round(w.v[j]);
     }
     const bool warp_in_row = (m.vecs & 31) == 0;
-    for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
-      V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
-      gn_eval(k, y, xh, z, f, h);
-      float acc = 0.f;
+    const __nv_bfloat16* yb = g.y + m.b * g.y_bs + m.c0;
+    RB_FOR_BATCH(R) {
+      uint4 raw[R];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc += bf16_round(h.v[j]) * w.v[j];
-      if (warp_in_row) {
-        acc = warp_sum(acc);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&s_red[l - m.l_begin], acc);
-      } else {
-        atomicAdd(&s_red[l - m.l_begin], acc);
+      for (int r = 0; r < R; ++r)
+        if (RB_ROW(r) < m.l_end) raw[r] = ldg16(yb + (long long)RB_ROW(r) * g.y_ld);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          V8 h = gn_h(k, cvt_bf16x8(raw[r]));
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc = fmaf(bf16_round(h.v[j]), w.v[j], acc);
+          if (warp_in_row) {
+            acc = warp_sum(acc);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_red[RB_ROW(r) - m.l_begin], acc);
+          } else {
+            atomicAdd(&s_red[RB_ROW(r) - m.l_begin], acc);
+          }
+        }
       }
     }
   }
@@ -196,64 +244,113 @@ __global__ void __launch_bounds__(1024) softmax_rows_kernel(float* rows, int L) 
   for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] = expf(r[i] - mx) * inv;
 }
 
-__global__ void __launch_bounds__(kRbThreads) rb_pool_kernel(const of_rb_args a, const int rpc) {
+__global__ void __launch_bounds__(kRbThreads, 3) rb_pool_kernel(const of_rb_args a, const int rpc) {
+  constexpr int R = 8;
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L, rpc);
-  ChanConst k;
-  if (m.active) k = load_consts(g, m.b, m.c0);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int l = m.l_begin + m.rsub; m.active && l < m.l_end; l += m.rpar) {
-    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
-    gn_eval(k, y, xh, z, f, h);
-    const float pl = bf16_round(a.p[(long long)m.b * a.L + l]);  // einsum operand is cast to bf16 (autocast)
+  if (m.active) {
+    ChanConst<false> k = load_consts<false>(g, m.b, m.c0);
+    const __nv_bfloat16* yb = g.y + m.b * g.y_bs + m.c0;
+    const float* pb = a.p + (long long)m.b * a.L;
+    RB_FOR_BATCH(R) {
+      uint4 raw[R];
+      float pl[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += bf16_round(h.v[j]) * pl;
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          raw[r] = ldg16(yb + (long long)RB_ROW(r) * g.y_ld);
+          pl[r] = pb[RB_ROW(r)];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          V8 h = gn_h(k, cvt_bf16x8(raw[r]));
+          const float pw = bf16_round(pl[r]);  // einsum operand is cast to bf16 (autocast)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(bf16_round(h.v[j]), pw, acc[j]);
+        }
+      }
+    }
   }
   cta_channel_reduce(m, a.C, acc, s_red, a.acc_bc + (long long)m.b * a.C);
 }
 
-__global__ void __launch_bounds__(kRbThreads) rb_gate_fwd_kernel(const of_rb_args a, const int rpc) {
+__global__ void __launch_bounds__(kRbThreads, 2) rb_gate_fwd_kernel(const of_rb_args a, const int rpc) {
+  constexpr int R = 4;
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L, rpc);
   if (!m.active) return;
-  ChanConst k = load_consts(g, m.b, m.c0);
+  ChanConst<false> k = load_consts<false>(g, m.b, m.c0);
   V8 gate = ld_f32x8(a.gate + (long long)m.b * a.C + m.c0);
-  const __nv_bfloat16* r16 = reinterpret_cast<const __nv_bfloat16*>(a.res_bf16);
-  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
-  for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
-    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h, o;
-    gn_eval(k, y, xh, z, f, h);
-    V8 r;
-    if (a.res_f32) r = ld_f32x8(a.res_f32 + m.b * a.res_f32_bs + (long long)l * a.res_f32_ld + m.c0);
-    else r = ld_bf16x8(r16 + m.b * a.res_bf16_bs + (long long)l * a.res_bf16_ld + m.c0);
+  const __nv_bfloat16* yb = g.y + m.b * g.y_bs + m.c0;
+  const __nv_bfloat16* r16 = a.res_bf16 ? reinterpret_cast<const __nv_bfloat16*>(a.res_bf16) + m.b * a.res_bf16_bs + m.c0 : nullptr;
+  const float* r32 = a.res_f32 ? a.res_f32 + m.b * a.res_f32_bs + m.c0 : nullptr;
+  __nv_bfloat16* o16 = a.out_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.out_bf16) + m.b * a.out_bf16_bs + m.c0 : nullptr;
+  float* o32 = a.out_f32 ? a.out_f32 + m.b * a.out_f32_bs + m.c0 : nullptr;
+  RB_FOR_BATCH(R) {
+    uint4 raw[R];
+    V8 res[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = h.v[j] * gate.v[j] + r.v[j];
-    if (a.out_f32) st_f32x8(a.out_f32 + m.b * a.out_f32_bs + (long long)l * a.out_f32_ld + m.c0, o);
-    if (o16) st_bf16x8(o16 + m.b * a.out_bf16_bs + (long long)l * a.out_bf16_ld + m.c0, o);
+    for (int r = 0; r < R; ++r) {
+      if (RB_ROW(r) < m.l_end) {
+        raw[r] = ldg16(yb + (long long)RB_ROW(r) * g.y_ld);
+        if (r32) res[r] = ld_f32x8(r32 + (long long)RB_ROW(r) * a.res_f32_ld);
+        else res[r] = cvt_bf16x8(ldg16(r16 + (long long)RB_ROW(r) * a.res_bf16_ld));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (RB_ROW(r) < m.l_end) {
+        V8 h = gn_h(k, cvt_bf16x8(raw[r])), o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = fmaf(h.v[j], gate.v[j], res[r].v[j]);
+        if (o32) st_f32x8(o32 + (long long)RB_ROW(r) * a.out_f32_ld, o);
+        if (o16) st_bf16x8(o16 + (long long)RB_ROW(r) * a.out_bf16_ld, o);
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(kRbThreads) rb_gate_bwd_reduce_kernel(const of_rb_args a, const int rpc) {
+__global__ void __launch_bounds__(kRbThreads, 3) rb_gate_bwd_reduce_kernel(const of_rb_args a, const int rpc) {
+  constexpr int R = 4;
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L, rpc);
-  ChanConst k;
-  if (m.active) k = load_consts(g, m.b, m.c0);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int l = m.l_begin + m.rsub; m.active && l < m.l_end; l += m.rpar) {
-    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h;
-    gn_eval(k, y, xh, z, f, h);
-    V8 d = ld_f32x8(a.dout_f32 + m.b * a.dout_f32_bs + (long long)l * a.dout_f32_ld + m.c0);
+  if (m.active) {
+    ChanConst<false> k = load_consts<false>(g, m.b, m.c0);
+    const __nv_bfloat16* yb = g.y + m.b * g.y_bs + m.c0;
+    const float* db = a.dout_f32 + m.b * a.dout_f32_bs + m.c0;
+    RB_FOR_BATCH(R) {
+      uint4 raw[R];
+      V8 d[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += d.v[j] * h.v[j];
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          raw[r] = ldg16(yb + (long long)RB_ROW(r) * g.y_ld);
+          d[r] = ld_f32x8(db + (long long)RB_ROW(r) * a.dout_f32_ld);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          V8 h = gn_h(k, cvt_bf16x8(raw[r]));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[r].v[j], h.v[j], acc[j]);
+        }
+      }
+    }
   }
   cta_channel_reduce(m, a.C, acc, s_red, a.acc_bc + (long long)m.b * a.C);
 }
 
-template <int MODE>
+template <int MODE, bool FILM>
 __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb_args a, const int rpc) {
+  constexpr int R = MODE == 0 ? 2 : 4;
   __shared__ float sm[32];
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
@@ -262,7 +359,8 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
   float dgam[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbet[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float dsc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dsh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dwk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (m.active) {
-    ChanConst k = load_consts(g, m.b, m.c0);
+    ChanConst<FILM> k = load_consts<FILM>(g, m.b, m.c0);
+    const V8 gamma = ld_f32x8(g.gamma + m.c0);
     V8 gate, dpool, wk;
     if (MODE == 0) {
       gate = ld_f32x8(a.gate + (long long)m.b * a.C + m.c0);
@@ -271,50 +369,76 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
 #pragma unroll
       for (int j = 0; j < 8; ++j) wk.v[j] = bf16_round(wk.v[j]);
     }
-    const __nv_bfloat16* dh16 = reinterpret_cast<const __nv_bfloat16*>(a.dh_bf16);
-    __nv_bfloat16* dxh = reinterpret_cast<__nv_bfloat16*>(a.dxhat_bf16);
-    __nv_bfloat16* do16 = reinterpret_cast<__nv_bfloat16*>(a.dout_bf16);
-    for (int l = m.l_begin + m.rsub; l < m.l_end; l += m.rpar) {
-      V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0), xh, z, f, h, dh, dx;
-      gn_eval(k, y, xh, z, f, h);
-      if (MODE == 0) {
-        V8 d = ld_f32x8(a.dout_f32 + m.b * a.dout_f32_bs + (long long)l * a.dout_f32_ld + m.c0);
-        const float pl = bf16_round(a.p[(long long)m.b * a.L + l]);
-        const float da = a.da[(long long)m.b * a.L + l];
+    const __nv_bfloat16* yb = g.y + m.b * g.y_bs + m.c0;
+    const __nv_bfloat16* dh16 = MODE == 1 ? reinterpret_cast<const __nv_bfloat16*>(a.dh_bf16) + m.b * a.dh_bs + m.c0 : nullptr;
+    const float* d32 = MODE == 0 ? a.dout_f32 + m.b * a.dout_f32_bs + m.c0 : nullptr;
+    __nv_bfloat16* dxh = reinterpret_cast<__nv_bfloat16*>(a.dxhat_bf16) + m.b * a.dxhat_bs + m.c0;
+    __nv_bfloat16* do16 = (MODE == 0 && a.dout_bf16) ? reinterpret_cast<__nv_bfloat16*>(a.dout_bf16) + m.b * a.dout_bf16_bs + m.c0 : nullptr;
+    const float* pb = MODE == 0 ? a.p + (long long)m.b * a.L : nullptr;
+    const float* dab = MODE == 0 ? a.da + (long long)m.b * a.L : nullptr;
+    RB_FOR_BATCH(R) {
+      uint4 raw[R];
+      V8 din[R];
+      float pl[R], dal[R];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          dh.v[j] = d.v[j] * gate.v[j] + dpool.v[j] * pl + da * wk.v[j];
-          dwk[j] += da * bf16_round(h.v[j]);
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          raw[r] = ldg16(yb + (long long)RB_ROW(r) * g.y_ld);
+          if (MODE == 0) {
+            din[r] = ld_f32x8(d32 + (long long)RB_ROW(r) * a.dout_f32_ld);
+            pl[r] = pb[RB_ROW(r)];
+            dal[r] = dab[RB_ROW(r)];
+          } else {
+            din[r] = cvt_bf16x8(ldg16(dh16 + (long long)RB_ROW(r) * a.dh_ld));
+          }
         }
-        if (m.vi == 0) sda += da;
-        if (do16) st_bf16x8(do16 + m.b * a.dout_bf16_bs + (long long)l * a.dout_bf16_ld + m.c0, d);
-      } else {
-        dh = ld_bf16x8(dh16 + m.b * a.dh_bs + (long long)l * a.dh_ld + m.c0);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        // silu'(f) = s*(1 + f*(1-s)) with s = h/f reused from the forward recompute (s = sigmoid(f))
-        const float sg = 1.0f / (1.0f + expf(-f.v[j]));
-        float df = dh.v[j] * (sg * (1.0f + f.v[j] * (1.0f - sg)));
-        float dz = df;
-        if (MODE == 1 && k.film) {
-          dsc[j] += df * z.v[j];
-          dsh[j] += df;
-          dz = df * k.sp1.v[j];
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          const long long l = RB_ROW(r);
+          V8 y = cvt_bf16x8(raw[r]), z, f, h, sg, dh, dx;
+          gn_eval(k, y, z, f, h, sg);
+          if (MODE == 0) {
+            const float pw = bf16_round(pl[r]);
+            const float da = dal[r];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              dh.v[j] = fmaf(din[r].v[j], gate.v[j], fmaf(dpool.v[j], pw, da * wk.v[j]));
+              dwk[j] = fmaf(da, bf16_round(h.v[j]), dwk[j]);
+            }
+            if (m.vi == 0) sda += da;
+            if (do16) st_bf16x8(do16 + l * a.dout_bf16_ld, din[r]);
+          } else {
+            dh = din[r];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // silu'(f) = s*(1 + f*(1-s)), s = sigmoid(f) from the forward recompute
+            const float s = sg.v[j];
+            float df = dh.v[j] * (s * fmaf(f.v[j], 1.0f - s, 1.0f));
+            float dz = df;
+            if (FILM) {
+              dsc[j] = fmaf(df, z.v[j], dsc[j]);
+              dsh[j] += df;
+              dz = df * k.sp1.v[j];
+            }
+            const float xh = fmaf(y.v[j], k.rstd, k.nmr);
+            dgam[j] = fmaf(dz, xh, dgam[j]);
+            dbet[j] += dz;
+            dx.v[j] = dz * gamma.v[j];
+            float dxr = bf16_round(dx.v[j]);  // what pass 2 will read back
+            s1 += dxr;
+            s2 = fmaf(dxr, xh, s2);
+          }
+          st_bf16x8(dxh + l * a.dxhat_ld, dx);
         }
-        dgam[j] += dz * xh.v[j];
-        dbet[j] += dz;
-        dx.v[j] = dz * k.gamma.v[j];
-        float dxr = bf16_round(dx.v[j]);  // what pass 2 will read back
-        s1 += dxr;
-        s2 += dxr * xh.v[j];
       }
-      st_bf16x8(dxh + m.b * a.dxhat_bs + (long long)l * a.dxhat_ld + m.c0, dx);
     }
   }
   // CTA-level combine of the per-channel partials in shared memory (accumulators stay in registers: no indirection)
-  float* dst[5] = {a.dgamma, a.dbeta, (MODE == 1 && a.ss) ? a.dss + (long long)blockIdx.y * 2 * a.C : nullptr,
-                   (MODE == 1 && a.ss) ? a.dss + (long long)blockIdx.y * 2 * a.C + a.C : nullptr, MODE == 0 ? a.dwk : nullptr};
+  float* dst[5] = {a.dgamma, a.dbeta, FILM ? a.dss + (long long)blockIdx.y * 2 * a.C : nullptr,
+                   FILM ? a.dss + (long long)blockIdx.y * 2 * a.C + a.C : nullptr, MODE == 0 ? a.dwk : nullptr};
   for (int c = threadIdx.x; c < 5 * a.C; c += blockDim.x) s_red[c] = 0.f;
   __syncthreads();
   if (m.active) {
@@ -322,7 +446,7 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&s_red[0 * a.C + m.c0 + j], dgam[j]);
       atomicAdd(&s_red[1 * a.C + m.c0 + j], dbet[j]);
-      if (MODE == 1 && a.ss) {
+      if (FILM) {
         atomicAdd(&s_red[2 * a.C + m.c0 + j], dsc[j]);
         atomicAdd(&s_red[3 * a.C + m.c0 + j], dsh[j]);
       }
@@ -344,27 +468,44 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
   }
 }
 
-__global__ void __launch_bounds__(kRbThreads) rb_bwd_apply_kernel(const of_rb_args a, const int rpc) {
+__global__ void __launch_bounds__(kRbThreads, 3) rb_bwd_apply_kernel(const of_rb_args a, const int rpc) {
+  constexpr int R = 4;
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L, rpc);
   float mean, rstd;
   const double n = (double)a.L * (double)a.C;
   gn_mean_rstd(g.stats, m.b, n, g.eps, mean, rstd);
+  const float nmr = -mean * rstd;
   const float m1 = (float)(a.dstats[2 * m.b] / n), m2 = (float)(a.dstats[2 * m.b + 1] / n);
-  const __nv_bfloat16* dxh = reinterpret_cast<const __nv_bfloat16*>(a.dxhat_bf16);
-  __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(a.dy_bf16);
   float db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int l = m.l_begin + m.rsub; m.active && l < m.l_end; l += m.rpar) {
-    V8 y = ld_bf16x8(g.y + m.b * g.y_bs + (long long)l * g.y_ld + m.c0);
-    V8 dx = ld_bf16x8(dxh + m.b * a.dxhat_bs + (long long)l * a.dxhat_ld + m.c0), o;
+  if (m.active) {
+    const __nv_bfloat16* yb = g.y + m.b * g.y_bs + m.c0;
+    const __nv_bfloat16* dxh = reinterpret_cast<const __nv_bfloat16*>(a.dxhat_bf16) + m.b * a.dxhat_bs + m.c0;
+    __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(a.dy_bf16) + m.b * a.dy_bs + m.c0;
+    RB_FOR_BATCH(R) {
+      uint4 raw[R], rdx[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float xh = (y.v[j] - mean) * rstd;
-      o.v[j] = rstd * (dx.v[j] - m1 - xh * m2);
-      db[j] += bf16_round(o.v[j]);
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          raw[r] = ldg16(yb + (long long)RB_ROW(r) * g.y_ld);
+          rdx[r] = ldg16(dxh + (long long)RB_ROW(r) * a.dxhat_ld);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (RB_ROW(r) < m.l_end) {
+          V8 y = cvt_bf16x8(raw[r]), dx = cvt_bf16x8(rdx[r]), o;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = fmaf(y.v[j], rstd, nmr);
+            o.v[j] = rstd * (dx.v[j] - m1 - xh * m2);
+            db[j] += bf16_round(o.v[j]);
+          }
+          st_bf16x8(dy + (long long)RB_ROW(r) * a.dy_ld, o);
+        }
+      }
     }
-    st_bf16x8(dy + m.b * a.dy_bs + (long long)l * a.dy_ld + m.c0, o);
   }
   if (a.dbias) cta_channel_reduce(m, a.C, db, s_red, a.dbias);
 }
@@ -377,14 +518,24 @@ static int check_common(const of_rb_args* a, const char* who) {
   OF_REQUIRE(a->y_ld % 8 == 0, "%s: y_ld %% 8", who);
   return OF_OK;
 }
-// rows per CTA: enough CTAs for ~4 per SM, at least 2 rows per row-lane, at most 64 rows
-static int rb_rows_per_cta(const of_rb_args* a) {
-  const int rpar = kRbThreads / (a->C / 8) > 0 ? kRbThreads / (a->C / 8) : 1;
-  long long want = ((long long)a->B * a->L + 4 * device_sm_count() - 1) / (4 * device_sm_count());
-  int r = (int)want;
-  if (r < 2 * rpar) r = 2 * rpar;
-  if (r > 64) r = 64;
-  return r;
+// CTA = vecs * rpar threads (rpar = rows processed side by side): 256 threads when C/8 divides 256, e.g. 192 for C = 1536.
+static int rb_threads(const of_rb_args* a) {
+  const int vecs = a->C / 8;
+  const int rpar = kRbThreads / vecs > 0 ? kRbThreads / vecs : 1;
+  return vecs * rpar;
+}
+// rows per CTA: one wave of ~4 CTAs per SM, a whole number of row-lanes, at most 64 rows per row-lane
+static int rb_rows_per_cta(const of_rb_args* a, int ctas_per_sm) {
+  const int vecs = a->C / 8;
+  const int rpar = kRbThreads / vecs > 0 ? kRbThreads / vecs : 1;
+  const long long slots = (long long)ctas_per_sm * device_sm_count();
+  long long per_sample = (slots + a->B - 1) / a->B;           // CTAs available to one sample
+  if (per_sample < 1) per_sample = 1;
+  long long r = (a->L + per_sample - 1) / per_sample;
+  r = (r + rpar - 1) / rpar * rpar;
+  if (r < rpar) r = rpar;
+  if (r > 64LL * rpar) r = 64LL * rpar;
+  return (int)r;
 }
 static dim3 rb_grid(const of_rb_args* a, int rpc) { return dim3((a->L + rpc - 1) / rpc, a->B); }
 
@@ -392,9 +543,9 @@ static dim3 rb_grid(const of_rb_args* a, int rpc) { return dim3((a->L + rpc - 1)
 
 using namespace ofx;
 
-#define RB_LAUNCH(kernel)                                                                                                    \
-  const int rpc = rb_rows_per_cta(a);                                                                                        \
-  kernel<<<rb_grid(a, rpc), kRbThreads, 5 * (size_t)a->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(*a, rpc); \
+#define RB_LAUNCH(kernel, ctas_per_sm)                                                                                       \
+  const int rpc = rb_rows_per_cta(a, ctas_per_sm);                                                                                      \
+  kernel<<<rb_grid(a, rpc), rb_threads(a), 5 * (size_t)a->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(*a, rpc); \
   OF_CHECK_CUDA(cudaGetLastError());                                              \
   count_launch();                                                                 \
   return OF_OK;
@@ -403,14 +554,16 @@ extern "C" int of_rb_apply_fwd(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_apply_fwd");
   if (rc) return rc;
   OF_REQUIRE(a->out_bf16 && a->out_bf16_ld % 8 == 0, "of_rb_apply_fwd: bad out_bf16");
-  RB_LAUNCH(rb_apply_fwd_kernel)
+  if (a->ss) { RB_LAUNCH(rb_apply_fwd_kernel<true>, 3) }
+  RB_LAUNCH(rb_apply_fwd_kernel<false>, 3)
 }
 extern "C" int of_rb_rowdot(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_rowdot");
   if (rc) return rc;
+  OF_REQUIRE(a->ss == nullptr, "of_rb_rowdot: FiLM (ss) is only supported by of_rb_apply_fwd / of_rb_bwd_pass1(mode 1)");
   OF_REQUIRE(a->vec && a->out_rows, "of_rb_rowdot: null vec/out_rows");
-  const int rpc = rb_rows_per_cta(a);
-  rb_rowdot_kernel<<<rb_grid(a, rpc), kRbThreads, (size_t)(rpc > 5 * a->C ? rpc : 5 * a->C) * sizeof(float),
+  const int rpc = rb_rows_per_cta(a, 3);
+  rb_rowdot_kernel<<<rb_grid(a, rpc), rb_threads(a), (size_t)(rpc > 5 * a->C ? rpc : 5 * a->C) * sizeof(float),
                      reinterpret_cast<cudaStream_t>(stream)>>>(*a, rpc);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -433,20 +586,23 @@ extern "C" int of_softmax_bwd_rows(const float* p, float* rd, int B, int L, void
 extern "C" int of_rb_pool(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_pool");
   if (rc) return rc;
+  OF_REQUIRE(a->ss == nullptr, "of_rb_pool: FiLM (ss) is only supported by of_rb_apply_fwd / of_rb_bwd_pass1(mode 1)");
   OF_REQUIRE(a->p && a->acc_bc, "of_rb_pool: null p/acc_bc");
-  RB_LAUNCH(rb_pool_kernel)
+  RB_LAUNCH(rb_pool_kernel, 3)
 }
 extern "C" int of_rb_gate_fwd(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_gate_fwd");
   if (rc) return rc;
+  OF_REQUIRE(a->ss == nullptr, "of_rb_gate_fwd: FiLM (ss) is only supported by of_rb_apply_fwd / of_rb_bwd_pass1(mode 1)");
   OF_REQUIRE(a->gate && (a->res_f32 || a->res_bf16) && (a->out_f32 || a->out_bf16), "of_rb_gate_fwd: null gate/res/out");
-  RB_LAUNCH(rb_gate_fwd_kernel)
+  RB_LAUNCH(rb_gate_fwd_kernel, 2)
 }
 extern "C" int of_rb_gate_bwd_reduce(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_gate_bwd_reduce");
   if (rc) return rc;
+  OF_REQUIRE(a->ss == nullptr, "of_rb_gate_bwd_reduce: FiLM (ss) is only supported by of_rb_apply_fwd / of_rb_bwd_pass1(mode 1)");
   OF_REQUIRE(a->dout_f32 && a->acc_bc, "of_rb_gate_bwd_reduce: null dout/acc");
-  RB_LAUNCH(rb_gate_bwd_reduce_kernel)
+  RB_LAUNCH(rb_gate_bwd_reduce_kernel, 3)
 }
 extern "C" int of_rb_bwd_pass1(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_bwd_pass1");
@@ -459,13 +615,14 @@ extern "C" int of_rb_bwd_pass1(const of_rb_args* a, void* stream) {
     OF_REQUIRE(a->dh_bf16, "of_rb_bwd_pass1(mode 1): null dh");
   if (a->mode == 0) {
     OF_REQUIRE(a->ss == nullptr, "of_rb_bwd_pass1(mode 0): FiLM is not supported on block2");
-    RB_LAUNCH(rb_bwd_pass1_kernel<0>)
+    RB_LAUNCH((rb_bwd_pass1_kernel<0, false>), 2)
   }
-  RB_LAUNCH(rb_bwd_pass1_kernel<1>)
+  if (a->ss) { RB_LAUNCH((rb_bwd_pass1_kernel<1, true>), 2) }
+  RB_LAUNCH((rb_bwd_pass1_kernel<1, false>), 2)
 }
 extern "C" int of_rb_bwd_apply(const of_rb_args* a, void* stream) {
   int rc = check_common(a, "of_rb_bwd_apply");
   if (rc) return rc;
   OF_REQUIRE(a->dxhat_bf16 && a->dstats && a->dy_bf16, "of_rb_bwd_apply: null pointers");
-  RB_LAUNCH(rb_bwd_apply_kernel)
+  RB_LAUNCH(rb_bwd_apply_kernel, 3)
 }

@@ -17,48 +17,7 @@ import torch
 import torch.distributed as dist
 
 
-def backward_param_order(unet) -> List[torch.nn.Parameter]:
-    """Parameters in the order their gradients become final during the engine's backward pass."""
-    order: List[torch.nn.Parameter] = []
-    seen = set()
-
-    def add(module):
-        for p in module.parameters():
-            if id(p) not in seen:
-                seen.add(id(p))
-                order.append(p)
-
-    def add_block(blk):
-        add(blk.sampler)
-        for res, tr in reversed(list(zip(blk.resnets, blk.transformers))):
-            add(tr)
-            add(res)
-        add(blk.init_resnet)
-
-    add(unet.final_conv)
-    add(unet.final_resnet)
-    for blk in reversed(unet.up_layers):
-        add_block(blk)
-    add(unet.middle_resnet2)
-    for tr in reversed(unet.middle_transformer):
-        add(tr)
-    add(unet.middle_resnet1)
-    for blk in reversed(unet.down_layers):
-        add_block(blk)
-    add(unet.init_x)
-    add(unet.time_mlp)
-    add(unet.cond_mlp)
-    if id(unet.null_cond) not in seen:
-        seen.add(id(unet.null_cond))
-        order.append(unet.null_cond)
-    for blk in reversed(unet.audio_encoder.layers):
-        add_block(blk)
-    add(unet.audio_encoder.init_conv)
-    for p in unet.parameters():          # anything not covered above (e.g. adapters)
-        if id(p) not in seen:
-            seen.add(id(p))
-            order.append(p)
-    return order
+from .engine import backward_param_order  # noqa: E402,F401  (re-exported: the arena order is defined by the engine)
 
 
 class GradAllReducer:
@@ -68,30 +27,26 @@ class GradAllReducer:
         unet = model.unet if hasattr(model, "unet") else model
         self.unet, self.group, self.overlap = unet, group, overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        params = [p for p in backward_param_order(unet) if p.requires_grad]
-        ALIGN = 32                      # floats: every gradient view starts 128-byte aligned (kernels use 16-byte vector atomics)
-        total = sum((p.numel() + ALIGN - 1) // ALIGN * ALIGN for p in params)
+        store = unet._store
+        store.ensure_arena(unet)                 # the engine owns the gradient arena; buckets are contiguous slices of it
+        self.store = store
+        params = store.arena_params
         dev = params[0].device
-        self.arena = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.views = {}
         self.buckets = []      # (start, end, [param ids])
-        off = 0
         b_start, b_ids = 0, []
-        for p in params:
-            self.views[id(p)] = self.arena[off:off + p.numel()].view(p.shape)
+        end = 0
+        for p, (s0, e0) in zip(params, store.arena_offsets):
             b_ids.append(id(p))
-            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
-            if (off - b_start) * 4 >= bucket_bytes:
-                self.buckets.append((b_start, off, b_ids))
-                b_start, b_ids = off, []
+            end = e0
+            if (end - b_start) * 4 >= bucket_bytes:
+                self.buckets.append((b_start, end, b_ids))
+                b_start, b_ids = end, []
         if b_ids:
-            self.buckets.append((b_start, off, b_ids))
+            self.buckets.append((b_start, end, b_ids))
         self.bucket_of = {pid: bi for bi, (_, _, ids) in enumerate(self.buckets) for pid in ids}
         self.ready_at = None           # bucket index -> tape op index after which it is complete (learned in step 1)
         self.comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._pending: List[int] = []
-        store = unet._store
-        store.arena_views = self.views
         store.on_backward_begin = self._begin
         store.on_touch = self._touch
         unet.grad_sync = self._after_op
@@ -102,8 +57,15 @@ class GradAllReducer:
         self._launched = set()
 
     # ---- hooks called by the engine
+    @property
+    def arena(self) -> torch.Tensor:
+        return self.store.arena
+
+    @property
+    def views(self):
+        return self.store.arena_views
+
     def _begin(self) -> None:
-        self.arena.zero_()
         self._launched = set()
         self._touch_log = {}
 

@@ -71,7 +71,42 @@ def empty(shape, dtype, device):
     return torch.empty(shape, dtype=dtype, device=device)
 
 
+class ZeroPool:
+    """Bump allocator over freshly zeroed chunks: the hundreds of tiny zero-initialised scratch tensors of one step (GroupNorm
+    statistics, per-channel accumulators, gate-MLP gradients) cost one fill per 4 MB chunk instead of one launch each.  Views
+    keep their chunk alive, so lifetimes are ordinary tensor lifetimes."""
+    CHUNK = 4 << 20
+
+    def __init__(self, device) -> None:
+        self.device, self.buf, self.off = device, None, 0
+
+    def take(self, shape, dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        aligned = (nbytes + 255) // 256 * 256
+        if aligned > self.CHUNK // 4:
+            return torch.zeros(shape, dtype=dtype, device=self.device)
+        if self.buf is None or self.off + aligned > self.CHUNK:
+            self.buf = torch.zeros(self.CHUNK, dtype=torch.uint8, device=self.device)
+            self.off = 0
+        v = self.buf[self.off:self.off + nbytes].view(dtype).view(shape)
+        self.off += aligned
+        return v
+
+
+_POOL: Optional[ZeroPool] = None     # pool of the forward/backward pass currently being recorded (set by Ctx / backward_from)
+
+
+def use_pool(pool: Optional[ZeroPool]) -> None:
+    global _POOL
+    _POOL = pool
+
+
 def zeros(shape, dtype, device):
+    if _POOL is not None and _POOL.device == device:
+        return _POOL.take(tuple(shape), dtype)
     return torch.zeros(shape, dtype=dtype, device=device)
 
 
@@ -123,26 +158,273 @@ def _adapter(m):
 
 
 # ------------------------------------------------------------------------------------------------ parameter staging
+def backward_param_order(unet) -> List[torch.nn.Parameter]:
+    """Parameters in the order their gradients become final during the engine's backward pass.  The FiLM heads
+    (`ResidualBlock.mlp`) are the exception: their gradients are produced by ONE grouped kernel when the conditioning
+    MLPs are reached, so they sit together right after `init_x`."""
+    order: List[torch.nn.Parameter] = []
+    seen = set()
+    film = []
+
+    def add(module):
+        for name, p in module.named_parameters():
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            (film if name.startswith("mlp.") or ".mlp." in name else order).append(p)
+
+    def add_block(blk):
+        add(blk.sampler)
+        for res, tr in reversed(list(zip(blk.resnets, blk.transformers))):
+            add(tr)
+            add(res)
+        add(blk.init_resnet)
+
+    add(unet.final_conv)
+    add(unet.final_resnet)
+    for blk in reversed(unet.up_layers):
+        add_block(blk)
+    add(unet.middle_resnet2)
+    for tr in reversed(unet.middle_transformer):
+        add(tr)
+    add(unet.middle_resnet1)
+    for blk in reversed(unet.down_layers):
+        add_block(blk)
+    add(unet.init_x)
+    film_start = len(order)
+    order.extend(film)
+    film_end = len(order)
+    for p in list(unet.time_mlp.parameters()) + list(unet.cond_mlp.parameters()) + [unet.null_cond]:
+        if id(p) not in seen:
+            seen.add(id(p))
+            order.append(p)
+    for blk in reversed(unet.audio_encoder.layers):
+        add_block(blk)
+    add(unet.audio_encoder.init_conv)
+    for p in unet.parameters():          # anything not covered above
+        if id(p) not in seen:
+            seen.add(id(p))
+            order.append(p)
+    backward_param_order.film_span = (film_start, film_end)
+    return order
+
+
 class ParamStore:
-    """bf16 GEMM-operand copies of the fp32 master parameters and the fp32 gradient buffers the kernels accumulate into.
+    """bf16 GEMM-operand copies of the fp32 master parameters and the fp32 gradient arena the kernels accumulate into.
 
     `refresh=True` (training): operand copies are rebuilt on every forward (the reference's autocast also re-casts every
-    weight each iteration).  `refresh=False` (sampling): copies are cached per parameter version.
+    weight each iteration) by ONE grouped launch.  `refresh=False` (sampling): copies are cached per parameter version.
+
+    Gradients of all trainable parameters live in ONE flat fp32 arena laid out in backward-completion order: one memset
+    per step instead of one fill per tensor, `p.grad` are views of it, and the data-parallel wrapper all-reduces contiguous
+    slices in place (osufusion_b200/ddp.py).
     """
+    ALIGN = 32   # floats: every gradient view starts 128-byte aligned (kernels use 16-byte vector atomics)
 
     def __init__(self) -> None:
         self.cache = {}
-        self.grads = {}
         self.refresh = True
         self.epoch = 0
-        # set by ddp.GradAllReducer: gradients then live in one flat arena (views keyed by id(param))
-        self.arena_views = None
+        self.arena = None
+        self.arena_views = {}
+        self.arena_params = []       # trainable parameters in arena order
+        self.arena_offsets = []      # (start, end) in floats, aligned
+        self.arena_key = None
+        self.film_floats = None      # (start, end) floats of the FiLM-head block (written, never accumulated -> not zeroed)
+        self.touched = set()
+        self.pack_plan = None
+        self.film_plans = {}
+        # set by ddp.GradAllReducer
         self.on_backward_begin = None
         self.on_touch = None
 
-    def begin_forward(self, refresh: bool) -> None:
+    # ---- gradient arena
+    def ensure_arena(self, unet) -> None:
+        order = backward_param_order(unet)
+        fs, fe = backward_param_order.film_span
+        film_ids = {id(p) for p in order[fs:fe]}
+        params = [p for p in order if p.requires_grad]
+        key = tuple(id(p) for p in params) + (str(params[0].device) if params else "",)
+        if key == self.arena_key:
+            return
+        if not params:
+            self.arena, self.arena_views, self.arena_params, self.arena_offsets = None, {}, [], []
+            self.film_floats, self.arena_key, self.film_plans = None, key, {}
+            return
+        A = self.ALIGN
+        total = sum((p.numel() + A - 1) // A * A for p in params)
+        dev = params[0].device
+        self.arena = torch.zeros(max(total, 1), dtype=F32, device=dev)
+        self.arena_views, self.arena_params, self.arena_offsets = {}, params, []
+        off = 0
+        f0 = f1 = None
+        for p in params:
+            n = (p.numel() + A - 1) // A * A
+            self.arena_views[id(p)] = self.arena[off:off + p.numel()].view(p.shape)
+            self.arena_offsets.append((off, off + n))
+            if id(p) in film_ids:
+                f0 = off if f0 is None else f0
+                f1 = off + n
+            off += n
+        self.film_floats = (f0, f1) if f0 is not None else None
+        self.arena_key = key
+        self.film_plans = {}
+
+    def begin_backward(self, unet, film_overwritten: bool) -> None:
+        """Start of a backward pass: detach any `p.grad` still aliasing the arena (gradient accumulation without
+        zero_grad(set_to_none=True)), zero the arena, forget which gradients have been produced."""
+        self.ensure_arena(unet)
+        for p in self.arena_params:
+            g = p.grad
+            if g is not None and g.data_ptr() == self.arena_views[id(p)].data_ptr():
+                p.grad = g.clone()
+        if self.arena is None:
+            pass
+        elif film_overwritten and self.film_floats is not None:
+            f0, f1 = self.film_floats
+            if f0 > 0:
+                self.arena[:f0].zero_()
+            if f1 < self.arena.numel():
+                self.arena[f1:].zero_()
+        else:
+            self.arena.zero_()
+        self.touched = set()
+        if self.on_backward_begin is not None:
+            self.on_backward_begin()
+
+    def begin_forward(self, refresh: bool, unet=None) -> None:
         self.refresh = refresh
         self.epoch += 1
+        if unet is not None:
+            self.refresh_operands(unet)
+
+    # ---- grouped operand packing: every plain Conv1d / Linear weight of the denoiser in one launch
+    def _build_pack_plan(self, unet):
+        entries = []     # (cache key, params, [(param, Cout, Cin, k, cin_pad, element offset)], shape)
+        total = 0
+
+        def conv_entry(w):
+            nonlocal total
+            Cout, Cin, k = w.shape
+            cp = (Cin + 7) // 8 * 8
+            if k > 4:
+                return
+            entries.append((("conv", id(w)), (w,), [(w, Cout, Cin, k, cp, total)], (k, Cout, cp), total))
+            total += (k * Cout * cp + 127) // 128 * 128
+
+        def lin_entry(*ws):
+            nonlocal total
+            K = ws[0].shape[1]
+            segs, r = [], 0
+            for w in ws:
+                segs.append((w, w.shape[0], K, 1, K, total + r * K))
+                r += w.shape[0]
+            entries.append((("lin",) + tuple(id(w) for w in ws), tuple(ws), segs, (r, K), total))
+            total += (r * K + 127) // 128 * 128
+
+        for m in unet.modules():
+            kind = type(m).__name__
+            if kind == "ResidualBlock":
+                for blk in (m.block1, m.block2):
+                    if _adapter(blk.proj) is None:
+                        conv_entry(blk.proj.weight)
+                if not isinstance(m.res_conv, torch.nn.Identity):
+                    lin_entry(m.res_conv.weight)
+            elif kind == "TransformerBlock":
+                at = m.attn
+                if _adapter(at.to_q) is None and _adapter(at.to_kv) is None:
+                    lin_entry(at.to_q.weight, at.to_kv.weight)
+                lin_entry(at.to_out.weight)
+                lin_entry(m.ff[0].weight)
+                lin_entry(m.ff[2].weight)
+            elif kind == "Upsample":
+                conv_entry(m.conv.weight)
+            elif kind == "Parallel":
+                conv_entry(m.fns[0].weight)
+                lin_entry(m.fns[1].weight)
+        if not entries:
+            return None
+        dev = entries[0][1][0].device
+        buf = torch.empty(total, dtype=BF16, device=dev)
+        lib = N.lib()
+        segs = []
+        cta = 0
+        for _, _, seglist, _, _ in entries:
+            for (w, Cout, Cin, k, cp, off) in seglist:
+                n = lib.of_pack_seg_ctas(Cout, Cin, k, cp)
+                assert n > 0
+                segs.append(N.PackSeg(w.data_ptr(), buf.data_ptr() + 2 * off, Cout, Cin, k, cp, cta, 0))
+                cta += n
+        arr = (N.PackSeg * len(segs))(*segs)
+        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        views = []
+        for key, params, _, shape, off0 in entries:
+            n = 1
+            for d in shape:
+                n *= d
+            views.append((key, params, buf[off0:off0 + n].view(shape)))
+        ptrs = tuple(p.data_ptr() for _, ps, _ in views for p in ps)
+        return {"table": table, "num_segs": len(segs), "ctas": cta, "views": views, "ptrs": ptrs, "buf": buf, "vers": None}
+
+    def refresh_operands(self, unet) -> None:
+        plan = self.pack_plan
+        if plan is not None:
+            ptrs = tuple(p.data_ptr() for _, ps, _ in plan["views"] for p in ps)
+            if ptrs != plan["ptrs"] or plan.get("n_adapters") != sum(1 for m in unet.modules() if hasattr(m, "base_layer")):
+                plan = None
+        if plan is None:
+            plan = self.pack_plan = self._build_pack_plan(unet)
+            if plan is None:
+                return
+            plan["n_adapters"] = sum(1 for m in unet.modules() if hasattr(m, "base_layer"))
+        vers = tuple(p._version for _, ps, _ in plan["views"] for p in ps)
+        if not self.refresh and vers == plan["vers"]:
+            return
+        N.call("of_pack_weights", plan["table"].data_ptr(), plan["num_segs"], plan["ctas"])
+        plan["vers"] = vers
+        for key, params, view in plan["views"]:
+            self.cache[key] = (tuple((p.data_ptr(), p._version) for p in params), view, self.epoch)
+
+    # ---- grouped FiLM heads
+    def film_plan(self, unet, B: int, with_grads: bool):
+        """Descriptor tables of every `ResidualBlock.mlp[1]` head for batch size B (device-resident, built once)."""
+        key = (B, with_grads)
+        plan = self.film_plans.get(key)
+        heads = [m for m in unet.modules() if type(m).__name__ == "ResidualBlock" and m.mlp is not None]
+        if not heads:
+            return None
+        ptrs = tuple(h.mlp[1].weight.data_ptr() for h in heads) + (self.arena.data_ptr() if (with_grads and self.arena is not None) else 0,)
+        if plan is not None and plan["ptrs"] == ptrs:
+            return plan
+        dev = heads[0].mlp[1].weight.device
+        K = heads[0].mlp[1].weight.shape[1]
+        groups, chunks, slices = [], [], {}
+        row = 0
+        ch = N.lib().of_film_chunk_rows()
+        for gi, h in enumerate(heads):
+            lin = h.mlp[1]
+            Nn = lin.weight.shape[0]
+            assert lin.weight.shape[1] == K and Nn % 4 == 0
+            dW = db = 0
+            if with_grads:
+                if lin.weight.requires_grad:
+                    dW = self.arena_views[id(lin.weight)].data_ptr()
+                if lin.bias is not None and lin.bias.requires_grad:
+                    db = self.arena_views[id(lin.bias)].data_ptr()
+            groups.append(N.FilmGroup(lin.weight.data_ptr(), lin.bias.data_ptr() if lin.bias is not None else 0, dW, db,
+                                      B * row, Nn, row))
+            for n0 in range(0, Nn, ch):
+                chunks += [gi, n0]
+            slices[id(h)] = (B * row, Nn)
+            row += Nn
+        arr = (N.FilmGroup * len(groups))(*groups)
+        plan = {
+            "ptrs": ptrs, "heads": heads, "K": K, "rows": row, "num_groups": len(groups), "slices": slices,
+            "groups": torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev),
+            "chunks": torch.tensor(chunks, dtype=torch.int32).to(dev), "num_chunks": len(chunks) // 2,
+        }
+        self.film_plans[key] = plan
+        return plan
 
     def _cached(self, key, params, build):
         ver = tuple((p.data_ptr(), p._version) for p in params)
@@ -273,16 +555,14 @@ class ParamStore:
             return out
         return self._cached(("linm",) + tuple(id(_base(m).weight) for m in mods), tuple(ps), build)
 
-    # ---- gradient buffers (fp32, zero-initialised, torch layout) handed back to autograd at the end of backward
-    def existing_grad(self, p: torch.nn.Parameter):
-        """The gradient buffer of p if one exists already (arena view or earlier contribution), else None."""
+    # ---- gradient buffers: zero-initialised fp32 views of the arena in the reference's parameter layout
+    def touch(self, p: torch.nn.Parameter) -> bool:
+        """Mark p's gradient as produced; returns True the first time (the buffer still holds zeros)."""
+        first = id(p) not in self.touched
+        self.touched.add(id(p))
         if self.on_touch is not None:
             self.on_touch(id(p))
-        g = self.grads.get(id(p))
-        if g is None and self.arena_views is not None and id(p) in self.arena_views:
-            g = self.arena_views[id(p)]
-            self.grads[id(p)] = g
-        return g
+        return first
 
     def grad_opt(self, p):
         """Gradient buffer of p, or None when p is absent / frozen (kernels skip NULL outputs)."""
@@ -291,22 +571,30 @@ class ParamStore:
         return self.grad(p)
 
     def grad(self, p: torch.nn.Parameter) -> torch.Tensor:
-        g = self.existing_grad(p)
-        if g is None:
-            g = zeros(p.shape, F32, p.device)
-            self.grads[id(p)] = g
-        return g
+        if not p.requires_grad:      # frozen (LoRA fine-tuning): kernels with mandatory outputs write into throw-away scratch
+            return zeros(p.shape, F32, p.device)
+        self.touch(p)
+        return self.arena_views[id(p)]
 
     def set_grad(self, p: torch.nn.Parameter, g: torch.Tensor) -> None:
-        old = self.existing_grad(p)
-        if old is None:
-            self.grads[id(p)] = g
+        if not p.requires_grad:
+            return
+        first = self.touch(p)
+        v = self.arena_views[id(p)]
+        if first:
+            v.copy_(g.view(v.shape))
         else:
-            old.add_(g.view(old.shape))
+            v.add_(g.view(v.shape))
 
     def take_grads(self, params):
-        out = [self.grads.get(id(p)) if p.requires_grad else None for p in params]
-        self.grads = {}
+        """Fresh view objects (so autograd's AccumulateGrad adopts them without a copy) of every gradient produced."""
+        out = []
+        for p in params:
+            if p.requires_grad and id(p) in self.touched:
+                v = self.arena_views[id(p)]
+                out.append(v.view(v.shape))
+            else:
+                out.append(None)
         return out
 
 
@@ -351,13 +639,8 @@ def _wgrad_conv(store: ParamStore, w: torch.nn.Parameter, dy16, x16, taps, shift
     cp = (Cin + 7) // 8 * 8
     tmp = zeros((k, Cout, cp), F32, w.device)
     R.gemm_wgrad(dy16, x16, tmp, M=Cout, N_out=cp, taps=taps, shift0=shift0, shift_step=1)
-    g = store.existing_grad(w)
-    if g is None:
-        g = empty(w.shape, F32, w.device)
-        store.grads[id(w)] = g
-        acc = 0
-    else:
-        acc = 1
+    acc = 0 if store.touch(w) else 1
+    g = store.grad(w)
     N.call("of_unpack_conv_wgrad", _p(tmp), Cout, Cin, k, cp, 0, _p(g), acc)
 
 
@@ -400,6 +683,10 @@ class Ctx:
         self.d_emb_act = None    # its gradient accumulator
         self.rope_cache = {}
         self.attn_variant = 0
+        self.zpool = ZeroPool(device)
+        use_pool(self.zpool)
+        self.film = None         # id(ResidualBlock) -> (B, 2C) fp32 view of the grouped FiLM output
+        self.film_dss = None     # ... and of its gradient accumulator
 
 
 def conv3(ctx: Ctx, x16, conv, *, stats=None, out=None):
@@ -443,7 +730,7 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
     Cout = _base(m.block1.proj).weight.shape[0]
     ss = None
     if m.mlp is not None:
-        ss, _ = linear_small_fwd(ctx.emb_act, m.mlp[1].weight, m.mlp[1].bias)
+        ss = ctx.film[id(m)]     # computed for all heads at once by UNet.conditioning (of_film_fwd)
     stats1 = zeros((B, 2), F64, dev)
     y1 = conv3(ctx, x16, m.block1.proj, stats=stats1)
     a1 = _rb_args(B, L, Cout, y1, stats1, m.block1.norm, ss)
@@ -549,10 +836,8 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             dstats1 = zeros((B, 2), F64, dev)
             b1.dstats = dstats1.data_ptr()
             b1.dgamma, b1.dbeta = st.grad(m.block1.norm.weight).data_ptr(), st.grad(m.block1.norm.bias).data_ptr()
-            dss = None
             if ss is not None:
-                dss = zeros((B, 2 * Cout), F32, dev)
-                b1.dss = dss.data_ptr()
+                b1.dss = ctx.film_dss[id(m)].data_ptr()   # consumed by of_film_bwd in UNet.conditioning's backward
             b1.dxhat_bf16 = dxh1.data_ptr()
             b1.dxhat_bs, b1.dxhat_ld = _bl(dxh1)
             N.call("of_rb_bwd_pass1", C.byref(b1))
@@ -569,9 +854,6 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             else:
                 x.add_grad(dout)
             conv3_bwd(ctx, m.block1.proj, x, x16, dy1)
-            if ss is not None:
-                W = m.mlp[1].weight
-                linear_small_bwd(dss, None, 0, ctx.emb_act, W, st.grad_opt(W), st.grad_opt(m.mlp[1].bias), ctx.d_emb_act)
         ctx.tape.push(backward)
     return out
 

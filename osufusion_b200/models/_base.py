@@ -88,7 +88,7 @@ class BaseOsuFusion(nn.Module):
         cfg = cond_scale != 1.0
         ctx = Ctx(dev, unet._store, None)
         ctx.attn_variant = unet.attn_variant
-        unet._store.begin_forward(False)
+        unet._store.begin_forward(False, unet)
         a16 = _pack(a.float(), AUDIO_DIM, Lp, A_PAD_VALUE)
         a_feat = unet.encode_audio(ctx, a16)
         cc = c.float()

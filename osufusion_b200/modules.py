@@ -286,10 +286,33 @@ class UNet(nn.Module):
         emb_act = E.empty((B, 2 * Em), F32, dev)
         N.call("of_silu_small", cat.data_ptr(), None, emb_act.data_ptr(), cat.numel())
         ctx.emb_act = emb_act
-        if ctx.tape is not None:
+        # every FiLM head of the denoiser in one launch (their common input is emb_act; bf16-rounded as under autocast)
+        training = ctx.tape is not None
+        if training:
+            st.ensure_arena(self)
+        plan = st.film_plan(self, B, training)
+        emb_r = None
+        if plan is not None:
+            emb_r = emb_act.to(BF16).to(F32)
+            ss_all = E.empty((B * plan["rows"],), F32, dev)
+            N.call("of_film_fwd", plan["groups"].data_ptr(), plan["num_groups"], plan["rows"], emb_r.data_ptr(), B, plan["K"],
+                   ss_all.data_ptr())
+            ctx.film = {k: ss_all[o:o + B * n].view(B, n) for k, (o, n) in plan["slices"].items()}
+        if training:
             ctx.d_emb_act = E.zeros((B, 2 * Em), F32, dev)
+            dss_all = None
+            if plan is not None:
+                dss_all = torch.zeros((B * plan["rows"],), dtype=F32, device=dev)
+                ctx.film_dss = {k: dss_all[o:o + B * n].view(B, n) for k, (o, n) in plan["slices"].items()}
 
             def backward():
+                if plan is not None:
+                    N.call("of_film_bwd", plan["groups"].data_ptr(), plan["chunks"].data_ptr(), plan["num_chunks"],
+                           dss_all.data_ptr(), emb_r.data_ptr(), B, plan["K"], ctx.d_emb_act.data_ptr())
+                    for h in plan["heads"]:
+                        for p_ in h.mlp[1].parameters():
+                            if p_.requires_grad:
+                                st.touch(p_)
                 dcat = E.empty((B, 2 * Em), F32, dev)
                 N.call("of_silu_small", cat.data_ptr(), ctx.d_emb_act.data_ptr(), dcat.data_ptr(), cat.numel())
                 dt = dcat[:, :Em]
@@ -353,7 +376,7 @@ class UNet(nn.Module):
         Lp = self.padded_len(n)
         ctx = Ctx(x.device, self._store, tape)
         ctx.attn_variant = self.attn_variant
-        self._store.begin_forward(refresh if refresh is not None else tape is not None)
+        self._store.begin_forward(refresh if refresh is not None else tape is not None, self)
         x16 = _pack(x, 8, Lp, X_PAD_VALUE, noise, ca, cb)
         a16 = _pack(a, self.dim_in_a, Lp, A_PAD_VALUE)
         a_feat = self.encode_audio(ctx, a16)
@@ -362,8 +385,8 @@ class UNet(nn.Module):
 
     def backward_from(self, ctx: Ctx, xf: Act, dY16: torch.Tensor, params):
         st = ctx.store
-        if st.on_backward_begin is not None:
-            st.on_backward_begin()
+        E.use_pool(ctx.zpool)
+        st.begin_backward(self, film_overwritten=ctx.film_dss is not None)
         if self.grad_sync is not None:
             self.grad_sync(len(ctx.tape.ops) + 1)
         self.final_backward(ctx, xf, dY16)

@@ -30,7 +30,7 @@ def _worker(rank, world, port, out):
     st = net._store
     n_ops = 40
     for step in range(2):                              # step 0 learns bucket readiness, step 1 overlaps
-        st.on_backward_begin()
+        st.begin_backward(net, False)
         net.grad_sync(n_ops + 1)
         per = max(1, len(order) // n_ops)
         k = 0

@@ -170,3 +170,65 @@ def test_layernorm_and_small_linear():
     pre_r = (xb @ Wb.t() + bias)
     torch.nn.functional.silu(pre_r).backward(dyl)
     assert rel(dW, Wb.grad) < 5e-3 and rel(dxs, xb.grad) < 5e-3
+
+
+@pytest.mark.parametrize("M,K,Ns", [(4, 512, (192, 64, 256)), (2, 768, (384,)), (9, 256, (128, 132))])
+def test_grouped_film_heads(M, K, Ns):
+    """of_film_fwd / of_film_bwd (all FiLM heads in one launch) vs torch on bf16-rounded operands."""
+    from osufusion_b200 import _native as N
+    torch.manual_seed(3)
+    lib = N.lib()
+    Ws = [torch.randn(n, K, device=dev) / K ** 0.5 for n in Ns]
+    bs = [torch.randn(n, device=dev) for n in Ns]
+    dWs = [torch.full((n, K), 7.0, device=dev) for n in Ns]       # must be overwritten, not accumulated
+    dbs = [torch.full((n,), 7.0, device=dev) for n in Ns]
+    x = torch.randn(M, K, device=dev).bfloat16().float()
+    groups, chunks, row = [], [], 0
+    ch = lib.of_film_chunk_rows()
+    for gi, n in enumerate(Ns):
+        groups.append(N.FilmGroup(Ws[gi].data_ptr(), bs[gi].data_ptr(), dWs[gi].data_ptr(), dbs[gi].data_ptr(), M * row, n, row))
+        for n0 in range(0, n, ch):
+            chunks += [gi, n0]
+        row += n
+    gt = torch.frombuffer(bytearray(bytes((N.FilmGroup * len(groups))(*groups))), dtype=torch.uint8).to(dev)
+    ct = torch.tensor(chunks, dtype=torch.int32, device=dev)
+    out = torch.empty(M * row, device=dev)
+    N.call("of_film_fwd", gt.data_ptr(), len(groups), row, x.data_ptr(), M, K, out.data_ptr())
+    dss = torch.randn(M * row, device=dev)
+    demb = torch.zeros(M, K, device=dev)
+    N.call("of_film_bwd", gt.data_ptr(), ct.data_ptr(), len(chunks) // 2, dss.data_ptr(), x.data_ptr(), M, K, demb.data_ptr())
+    off, demb_ref = 0, torch.zeros(M, K, device=dev)
+    for gi, n in enumerate(Ns):
+        w16 = Ws[gi].bfloat16().float()
+        ref = (x @ w16.t() + bs[gi]).bfloat16().float()
+        assert rel(out[off:off + M * n].view(M, n), ref) < 1e-2 and rel(out[off:off + M * n].view(M, n), x @ w16.t() + bs[gi]) < 1e-2
+        d = dss[off:off + M * n].view(M, n)
+        assert rel(dWs[gi], d.t() @ x) < 1e-4
+        assert rel(dbs[gi], d.sum(0)) < 1e-4
+        demb_ref += d @ w16
+        off += M * n
+    assert rel(demb, demb_ref) < 1e-4
+
+
+def test_grouped_weight_pack():
+    """of_pack_weights: conv (Cout,Cin,k) -> [k][Cout][cin_pad] bf16 and plain casts, many tensors in one launch."""
+    from osufusion_b200 import _native as N
+    torch.manual_seed(4)
+    lib = N.lib()
+    shapes = [(96, 96, 3), (520, 264, 1), (64, 100, 3), (1024, 2048, 1), (7, 13, 1), (130, 2051, 3)]
+    ws = [torch.randn(s, device=dev) for s in shapes]
+    segs, outs, cta = [], [], 0
+    for w in ws:
+        Cout, Cin, k = w.shape
+        cp = Cin if k == 1 else (Cin + 7) // 8 * 8
+        o = torch.full((k, Cout, cp), 9.0, device=dev, dtype=torch.bfloat16)
+        outs.append(o)
+        segs.append(N.PackSeg(w.data_ptr(), o.data_ptr(), Cout, Cin, k, cp, cta, 0))
+        cta += lib.of_pack_seg_ctas(Cout, Cin, k, cp)
+    table = torch.frombuffer(bytearray(bytes((N.PackSeg * len(segs))(*segs))), dtype=torch.uint8).to(dev)
+    N.call("of_pack_weights", table.data_ptr(), len(segs), cta)
+    for w, o in zip(ws, outs):
+        Cout, Cin, k = w.shape
+        ref = torch.zeros_like(o)
+        ref[:, :, :Cin] = w.permute(2, 0, 1).bfloat16()
+        assert torch.equal(o, ref), w.shape
