@@ -87,9 +87,94 @@ __device__ __forceinline__ void red_add_v4(float* ptr, float a, float b, float c
                : "memory");
 }
 
+// ---- epilogue variants.  The epilogue is instruction-issue bound (8 warps, one accumulator row per thread), so the fused
+// options are compile-time flags: each (flag set) the engine uses gets its own instantiation with the dead paths removed;
+// anything else runs the kEpiRuntime instance, which reads the same flags from the parameter block.
+enum : uint32_t {
+  E_BIAS = 1u, E_AUX32 = 2u, E_AUX16_ADD = 4u, E_AUX16_DSILU = 8u, E_PRE16 = 16u, E_SILU = 32u, E_O16 = 64u, E_O32 = 128u,
+  E_STATS = 256u, E_WGRAD = 512u, kEpiRuntime = 0x80000000u
+};
+
+template <uint32_t F>
+struct EpiFlags {
+  bool bias, aux32, aux16_add, aux16_dsilu, pre16, silu, o16, o32, stats;
+  __device__ __forceinline__ explicit EpiFlags(const GemmKParams& p) {
+    if (F == kEpiRuntime) {
+      bias = p.bias != nullptr; aux32 = p.aux_f32 != nullptr;
+      aux16_add = p.aux_bf16 != nullptr && !p.aux_is_dsilu; aux16_dsilu = p.aux_bf16 != nullptr && p.aux_is_dsilu;
+      pre16 = p.pre_bf16 != nullptr; silu = p.act == OF_ACT_SILU; o16 = p.out_bf16 != nullptr; o32 = p.out_f32 != nullptr;
+      stats = p.stats != nullptr;
+    } else {
+      bias = F & E_BIAS; aux32 = F & E_AUX32; aux16_add = F & E_AUX16_ADD; aux16_dsilu = F & E_AUX16_DSILU; pre16 = F & E_PRE16;
+      silu = F & E_SILU; o16 = F & E_O16; o32 = F & E_O32; stats = F & E_STATS;
+    }
+  }
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* x) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+}
+
+// One 32-column chunk of this thread's accumulator row.  FULL: all 32 columns are < N (no column predicates).
+template <uint32_t F, bool FULL>
+__device__ __forceinline__ void epi_chunk(const GemmKParams& p, const EpiFlags<F>& e, const uint32_t (&v)[32], int nb,
+                                          const float* aux32, const __nv_bfloat16* aux16, __nv_bfloat16* pre16,
+                                          __nv_bfloat16* o16, float* o32, float& s1, float& s2) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = nb + g * 8;
+    if (FULL || n < p.N) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+      if (e.bias) {
+        const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n), b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      }
+      if (e.aux32) {
+        const float4 a0 = *reinterpret_cast<const float4*>(aux32 + n), a1 = *reinterpret_cast<const float4*>(aux32 + n + 4);
+        f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w; f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+      }
+      float x16[8];
+      if (e.aux16_add || e.aux16_dsilu) {
+        unpack8(*reinterpret_cast<const uint4*>(aux16 + n), x16);
+        if (e.aux16_add) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += x16[j];
+        }
+      }
+      if (e.pre16)
+        st_global_v4(pre16 + n, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      if (e.silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+      }
+      if (e.aux16_dsilu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= dsilu_f(x16[j]);
+      }
+      if (e.o16)
+        st_global_v4(o16 + n, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      if (e.o32) {
+        *reinterpret_cast<float4*>(o32 + n) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(o32 + n + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      }
+      if (e.stats) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float rv = bf16_round(f[j]);
+          s1 += rv;
+          s2 = fmaf(rv, rv, s2);
+        }
+      }
+    }
+  }
+}
+
 // kMC: launched as clusters of 2 CTAs that own two M-adjacent tiles with the same N tile; each CTA fetches half of the shared
 // B (weight / X) tile and TMA-multicasts it to both, cutting L2->SM operand traffic per CTA from A+B to A+B/2.
-template <bool kMC>
+template <bool kMC, uint32_t F>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmKParams p) {
@@ -136,8 +221,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int tile_first = kMC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = kMC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-  const bool a_mn = (p.mode == OF_GEMM_WGRAD);
-  const bool b_mn = (p.mode == OF_GEMM_WGRAD) || (p.b_mn != 0);
+  constexpr bool kWgrad = (F == E_WGRAD);
+  const bool a_mn = kWgrad;
+  const bool b_mn = kWgrad || (p.b_mn != 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -155,7 +241,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           uint8_t* sb = sa + kABytes;
           if (leader) {
           mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
-          if (p.mode == OF_GEMM_FWD) {
+          if (!kWgrad) {
             int t = it / p.k_chunks;
             int kc = it - t * p.k_chunks;
             tma_load_3d(sa, &tmap_a, &full_bar[stage], kc * kBK, tc.m0 + p.shift0 + t * p.shift_step, tc.b);
@@ -255,98 +341,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m = tc.m0 + r;
       const bool k_nonempty = tc.k_end > tc.k_begin;
       float s1 = 0.f, s2 = 0.f;
-      if (p.mode == OF_GEMM_FWD) {
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
+      const int nchunks = p.BN / 32;
+      if (!kWgrad) {
+        const EpiFlags<F> e(p);
         const bool row_ok = m < p.rows;
         const long long brow = (long long)tc.b;
-        const float* aux32 = p.aux_f32 ? p.aux_f32 + brow * p.aux_f32_bs + (long long)m * p.aux_f32_ld : nullptr;
+        const float* aux32 = e.aux32 ? p.aux_f32 + brow * p.aux_f32_bs + (long long)m * p.aux_f32_ld : nullptr;
         const __nv_bfloat16* aux16 =
-            p.aux_bf16 ? p.aux_bf16 + brow * p.aux_bf16_bs + (long long)m * p.aux_bf16_ld : nullptr;
-        __nv_bfloat16* o16 = p.out_bf16 ? p.out_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
-        __nv_bfloat16* pre16 = p.pre_bf16 ? p.pre_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
-        float* o32 = p.out_f32 ? p.out_f32 + brow * p.out_f32_bs + (long long)m * p.out_f32_ld : nullptr;
-        for (int c = chalf; c < p.BN / 32; c += 2) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c * 32, v);
-          const int nb = tc.n0 + c * 32;
-          const bool chunk_ok = row_ok && nb < p.N;
-          // Issue every global load of this chunk BEFORE waiting on the TMEM load, so their latency overlaps instead of being
-          // paid once per 8-column group.
-          float4 bz[8], ax[8];
-          uint4 ah[4];
-          if (chunk_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = nb + g * 8;
-              const bool ok = n < p.N;
-              if (p.bias && ok) {
-                bz[2 * g] = *reinterpret_cast<const float4*>(p.bias + n);
-                bz[2 * g + 1] = *reinterpret_cast<const float4*>(p.bias + n + 4);
-              } else {
-                bz[2 * g] = bz[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-              if (aux32 && ok) {
-                ax[2 * g] = *reinterpret_cast<const float4*>(aux32 + n);
-                ax[2 * g + 1] = *reinterpret_cast<const float4*>(aux32 + n + 4);
-              } else {
-                ax[2 * g] = ax[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-              if (aux16 && ok) ah[g] = *reinterpret_cast<const uint4*>(aux16 + n);
-              else ah[g] = make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
+            (e.aux16_add || e.aux16_dsilu) ? p.aux_bf16 + brow * p.aux_bf16_bs + (long long)m * p.aux_bf16_ld : nullptr;
+        __nv_bfloat16* o16 = e.o16 ? p.out_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
+        __nv_bfloat16* pre16 = e.pre16 ? p.pre_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
+        float* o32 = e.o32 ? p.out_f32 + brow * p.out_f32_bs + (long long)m * p.out_f32_ld : nullptr;
+        // two 32-column chunks per iteration: both TMEM loads are in flight before the single wait
+        for (int c = chalf; c < nchunks; c += 4) {
+          uint32_t va[32], vb[32];
+          const bool two = c + 2 < nchunks;
+          tmem_ld_32x32b_x32(tacc + c * 32, va);
+          if (two) tmem_ld_32x32b_x32(tacc + (c + 2) * 32, vb);
           tmem_wait_ld();
-          if (chunk_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = nb + g * 8;
-              if (n < p.N) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = k_nonempty ? __uint_as_float(v[g * 8 + j]) : 0.f;
-                f[0] += bz[2 * g].x + ax[2 * g].x; f[1] += bz[2 * g].y + ax[2 * g].y;
-                f[2] += bz[2 * g].z + ax[2 * g].z; f[3] += bz[2 * g].w + ax[2 * g].w;
-                f[4] += bz[2 * g + 1].x + ax[2 * g + 1].x; f[5] += bz[2 * g + 1].y + ax[2 * g + 1].y;
-                f[6] += bz[2 * g + 1].z + ax[2 * g + 1].z; f[7] += bz[2 * g + 1].w + ax[2 * g + 1].w;
-                float x16[8];
-                {
-                  float2 t0 = unpack_bf16x2(ah[g].x), t1 = unpack_bf16x2(ah[g].y), t2 = unpack_bf16x2(ah[g].z),
-                         t3 = unpack_bf16x2(ah[g].w);
-                  x16[0] = t0.x; x16[1] = t0.y; x16[2] = t1.x; x16[3] = t1.y;
-                  x16[4] = t2.x; x16[5] = t2.y; x16[6] = t3.x; x16[7] = t3.y;
-                }
-                if (aux16 && !p.aux_is_dsilu) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] += x16[j];
-                }
-                if (pre16) {
-                  *reinterpret_cast<uint4*>(pre16 + n) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                                    pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                }
-                if (p.act == OF_ACT_SILU) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
-                }
-                if (aux16 && p.aux_is_dsilu) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] *= dsilu_f(x16[j]);
-                }
-                if (o16) {
-                  *reinterpret_cast<uint4*>(o16 + n) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                }
-                if (o32) {
-                  *reinterpret_cast<float4*>(o32 + n) = make_float4(f[0], f[1], f[2], f[3]);
-                  *reinterpret_cast<float4*>(o32 + n + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                }
-                if (p.stats) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    float rv = bf16_round(f[j]);
-                    s1 += rv;
-                    s2 += rv * rv;
-                  }
-                }
-              }
+          if (row_ok) {
+            const int na = tc.n0 + c * 32, nb2 = tc.n0 + (c + 2) * 32;
+            if (na + 32 <= p.N) epi_chunk<F, true>(p, e, va, na, aux32, aux16, pre16, o16, o32, s1, s2);
+            else if (na < p.N) epi_chunk<F, false>(p, e, va, na, aux32, aux16, pre16, o16, o32, s1, s2);
+            if (two) {
+              if (nb2 + 32 <= p.N) epi_chunk<F, true>(p, e, vb, nb2, aux32, aux16, pre16, o16, o32, s1, s2);
+              else if (nb2 < p.N) epi_chunk<F, false>(p, e, vb, nb2, aux32, aux16, pre16, o16, o32, s1, s2);
             }
           }
         }
@@ -354,9 +374,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // WGRAD: atomically accumulate fp32 into out_f32[tap][m][n]
         const bool row_ok = (m < p.K) && k_nonempty;
         float* o32 = p.out_f32 + (long long)tc.tap * p.out_f32_bs + (long long)m * p.out_f32_ld;
-        for (int c = chalf; c < p.BN / 32; c += 2) {
+        for (int c = chalf; c < nchunks; c += 2) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c * 32, v);
+          tmem_ld_32x32b_x32(tacc + c * 32, v);
           tmem_wait_ld();
           const int nb = tc.n0 + c * 32;
           if (row_ok && nb < p.N) {
@@ -374,8 +394,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // accumulator drained: the MMA warp may start the next tile into it
-      if (p.mode == OF_GEMM_FWD) {
-      if (p.stats) {
+      if (!kWgrad) {
+      if (F == kEpiRuntime ? (p.stats != nullptr) : ((F & E_STATS) != 0)) {
         // one pair of global double atomics per TILE: the 8 epilogue warps first combine in shared memory
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -409,6 +429,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 }
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace ofx
+
+namespace ofx {
+
+template <bool kMC, uint32_t F>
+static int launch_one(const GemmKParams& p, const CUtensorMap& ta, const CUtensorMap& tb, size_t smem_bytes, cudaStream_t stream) {
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    OF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kMC, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (!kMC) {
+    int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
+    gemm_kernel<false, F><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  } else {
+    int pairs = device_sm_count() / 2;
+    if (p.num_tiles < pairs) pairs = p.num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true, F>, ta, tb, p));
+  }
+  return OF_OK;
+}
+
+// The flag sets the engine produces (osufusion_b200/engine.py); everything else falls back to the runtime-flag instance.
+#define OF_GEMM_EPILOGUES(X)                                                                                                   \
+  X(E_WGRAD)                                                                                                                    \
+  X(E_O16) X(E_BIAS | E_O16) X(E_BIAS | E_O16 | E_STATS)                               /* qkv / conv, res_conv / conv + GN stats */ \
+  X(E_BIAS | E_AUX32 | E_O32 | E_O16)                                                  /* to_out, ff2: + fp32 residual */        \
+  X(E_BIAS | E_SILU | E_PRE16 | E_O16) X(E_BIAS | E_SILU | E_O16)                      /* ff1 (training / inference) */          \
+  X(E_O32) X(E_AUX32 | E_O32) X(E_AUX32 | E_O32 | E_O16) X(E_O32 | E_O16)              /* dgrad, gradient accumulated in place */ \
+  X(E_AUX16_DSILU | E_O16)                                                             /* ff backward through SiLU */            \
+  X(E_BIAS | E_AUX16_ADD | E_O16) X(E_AUX16_ADD | E_O16)                               /* Parallel sampler, Downsample fix-up */
+
+static int launch_gemm(uint32_t mask, bool mc, const GemmKParams& p, const CUtensorMap& ta, const CUtensorMap& tb, size_t smem_bytes,
+                       cudaStream_t stream) {
+#define OF_CASE(FLAGS)                                                                                   \
+  if (mask == (uint32_t)(FLAGS))                                                                         \
+    return mc ? launch_one<true, (uint32_t)(FLAGS)>(p, ta, tb, smem_bytes, stream)                       \
+              : launch_one<false, (uint32_t)(FLAGS)>(p, ta, tb, smem_bytes, stream);
+  OF_GEMM_EPILOGUES(OF_CASE)
+#undef OF_CASE
+  return mc ? launch_one<true, kEpiRuntime>(p, ta, tb, smem_bytes, stream) : launch_one<false, kEpiRuntime>(p, ta, tb, smem_bytes, stream);
+}
 
 }  // namespace ofx
 
@@ -559,32 +634,16 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
   }
 
   size_t smem_bytes = (size_t)p.num_stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    OF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  if (!use_mc) {
-    int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
-    gemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  uint32_t mask;
+  if (wgrad) {
+    mask = E_WGRAD;
   } else {
-    int pairs = device_sm_count() / 2;
-    if (p.num_tiles < pairs) pairs = p.num_tiles;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    OF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, ta, tb, p));
+    mask = (p.bias ? E_BIAS : 0u) | (p.aux_f32 ? E_AUX32 : 0u) | (p.aux_bf16 ? (p.aux_is_dsilu ? E_AUX16_DSILU : E_AUX16_ADD) : 0u) |
+           (p.pre_bf16 ? E_PRE16 : 0u) | (p.act == OF_ACT_SILU ? E_SILU : 0u) | (p.out_bf16 ? E_O16 : 0u) |
+           (p.out_f32 ? E_O32 : 0u) | (p.stats ? E_STATS : 0u);
   }
+  int rc2 = launch_gemm(mask, use_mc, p, ta, tb, smem_bytes, stream);
+  if (rc2 != OF_OK) return rc2;
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

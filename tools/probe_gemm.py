@@ -150,6 +150,44 @@ def perf():
         print(f"perf wgrad M{N} N{K} T{T}: {ms * 1e3:.1f} us  {2.0 * B * L * N * K * T / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def perfepi():
+    """Epilogue-variant timing on the transformer-block shapes (which fused option costs what)."""
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20 * 1e3
+    for (B, L, N, K) in [(4, 4096, 512, 1024), (4, 4096, 1024, 512)]:
+        x = torch.randn(B, L, K, device=dev).bfloat16()
+        w = (torch.randn(1, N, K, device=dev) / K ** 0.5).bfloat16()
+        wt = w.transpose(1, 2).contiguous()
+        bias = torch.randn(N, device=dev)
+        aux32 = torch.randn(B, L, N, device=dev)
+        aux16 = torch.randn(B, L, N, device=dev).bfloat16()
+        o16 = torch.empty(B, L, N, device=dev, dtype=torch.bfloat16)
+        pre = torch.empty_like(o16)
+        o32 = torch.empty(B, L, N, device=dev)
+        fl = 2.0 * B * L * N * K
+        variants = {
+            "o16": dict(out_bf16=o16), "bias+o16": dict(bias=bias, out_bf16=o16), "o32": dict(out_f32=o32),
+            "o32+o16": dict(out_f32=o32, out_bf16=o16), "aux32+o32": dict(aux_f32=aux32, out_f32=o32),
+            "aux32+o32 inplace": dict(aux_f32=o32, out_f32=o32),
+            "bias+aux32+o32+o16": dict(bias=bias, aux_f32=aux32, out_f32=o32, out_bf16=o16),
+            "bias+silu+pre+o16": dict(bias=bias, act=R.ACT_SILU, pre_bf16=pre, out_bf16=o16),
+            "aux16dsilu+o16": dict(aux_bf16=aux16, aux_is_dsilu=True, out_bf16=o16),
+        }
+        for name, kw in variants.items():
+            us = timeit(lambda: R.gemm_fwd(x, w, N_out=N, K=K, **kw))
+            us2 = timeit(lambda: R.gemm_fwd(x, wt, N_out=N, K=K, b_mn_major=True, **kw))
+            print(f"perfepi B{B} L{L} N{N} K{K} {name:22s}: {us:6.1f} us {fl / us / 1e6:7.1f} TF/s | B mn-major {us2:6.1f} us", flush=True)
+
+
 if __name__ == "__main__":
     grp = sys.argv[1] if len(sys.argv) > 1 else "all"
     t0 = time.time()
@@ -175,4 +213,6 @@ if __name__ == "__main__":
         case_epi()
     if grp in ("perf",):
         perf()
+    if grp in ("perfepi",):
+        perfepi()
     print(f"done {grp} in {time.time() - t0:.1f}s", flush=True)
