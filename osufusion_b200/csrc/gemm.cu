@@ -82,6 +82,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile,
 __device__ __forceinline__ void st_global_v4(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void red_add_v4(float* ptr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -116,53 +117,141 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* x) {
   x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
 }
 
-// One 32-column chunk of this thread's accumulator row.  FULL: all 32 columns are < N (no column predicates).
+// ---- epilogue staging tile: 32 rows x 128 bytes per warp, the 16-byte group index XOR-swizzled with (row & 7).
+// A thread owns one accumulator ROW, so direct global accesses touch 32 different cache lines per warp instruction (measured:
+// ~2.8 clk per line on the LSU, the bound of every epilogue with fp32 streams); staged, an instruction covers 4 full 128-byte
+// lines (fp32) or 8 64-byte row segments (bf16).
+__device__ __forceinline__ uint8_t* stage_at(uint8_t* stg, int row, int grp) { return stg + row * 128 + ((grp ^ (row & 7)) << 4); }
+
+// f[32] = this lane's row of a 32-column chunk at column nb -> bf16 global rows (row_base + 0..31), coalesced.
+template <bool FULL>
+__device__ __forceinline__ void store_chunk_bf16(uint8_t* stg, int lane, const float (&f)[32], __nv_bfloat16* base, long long ld,
+                                                 int row_base, int row_lim, int nb, int N) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(stage_at(stg, lane, g)) =
+        make_uint4(pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
+                   pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
+  __syncwarp();
+  const int rr = lane >> 2, gg = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mm = row_base + i * 8 + rr, nn = nb + gg * 8;
+    if (mm < row_lim && (FULL || nn < N)) {
+      const uint4 t = *reinterpret_cast<const uint4*>(stage_at(stg, i * 8 + rr, gg));
+      st_global_v4(base + (long long)mm * ld + nn, t.x, t.y, t.z, t.w);
+    }
+  }
+  __syncwarp();
+}
+template <bool FULL, bool kRed>
+__device__ __forceinline__ void store_chunk_f32(uint8_t* stg, int lane, const float (&f)[32], float* base, long long ld, int row_base,
+                                                int row_lim, int nb, int N) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(stage_at(stg, lane, g)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+  __syncwarp();
+  const int rr = lane >> 3, gg = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int mm = row_base + i * 4 + rr, nn = nb + gg * 4;
+    if (mm < row_lim && (FULL || nn < N)) {
+      const float4 t = *reinterpret_cast<const float4*>(stage_at(stg, i * 4 + rr, gg));
+      if (kRed) red_add_v4(base + (long long)mm * ld + nn, t.x, t.y, t.z, t.w);
+      else *reinterpret_cast<float4*>(base + (long long)mm * ld + nn) = t;
+    }
+  }
+  __syncwarp();
+}
+// Coalesced gather of a 32x32 fp32 / bf16 tile into this lane's row.
+template <bool FULL>
+__device__ __forceinline__ void load_chunk_f32(uint8_t* stg, int lane, float (&x)[32], const float* base, long long ld, int row_base,
+                                               int row_lim, int nb, int N) {
+  const int rr = lane >> 3, gg = lane & 7;
+  float4 t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int mm = row_base + i * 4 + rr, nn = nb + gg * 4;
+    t[i] = (mm < row_lim && (FULL || nn < N)) ? *reinterpret_cast<const float4*>(base + (long long)mm * ld + nn)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stage_at(stg, i * 4 + rr, gg)) = t[i];
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 u = *reinterpret_cast<const float4*>(stage_at(stg, lane, g));
+    x[4 * g] = u.x; x[4 * g + 1] = u.y; x[4 * g + 2] = u.z; x[4 * g + 3] = u.w;
+  }
+  __syncwarp();
+}
+template <bool FULL>
+__device__ __forceinline__ void load_chunk_bf16(uint8_t* stg, int lane, float (&x)[32], const __nv_bfloat16* base, long long ld,
+                                                int row_base, int row_lim, int nb, int N) {
+  const int rr = lane >> 2, gg = lane & 3;
+  uint4 t[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mm = row_base + i * 8 + rr, nn = nb + gg * 8;
+    t[i] = (mm < row_lim && (FULL || nn < N)) ? *reinterpret_cast<const uint4*>(base + (long long)mm * ld + nn) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage_at(stg, i * 8 + rr, gg)) = t[i];
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < 4; ++g) unpack8(*reinterpret_cast<const uint4*>(stage_at(stg, lane, g)), &x[8 * g]);
+  __syncwarp();
+}
+
+// One 32-column chunk (columns nb..nb+31) of the 32 accumulator rows of this warp (thread = row row_base + lane).  Warp-collective.
+// FULL: all 32 columns are < N (no column predicates).  Base pointers are per batch (row 0, column 0).
 template <uint32_t F, bool FULL>
-__device__ __forceinline__ void epi_chunk(const GemmKParams& p, const EpiFlags<F>& e, const uint32_t (&v)[32], int nb,
-                                          const float* aux32, const __nv_bfloat16* aux16, __nv_bfloat16* pre16,
-                                          __nv_bfloat16* o16, float* o32, float& s1, float& s2) {
+__device__ __forceinline__ void epi_chunk(const GemmKParams& p, const EpiFlags<F>& e, uint8_t* stg, int lane, const uint32_t (&v)[32],
+                                          int row_base, int nb, const float* aux32, const __nv_bfloat16* aux16,
+                                          __nv_bfloat16* pre16, __nv_bfloat16* o16, float* o32, float& s1, float& s2) {
+  const int row_lim = p.rows;
+  float f[32];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int n = nb + g * 8;
-    if (FULL || n < p.N) {
-      float f[8];
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (e.bias) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-      if (e.bias) {
-        const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n), b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
-        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    for (int g = 0; g < 8; ++g) {
+      if (FULL || nb + g * 4 < p.N) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + nb + g * 4);   // same address in every lane: one line
+        f[4 * g] += b.x; f[4 * g + 1] += b.y; f[4 * g + 2] += b.z; f[4 * g + 3] += b.w;
       }
-      if (e.aux32) {
-        const float4 a0 = *reinterpret_cast<const float4*>(aux32 + n), a1 = *reinterpret_cast<const float4*>(aux32 + n + 4);
-        f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w; f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
-      }
-      float x16[8];
-      if (e.aux16_add || e.aux16_dsilu) {
-        unpack8(*reinterpret_cast<const uint4*>(aux16 + n), x16);
-        if (e.aux16_add) {
+    }
+  }
+  if (e.aux32) {
+    float x[32];
+    load_chunk_f32<FULL>(stg, lane, x, aux32, p.aux_f32_ld, row_base, row_lim, nb, p.N);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] += x16[j];
-        }
-      }
-      if (e.pre16)
-        st_global_v4(pre16 + n, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      if (e.silu) {
+    for (int j = 0; j < 32; ++j) f[j] += x[j];
+  }
+  float x16[32];
+  if (e.aux16_add || e.aux16_dsilu) {
+    load_chunk_bf16<FULL>(stg, lane, x16, aux16, p.aux_bf16_ld, row_base, row_lim, nb, p.N);
+    if (e.aux16_add) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
-      }
-      if (e.aux16_dsilu) {
+      for (int j = 0; j < 32; ++j) f[j] += x16[j];
+    }
+  }
+  if (e.pre16) store_chunk_bf16<FULL>(stg, lane, f, pre16, p.out_bf16_ld, row_base, row_lim, nb, p.N);
+  if (e.silu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] *= dsilu_f(x16[j]);
-      }
-      if (e.o16)
-        st_global_v4(o16 + n, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      if (e.o32) {
-        *reinterpret_cast<float4*>(o32 + n) = make_float4(f[0], f[1], f[2], f[3]);
-        *reinterpret_cast<float4*>(o32 + n + 4) = make_float4(f[4], f[5], f[6], f[7]);
-      }
-      if (e.stats) {
+    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+  }
+  if (e.aux16_dsilu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 32; ++j) f[j] *= dsilu_f(x16[j]);
+  }
+  if (e.o16) store_chunk_bf16<FULL>(stg, lane, f, o16, p.out_bf16_ld, row_base, row_lim, nb, p.N);
+  if (e.o32) store_chunk_f32<FULL, false>(stg, lane, f, o32, p.out_f32_ld, row_base, row_lim, nb, p.N);
+  if (e.stats) {
+    if (row_base + lane < row_lim) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (FULL || nb + j < p.N) {
           const float rv = bf16_round(f[j]);
           s1 += rv;
           s2 = fmaf(rv, rv, s2);
@@ -189,6 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* stat_sm = reinterpret_cast<float*>(tmem_base_slot + 2);   // [2] per-tile GroupNorm partial sums
+  uint8_t* staging = reinterpret_cast<uint8_t*>(bars) + 256;         // [8 epilogue warps][4 KB]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -331,28 +421,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ------------------------------------------------------------------ epilogue warps (2..9)
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int chalf = (warp - 2) >> 2;   // the two warps of a quarter take alternate 32-column chunks
-    const int r = q * 32 + lane;
+    uint8_t* stg = staging + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
       TileCoord tc = decode_tile(p, tile, crank, kMC);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = tc.m0 + r;
       const bool k_nonempty = tc.k_end > tc.k_begin;
       float s1 = 0.f, s2 = 0.f;
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
       const int nchunks = p.BN / 32;
       if (!kWgrad) {
         const EpiFlags<F> e(p);
-        const bool row_ok = m < p.rows;
         const long long brow = (long long)tc.b;
-        const float* aux32 = e.aux32 ? p.aux_f32 + brow * p.aux_f32_bs + (long long)m * p.aux_f32_ld : nullptr;
-        const __nv_bfloat16* aux16 =
-            (e.aux16_add || e.aux16_dsilu) ? p.aux_bf16 + brow * p.aux_bf16_bs + (long long)m * p.aux_bf16_ld : nullptr;
-        __nv_bfloat16* o16 = e.o16 ? p.out_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
-        __nv_bfloat16* pre16 = e.pre16 ? p.pre_bf16 + brow * p.out_bf16_bs + (long long)m * p.out_bf16_ld : nullptr;
-        float* o32 = e.o32 ? p.out_f32 + brow * p.out_f32_bs + (long long)m * p.out_f32_ld : nullptr;
+        const int row_base = tc.m0 + q * 32;
+        const float* aux32 = e.aux32 ? p.aux_f32 + brow * p.aux_f32_bs : nullptr;
+        const __nv_bfloat16* aux16 = (e.aux16_add || e.aux16_dsilu) ? p.aux_bf16 + brow * p.aux_bf16_bs : nullptr;
+        __nv_bfloat16* o16 = e.o16 ? p.out_bf16 + brow * p.out_bf16_bs : nullptr;
+        __nv_bfloat16* pre16 = e.pre16 ? p.pre_bf16 + brow * p.out_bf16_bs : nullptr;
+        float* o32 = e.o32 ? p.out_f32 + brow * p.out_f32_bs : nullptr;
+        // L2 prefetch of the NEXT tile's aux operand rows (one 128-byte line per lane per chunk): by the time that tile's
+        // epilogue runs, its residual / SiLU-input tile is an L2 hit instead of a DRAM round trip per chunk.
+        if ((e.aux32 || e.aux16_add || e.aux16_dsilu) && tile + tile_step < p.num_tiles) {
+          const TileCoord tn = decode_tile(p, tile + tile_step, crank, kMC);
+          const int mrow = tn.m0 + q * 32 + lane;
+          if (mrow < p.rows) {
+            for (int c = chalf; c < nchunks; c += 2) {
+              const int nn = tn.n0 + c * 32;
+              if (nn < p.N) {
+                if (e.aux32) prefetch_l2(p.aux_f32 + (long long)tn.b * p.aux_f32_bs + (long long)mrow * p.aux_f32_ld + nn);
+                else prefetch_l2(p.aux_bf16 + (long long)tn.b * p.aux_bf16_bs + (long long)mrow * p.aux_bf16_ld + nn);
+              }
+            }
+          }
+        }
         // two 32-column chunks per iteration: both TMEM loads are in flight before the single wait
         for (int c = chalf; c < nchunks; c += 4) {
           uint32_t va[32], vb[32];
@@ -360,34 +463,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tmem_ld_32x32b_x32(tacc + c * 32, va);
           if (two) tmem_ld_32x32b_x32(tacc + (c + 2) * 32, vb);
           tmem_wait_ld();
-          if (row_ok) {
+          if (row_base < p.rows) {   // warp-uniform: the staged epilogue is warp-collective
             const int na = tc.n0 + c * 32, nb2 = tc.n0 + (c + 2) * 32;
-            if (na + 32 <= p.N) epi_chunk<F, true>(p, e, va, na, aux32, aux16, pre16, o16, o32, s1, s2);
-            else if (na < p.N) epi_chunk<F, false>(p, e, va, na, aux32, aux16, pre16, o16, o32, s1, s2);
+            if (na + 32 <= p.N) epi_chunk<F, true>(p, e, stg, lane, va, row_base, na, aux32, aux16, pre16, o16, o32, s1, s2);
+            else if (na < p.N) epi_chunk<F, false>(p, e, stg, lane, va, row_base, na, aux32, aux16, pre16, o16, o32, s1, s2);
             if (two) {
-              if (nb2 + 32 <= p.N) epi_chunk<F, true>(p, e, vb, nb2, aux32, aux16, pre16, o16, o32, s1, s2);
-              else if (nb2 < p.N) epi_chunk<F, false>(p, e, vb, nb2, aux32, aux16, pre16, o16, o32, s1, s2);
+              if (nb2 + 32 <= p.N) epi_chunk<F, true>(p, e, stg, lane, vb, row_base, nb2, aux32, aux16, pre16, o16, o32, s1, s2);
+              else if (nb2 < p.N) epi_chunk<F, false>(p, e, stg, lane, vb, row_base, nb2, aux32, aux16, pre16, o16, o32, s1, s2);
             }
           }
         }
       } else {
-        // WGRAD: atomically accumulate fp32 into out_f32[tap][m][n]
-        const bool row_ok = (m < p.K) && k_nonempty;
-        float* o32 = p.out_f32 + (long long)tc.tap * p.out_f32_bs + (long long)m * p.out_f32_ld;
+        // WGRAD: atomically accumulate fp32 into out_f32[tap][m][n] (coalesced red.v4 through the staging tile)
+        float* o32 = p.out_f32 + (long long)tc.tap * p.out_f32_bs;
+        const int row_base = tc.m0 + q * 32;
         for (int c = chalf; c < nchunks; c += 2) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tacc + c * 32, v);
           tmem_wait_ld();
           const int nb = tc.n0 + c * 32;
-          if (row_ok && nb < p.N) {
+          if (k_nonempty && nb < p.N && row_base < p.K) {
+            float f[32];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int n = nb + g * 4;
-              if (n < p.N) {
-                red_add_v4(o32 + n, __uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]),
-                           __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-              }
-            }
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            store_chunk_f32<false, true>(stg, lane, f, o32, p.out_f32_ld, row_base, p.K, nb, p.N);
           }
         }
       }
@@ -532,7 +631,7 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
   const uint32_t b_bytes = (uint32_t)BN * 128u;
   p.stage_bytes = kABytes + b_bytes;
   p.tx_bytes = p.stage_bytes;
-  int stages = (int)((200u * 1024u) / p.stage_bytes);
+  int stages = (int)((192u * 1024u) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
 
@@ -633,7 +732,7 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
     if ((rc = make_tmap_bf16(&tb, a->b, 3, bd, bstr, box)) != OF_OK) return rc;
   }
 
-  size_t smem_bytes = (size_t)p.num_stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  size_t smem_bytes = (size_t)p.num_stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
   uint32_t mask;
   if (wgrad) {
     mask = E_WGRAD;
