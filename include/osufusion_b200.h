@@ -208,7 +208,7 @@ int of_softmax_bwd_rows(const float* p, float* rd, int B, int L, void* stream);
  * of_linear_small_*    : nn.Linear with M <= 16 rows: time_mlp / cond_mlp (unet.py:356-366), FiLM heads
  *                        (residual.py:104-111), GlobalContext.layers 1x1 convs on the pooled (B,C,1) vector
  *                        (residual.py:22-27).  act: 0 none, 1 SiLU, 2 Sigmoid.  round_bf16 mimics autocast rounding
- *                        of inputs, weights and outputs.  bwd: dW/dbias accumulate (+=), dx accumulates atomically.
+ *                        of inputs, weights and outputs.  bwd: dW/dbias are written (accumulate=0) or accumulated (+=), dx accumulates atomically.
  * of_colsum_bf16       : bias gradients of the large Linear/Conv layers: db[n] += sum_rows dy[row, n].
  * of_pack_input        : F.pad(x, value=-1) / F.pad(a, value=-23) (unet.py:475-480) + channel-first -> channels-last
  *                        bf16, fused with `add_noise` (diffusion.py:96) / `t*x+(1-t)*noise` (rectified_flow.py:95).
@@ -238,7 +238,7 @@ int of_linear_small_fwd(const float* x, long long x_ld, int M, int N, int K, con
                         int act, int round_bf16, float* y, long long y_ld, float* ypre, void* stream);
 int of_linear_small_bwd(const float* dy, long long dy_ld, const float* ypre, int act, const float* x, long long x_ld, int M,
                         int N, int K, const float* W, long long w_ld, int round_bf16, float* dW, float* dbias, float* dx,
-                        long long dx_ld, void* stream);
+                        long long dx_ld, int accumulate, void* stream);
 int of_colsum_bf16(const void* dy, long long ld, long long rows, int N, float* db, void* stream);
 int of_pack_input(const float* x, const float* noise, const float* ca, const float* cb, int B, int C, int N, void* out, int Lp,
                   int Cp, float pad_value, void* stream);
@@ -261,8 +261,8 @@ int of_sampler_update(const float* xin, const void* cond, const void* null_, lon
                       void* packed, int Lp, int Cp, float pad_value, void* stream);
 int of_pack_conv_weight(const float* w, int Cout, int Cin, int k, void* out, int Cin_pad, int tap_offset, int taps_total,
                         void* stream);
-int of_unpack_conv_wgrad(const float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw, int accumulate,
-                         void* stream);
+int of_unpack_conv_wgrad(float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw, int accumulate,
+                         int rezero, void* stream);
 int of_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

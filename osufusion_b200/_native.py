@@ -103,7 +103,7 @@ _SIGS = {
     "of_rope_fwd": [P, LL, LL, I, I, I, I, I, P, P, I, P],
     "of_rope_bwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, P, P, I, P],
     "of_linear_small_fwd": [P, LL, I, I, I, P, LL, P, I, I, P, LL, P, P],
-    "of_linear_small_bwd": [P, LL, P, I, P, LL, I, I, I, P, LL, I, P, P, P, LL, P],
+    "of_linear_small_bwd": [P, LL, P, I, P, LL, I, I, I, P, LL, I, P, P, P, LL, I, P],
     "of_colsum_bf16": [P, LL, LL, I, P, P],
     "of_pack_input": [P, P, P, P, I, I, I, P, I, I, F, P],
     "of_unpack_output": [P, LL, LL, I, I, I, P, P],
@@ -116,7 +116,7 @@ _SIGS = {
     "of_mse_bwd": [P, LL, LL, P, P, F, F, P, I, I, I, I, I, P, P, P, P],
     "of_sampler_update": [P, P, P, LL, LL, F, I, F, F, F, F, I, I, I, P, P, I, I, F, P],
     "of_pack_conv_weight": [P, I, I, I, P, I, I, I, P],
-    "of_unpack_conv_wgrad": [P, I, I, I, I, I, P, I, P],
+    "of_unpack_conv_wgrad": [P, I, I, I, I, I, P, I, I, P],
     "of_cast_f32_bf16": [P, P, LL, P],
     "of_film_fwd": [P, I, I, P, I, I, P, P],
     "of_film_bwd": [P, P, I, P, P, I, I, P, P],

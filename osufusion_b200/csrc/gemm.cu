@@ -82,7 +82,6 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile,
 __device__ __forceinline__ void st_global_v4(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void red_add_v4(float* ptr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -441,21 +440,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         __nv_bfloat16* o16 = e.o16 ? p.out_bf16 + brow * p.out_bf16_bs : nullptr;
         __nv_bfloat16* pre16 = e.pre16 ? p.pre_bf16 + brow * p.out_bf16_bs : nullptr;
         float* o32 = e.o32 ? p.out_f32 + brow * p.out_f32_bs : nullptr;
-        // L2 prefetch of the NEXT tile's aux operand rows (one 128-byte line per lane per chunk): by the time that tile's
-        // epilogue runs, its residual / SiLU-input tile is an L2 hit instead of a DRAM round trip per chunk.
-        if ((e.aux32 || e.aux16_add || e.aux16_dsilu) && tile + tile_step < p.num_tiles) {
-          const TileCoord tn = decode_tile(p, tile + tile_step, crank, kMC);
-          const int mrow = tn.m0 + q * 32 + lane;
-          if (mrow < p.rows) {
-            for (int c = chalf; c < nchunks; c += 2) {
-              const int nn = tn.n0 + c * 32;
-              if (nn < p.N) {
-                if (e.aux32) prefetch_l2(p.aux_f32 + (long long)tn.b * p.aux_f32_bs + (long long)mrow * p.aux_f32_ld + nn);
-                else prefetch_l2(p.aux_bf16 + (long long)tn.b * p.aux_bf16_bs + (long long)mrow * p.aux_bf16_ld + nn);
-              }
-            }
-          }
-        }
         // two 32-column chunks per iteration: both TMEM loads are in flight before the single wait
         for (int c = chalf; c < nchunks; c += 4) {
           uint32_t va[32], vb[32];

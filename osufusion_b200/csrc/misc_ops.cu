@@ -78,24 +78,49 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     for (int j = 0; j < 8; ++j) dg[i].v[j] = db[i].v[j] = 0.f;
   }
   const int row0 = (blockIdx.x * 8 + warp) * rows_per_warp;
+  constexpr bool kPrefetch = NV <= 2;   // C <= 512: the next row's operands are loaded while this row is reduced
+  V8 xv[NV], dv[NV];
+  if (kPrefetch && row0 < rows) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < vecs) {
+        xv[i] = ld_f32x8(x + (long long)row0 * x_ld + vi * 8);
+        dv[i] = ld_f32x8(dy + (long long)row0 * dy_ld + vi * 8);
+      }
+    }
+  }
   for (int r = 0; r < rows_per_warp; ++r) {
     const int row = row0 + r;
     if (row >= rows) break;
     const float mean = mean_rstd[2 * row], rstd = mean_rstd[2 * row + 1];
-    V8 xh[NV], dxh[NV];
+    V8 xh[NV], dxh[NV], xn[NV], dn[NV];
+    const bool has_next = kPrefetch && (r + 1 < rows_per_warp) && (row + 1 < rows);
+    if (has_next) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < vecs) {
+          xn[i] = ld_f32x8(x + (long long)(row + 1) * x_ld + vi * 8);
+          dn[i] = ld_f32x8(dy + (long long)(row + 1) * dy_ld + vi * 8);
+        }
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < vecs) {
-        V8 xv = ld_f32x8(x + (long long)row * x_ld + vi * 8);
-        V8 d = ld_f32x8(dy + (long long)row * dy_ld + vi * 8);
+        if (!kPrefetch) {
+          xv[i] = ld_f32x8(x + (long long)row * x_ld + vi * 8);
+          dv[i] = ld_f32x8(dy + (long long)row * dy_ld + vi * 8);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i].v[j] = (xv.v[j] - mean) * rstd;
-          dg[i].v[j] += d.v[j] * xh[i].v[j];
-          db[i].v[j] += d.v[j];
-          dxh[i].v[j] = d.v[j] * g[i].v[j];
+          xh[i].v[j] = (xv[i].v[j] - mean) * rstd;
+          dg[i].v[j] += dv[i].v[j] * xh[i].v[j];
+          db[i].v[j] += dv[i].v[j];
+          dxh[i].v[j] = dv[i].v[j] * g[i].v[j];
           s1 += dxh[i].v[j];
           s2 += dxh[i].v[j] * xh[i].v[j];
         }
@@ -112,6 +137,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         for (int j = 0; j < 8; ++j) o.v[j] = rstd * (dxh[i].v[j] - s1 - xh[i].v[j] * s2);
         if (dx_f32) st_f32x8(dx_f32 + (long long)row * dx_ld + vi * 8, o);
         if (dx_bf16) st_bf16x8(dx_bf16 + (long long)row * dx_ld + vi * 8, o);
+      }
+    }
+    if (has_next) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xv[i] = xn[i];
+        dv[i] = dn[i];
       }
     }
   }
@@ -234,7 +266,7 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
   for (int m = 0; m < MM; ++m) acc[m] = 0.f;
   const float* w = W + (long long)n * w_ld;
   if ((K & 3) == 0 && (w_ld & 3) == 0 && (x_ld & 3) == 0) {
-#pragma unroll 2
+#pragma unroll 4
     for (int k = lane * 4; k < K; k += 128) {
       float4 wv = *reinterpret_cast<const float4*>(w + k);
       if (round_bf16) { wv.x = bf16_round(wv.x); wv.y = bf16_round(wv.y); wv.z = bf16_round(wv.z); wv.w = bf16_round(wv.w); }
@@ -278,8 +310,9 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
   }
 }
 
-// dpre[m,n] = dy[m,n] * act'(ypre[m,n]);  dW[n,k] += sum_m dpre*x ; db[n] += sum_m dpre ; dx[m,k] += sum_n dpre*W (atomic)
-// grid: (ceil(K/ (256*4 or 256)), ceil(N/NCHUNK)); thread owns 4 (or 1) consecutive k.
+// dpre[m,n] = dy[m,n] * act'(ypre[m,n]);  dW[n,k] (+)= sum_m dpre*x ; db[n] (+)= sum_m dpre ; dx[m,k] += sum_n dpre*W (atomic)
+// CTA = kNChunk output rows x a k-slice.  Threads are laid out as `kthreads` k-lanes (4 consecutive k each, or 1) times
+// `nlanes` row-lanes, so small K (gate MLPs: K = C/2) still fills the CTA; every thread keeps 4 rows of W (and dW) in flight.
 constexpr int kNChunk = 16;
 template <int MM>
 __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __restrict__ dy, long long dy_ld,
@@ -287,7 +320,7 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
                                                                const float* __restrict__ x, long long x_ld, int M, int N, int K,
                                                                const float* __restrict__ W, long long w_ld, int round_bf16,
                                                                float* __restrict__ dW, float* __restrict__ dbias,
-                                                               float* __restrict__ dx, long long dx_ld) {
+                                                               float* __restrict__ dx, long long dx_ld, int kthreads, int accumulate) {
   __shared__ float sdpre[kNChunk][kMaxM];
   const int n0 = blockIdx.y * kNChunk;
   const int nn = min(kNChunk, N - n0);
@@ -308,11 +341,14 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
   if (dbias && blockIdx.x == 0 && threadIdx.x < nn) {
     float s = 0.f;
     for (int m = 0; m < M; ++m) s += sdpre[threadIdx.x][m];
-    atomicAdd(dbias + n0 + threadIdx.x, s);
+    if (accumulate) dbias[n0 + threadIdx.x] += s;
+    else dbias[n0 + threadIdx.x] = s;
   }
   const bool vec4 = ((K & 3) == 0) && ((w_ld & 3) == 0) && ((x_ld & 3) == 0) && ((dx_ld & 3) == 0);
   const int kw = vec4 ? 4 : 1;
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * kw;
+  const int nlanes = blockDim.x / kthreads;
+  const int kt = threadIdx.x % kthreads, nl = threadIdx.x / kthreads;
+  const int k = (blockIdx.x * kthreads + kt) * kw;
   if (k >= K) return;
   float xa[MM][4];
   float dxa[MM][4];
@@ -328,33 +364,55 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
       }
     }
   }
-  for (int j = 0; j < nn; ++j) {
-    const long long wo = (long long)(n0 + j) * w_ld + k;
-    float wv[4], g[4];
+  for (int j0 = nl; j0 < nn; j0 += 4 * nlanes) {
+    float wv[4][4], gv[4][4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      wv[e] = 0.f;
-      g[e] = 0.f;
-      if (e < kw) {
-        wv[e] = W[wo + e];
-        if (round_bf16) wv[e] = bf16_round(wv[e]);
+    for (int r = 0; r < 4; ++r) {
+      const int j = j0 + r * nlanes;
+      const long long wo = (long long)(n0 + j) * w_ld + k;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        wv[r][e] = 0.f;
+        gv[r][e] = 0.f;
       }
-    }
-#pragma unroll
-    for (int m = 0; m < MM; ++m) {
-      if (m < M) {
-        const float d = sdpre[j][m];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          g[e] += d * xa[m][e];
-          dxa[m][e] += d * wv[e];
+      if (j < nn) {
+        if (vec4) {
+          const float4 t = *reinterpret_cast<const float4*>(W + wo);
+          wv[r][0] = t.x; wv[r][1] = t.y; wv[r][2] = t.z; wv[r][3] = t.w;
+          if (dW && accumulate) {
+            const float4 u = *reinterpret_cast<const float4*>(dW + wo);
+            gv[r][0] = u.x; gv[r][1] = u.y; gv[r][2] = u.z; gv[r][3] = u.w;
+          }
+        } else {
+          wv[r][0] = W[wo];
+          if (dW && accumulate) gv[r][0] = dW[wo];
         }
       }
     }
-    if (dW) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (e < kw) dW[wo + e] += g[e];
+    for (int r = 0; r < 4; ++r) {
+      const int j = j0 + r * nlanes;
+      if (j < nn) {
+        const long long wo = (long long)(n0 + j) * w_ld + k;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (round_bf16) wv[r][e] = bf16_round(wv[r][e]);
+#pragma unroll
+        for (int m = 0; m < MM; ++m) {
+          if (m < M) {
+            const float d = sdpre[j][m];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              gv[r][e] = fmaf(d, xa[m][e], gv[r][e]);
+              dxa[m][e] = fmaf(d, wv[r][e], dxa[m][e]);
+            }
+          }
+        }
+        if (dW) {
+          if (vec4) *reinterpret_cast<float4*>(dW + wo) = make_float4(gv[r][0], gv[r][1], gv[r][2], gv[r][3]);
+          else dW[wo] = gv[r][0];
+        }
+      }
     }
   }
   if (dx) {
@@ -639,16 +697,18 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
     out[((long long)(t + tap_offset) * Cout + co) * Cin_pad + ci0 + ci] = __float2bfloat16_rn(v);
   }
 }
-__global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(const float* __restrict__ packed, int Cout, int Cin, int k,
+__global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(float* __restrict__ packed, int Cout, int Cin, int k,
                                                                 int Cin_pad, int tap_offset, float* __restrict__ dw,
-                                                                int accumulate) {
+                                                                int accumulate, int rezero) {
   extern __shared__ float s_w[];
   const int co = blockIdx.x;
   const int ci0 = blockIdx.y * kPackChunk;
   const int nreal = max(0, min(kPackChunk, Cin - ci0));
   for (int i = threadIdx.x; i < nreal * k; i += blockDim.x) {
     const int t = i / nreal, ci = i - t * nreal;
-    s_w[ci * k + t] = packed[((long long)(t + tap_offset) * Cout + co) * Cin_pad + ci0 + ci];
+    float* src = packed + ((long long)(t + tap_offset) * Cout + co) * Cin_pad + ci0 + ci;
+    s_w[ci * k + t] = *src;
+    if (rezero) *src = 0.f;   // persistent split-K scratch: left clean for the next step (no per-step fill launch)
   }
   __syncthreads();
   float* dst = dw + ((long long)co * Cin + ci0) * k;
@@ -755,17 +815,20 @@ extern "C" int of_linear_small_fwd(const float* x, long long x_ld, int M, int N,
 
 extern "C" int of_linear_small_bwd(const float* dy, long long dy_ld, const float* ypre, int act, const float* x, long long x_ld,
                                    int M, int N, int K, const float* W, long long w_ld, int round_bf16, float* dW, float* dbias,
-                                   float* dx, long long dx_ld, void* stream) {
+                                   float* dx, long long dx_ld, int accumulate, void* stream) {
   OF_REQUIRE(dy && x && W, "of_linear_small_bwd: null pointer");
   OF_REQUIRE(M >= 1 && M <= kMaxM, "of_linear_small_bwd: M=%d out of range", M);
   OF_REQUIRE(act == 0 || ypre, "of_linear_small_bwd: ypre required for activation backward");
   const bool vec4 = ((K & 3) == 0) && ((w_ld & 3) == 0) && ((x_ld & 3) == 0) && (!dx || (dx_ld & 3) == 0);
   const int kw = vec4 ? 4 : 1;
-  dim3 grid((K + 256 * kw - 1) / (256 * kw), (N + kNChunk - 1) / kNChunk);
+  const int kcols = (K + kw - 1) / kw;
+  int kthreads = 16;                       // power of two: at most 16 row-lanes (= kNChunk rows side by side)
+  while (kthreads < kcols && kthreads < 256) kthreads <<= 1;
+  dim3 grid((kcols + kthreads - 1) / kthreads, (N + kNChunk - 1) / kNChunk);
   const long long dxl = dx ? dx_ld : 4;
-  if (M <= 4) linear_small_bwd_kernel<4><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl);
-  else if (M <= 8) linear_small_bwd_kernel<8><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl);
-  else linear_small_bwd_kernel<16><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl);
+  if (M <= 4) linear_small_bwd_kernel<4><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate);
+  else if (M <= 8) linear_small_bwd_kernel<8><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate);
+  else linear_small_bwd_kernel<16><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate);
   DONE()
 }
 
@@ -875,13 +938,13 @@ extern "C" int of_pack_conv_weight(const float* w, int Cout, int Cin, int k, voi
                                                                                  Cin_pad, tap_offset, taps_total);
   DONE()
 }
-extern "C" int of_unpack_conv_wgrad(const float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw,
-                                    int accumulate, void* stream) {
+extern "C" int of_unpack_conv_wgrad(float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw,
+                                    int accumulate, int rezero, void* stream) {
   OF_REQUIRE(packed && dw, "of_unpack_conv_wgrad: null pointer");
   OF_REQUIRE(k <= 32, "of_unpack_conv_wgrad: kernel size %d too large", k);
   dim3 grid(Cout, (Cin + kPackChunk - 1) / kPackChunk);
   unpack_conv_wgrad_kernel<<<grid, 256, kPackChunk * k * sizeof(float), STREAM>>>(packed, Cout, Cin, k, Cin_pad, tap_offset, dw,
-                                                                                  accumulate);
+                                                                                  accumulate, rezero);
   DONE()
 }
 extern "C" int of_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {

@@ -130,11 +130,18 @@ def linear_small_fwd(x, W, bias, act=0, want_pre=False):
     return y, pre
 
 
-def linear_small_bwd(dy, pre, act, x, W, dW, dbias, dx):
+def linear_small_bwd(dy, pre, act, x, W, dW, dbias, dx, accumulate=True):
     M, K = x.shape
     Nn = W.shape[0]
     N.call("of_linear_small_bwd", _p(dy), dy.stride(0), _p(pre), act, _p(x), x.stride(0), M, Nn, K, _p(W), K, 1, _p(dW),
-           _p(dbias), _p(dx), dx.stride(0) if dx is not None else 0)
+           _p(dbias), _p(dx), dx.stride(0) if dx is not None else 0, int(accumulate))
+
+
+def linear_small_bwd_param(st, dy, pre, act, x, w, b, dx):
+    """Backward of a small Linear / 1x1-conv whose parameters are `w` (viewed as (N, K)) and `b`: gradients go straight into the
+    arena; the first contribution of a step overwrites (the arena holds zeros), later ones accumulate."""
+    fresh = id(w) not in st.touched and (b is None or id(b) not in st.touched)
+    linear_small_bwd(dy, pre, act, x, w.view(w.shape[0], -1), st.grad_opt(w), st.grad_opt(b), dx, accumulate=not fresh)
 
 
 def colsum(dy16: torch.Tensor, out: torch.Tensor) -> None:
@@ -637,11 +644,13 @@ def _wgrad_conv(store: ParamStore, w: torch.nn.Parameter, dy16, x16, taps, shift
         return
     Cout, Cin, k = w.shape
     cp = (Cin + 7) // 8 * 8
+    # a fresh allocation (not a persistent scratch): the caching allocator hands back the block the previous layer just released,
+    # so fill -> split-K atomics -> unpack stay L2-resident (measured: a persistent 3 GB scratch made the unpack 6x slower)
     tmp = zeros((k, Cout, cp), F32, w.device)
     R.gemm_wgrad(dy16, x16, tmp, M=Cout, N_out=cp, taps=taps, shift0=shift0, shift_step=1)
     acc = 0 if store.touch(w) else 1
     g = store.grad(w)
-    N.call("of_unpack_conv_wgrad", _p(tmp), Cout, Cin, k, cp, 0, _p(g), acc)
+    N.call("of_unpack_conv_wgrad", _p(tmp), Cout, Cin, k, cp, 0, _p(g), acc, 0)
 
 
 def _wgrad_linear(store: ParamStore, w: torch.nn.Parameter, dy16, x16, row0: int = 0, rows: Optional[int] = None):
@@ -793,9 +802,9 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             N.call("of_rb_gate_bwd_reduce", C.byref(b2))
             # gate MLP backward
             dg1 = zeros((B, Wa.shape[0]), F32, dev)
-            linear_small_bwd(dgate, gatepre, 2, g1, Wb.view(Wb.shape[0], -1), st.grad_opt(Wb), st.grad_opt(se.layers[2].bias), dg1)
+            linear_small_bwd_param(st, dgate, gatepre, 2, g1, Wb, se.layers[2].bias, dg1)
             dpooled = zeros((B, Cout), F32, dev)
-            linear_small_bwd(dg1, g1pre, 1, pooled, Wa.view(Wa.shape[0], -1), st.grad_opt(Wa), st.grad_opt(se.layers[0].bias), dpooled)
+            linear_small_bwd_param(st, dg1, g1pre, 1, pooled, Wa, se.layers[0].bias, dpooled)
             # d logits
             da = empty((B, L), F32, dev)
             b2.mode = 1

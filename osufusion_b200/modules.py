@@ -321,11 +321,11 @@ class UNet(nn.Module):
                     st.set_grad(self.null_cond, (dcs * (~keep)[:, None]).sum(0))
                 dcv = (dcs * keep[:, None]).contiguous()
                 dc1 = E.zeros((B, Em), F32, dev)
-                E.linear_small_bwd(dcv, None, 0, c1, c2.weight, st.grad_opt(c2.weight), st.grad_opt(c2.bias), dc1)
-                E.linear_small_bwd(dc1, c1pre, 1, cin, c0.weight, st.grad_opt(c0.weight), st.grad_opt(c0.bias), None)
+                E.linear_small_bwd_param(st, dcv, None, 0, c1, c2.weight, c2.bias, dc1)
+                E.linear_small_bwd_param(st, dc1, c1pre, 1, cin, c0.weight, c0.bias, None)
                 dt1 = E.zeros((B, Em), F32, dev)
-                E.linear_small_bwd(dt, None, 0, t1, l3.weight, st.grad_opt(l3.weight), st.grad_opt(l3.bias), dt1)
-                E.linear_small_bwd(dt1, t1pre, 1, temb, l1.weight, st.grad_opt(l1.weight), st.grad_opt(l1.bias), None)
+                E.linear_small_bwd_param(st, dt, None, 0, t1, l3.weight, l3.bias, dt1)
+                E.linear_small_bwd_param(st, dt1, t1pre, 1, temb, l1.weight, l1.bias, None)
             ctx.tape.push(backward)
 
     def denoise(self, ctx: Ctx, x16: torch.Tensor, a_feat: Act, t, c, keep) -> tuple:
