@@ -150,6 +150,11 @@ def run_ours(args) -> None:
     torch.manual_seed(0)
     model = DiffusionOsuFusion(SIZES[size]).to(dev)
     torch.nn.init.normal_(model.unet.final_conv.weight, std=0.02)
+    adapted = None
+    if args.lora:      # BASELINE.json configs[4]: trainer_peft.py LoRA/DoRA fine-tuning step, base weights frozen
+        from osufusion_b200 import lora
+        adapted = lora.inject_adapters(model, r=32, lora_alpha=32, use_dora=True)
+        model.to(dev)
     sync = None
     if world > 1:
         from osufusion_b200.ddp import GradAllReducer
@@ -236,6 +241,22 @@ def run_ours(args) -> None:
 
     NN.PROFILE = None
     del l2
+    # ---- optimizer tail (excluded from the metric, reported beside it): fused grad-norm clip + AdamW over the gradient arena
+    opt_ms = None
+    if args.optimizer:
+        from osufusion_b200.optim import FusedAdamW
+        step()
+        opt = FusedAdamW(model, lr=1e-5)
+        for _ in range(2):
+            opt.step()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(5):
+            opt.step()
+        o1.record()
+        torch.cuda.synchronize()
+        opt_ms = o0.elapsed_time(o1) / 5
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cores, _ = cpu_reference_step_time(size, args.ref_frames, 1, 0)
@@ -249,7 +270,10 @@ def run_ours(args) -> None:
             "metric": "denoiser fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"CFG-{size} dim_h={SIZES[size]} denoiser train micro-step (fwd+bwd, all grads), cond_drop_prob=0.5",
+            "config": {"workload": (f"CFG-{size} dim_h={SIZES[size]} denoiser train micro-step (fwd+bwd, all grads), cond_drop_prob=0.5"
+                                    if adapted is None else
+                                    f"CFG-{size} dim_h={SIZES[size]} LoRA/DoRA fine-tuning micro-step (r=32, alpha=32, {len(adapted)} adapted "
+                                    f"modules, base frozen), cond_drop_prob=0.5"),
                        "per_gpu_batch": B, "global_batch": B * world, "frames": n, "parallelism": f"dp{world}",
                        "l2": "working set (2.6 GB bf16 weights + activations) >> 126 MB L2; no explicit flush",
                        "cuda_graph": True},
@@ -258,6 +282,7 @@ def run_ours(args) -> None:
             "gpu_launches": int(launches_per_step * args.steps),
             "model_tflops_per_gpu": step_tflop / (ms * 1e-3), "mfu_vs_measured_peak": step_tflop / (ms * 1e-3) / tf_peak,
             "roofline": roof, "cpu_baseline": cpu, "loss": float(step.loss.detach()),
+            "optimizer_ms_per_step": opt_ms,
         }
         print(json.dumps(line), flush=True)
     _finish(world)
@@ -367,6 +392,8 @@ def main() -> None:
     ap.add_argument("--frames", type=int, default=4096)
     ap.add_argument("--ref-frames", type=int, default=1024, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lora", action="store_true", help="BASELINE.json configs[4]: LoRA/DoRA fine-tuning step (base frozen)")
+    ap.add_argument("--optimizer", action="store_true", help="also time the fused clip + AdamW step (reported separately)")
     ap.add_argument("--mode", default="train", choices=["train", "sample"], help="train: fwd+bwd samples/s; sample: frames/s")
     ap.add_argument("--cond-scale", type=float, default=2.0)
     args = ap.parse_args()

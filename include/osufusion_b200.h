@@ -318,6 +318,28 @@ int of_film_chunk_rows(void);
 int of_pack_weights(const of_pack_seg* segs_dev, int num_segs, int total_ctas, void* stream);
 int of_pack_seg_ctas(int Cout, int Cin, int k, int cin_pad);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused optimizer step (trainer.py:302-309: clip_grad_norm_(params, 1.0) + torch.optim.AdamW.step()).
+ * Gradients / exp_avg / exp_avg_sq are flat fp32 arenas with one common layout; parameters are separate tensors.
+ *   of_grad_sumsq : out[0] = sum g^2 over the arena (double; padding between tensors must be zero)
+ *   of_adamw_step : torch.optim.AdamW semantics (decoupled weight decay, bias correction, amsgrad off); gradients are
+ *                   scaled by min(1, max_norm / (sqrt(sumsq) + 1e-6)) read from DEVICE memory (sumsq NULL or max_norm <= 0:
+ *                   no clipping) -- no host synchronisation.  Bytes per element: 16 read + 12 written.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  float* param;          /* fp32 parameter tensor (contiguous) */
+  long long arena_off;   /* offset (floats) of its gradient / moments in the arenas */
+  long long numel;
+  int cta_begin;         /* running sum of of_opt_tensor_ctas(numel) */
+  int _pad;
+} of_opt_tensor;
+
+int of_grad_sumsq(const float* grads, long long n, double* out, void* stream);
+int of_opt_tensor_ctas(long long numel);
+int of_adamw_step(const of_opt_tensor* table_dev, int num_tensors, int total_ctas, const float* grads, float* exp_avg,
+                  float* exp_avg_sq, const double* sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

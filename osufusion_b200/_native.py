@@ -84,6 +84,10 @@ class PackSeg(C.Structure):
     _fields_ = [("src", P), ("dst", P), ("Cout", I), ("Cin", I), ("k", I), ("cin_pad", I), ("cta_begin", I), ("_pad", I)]
 
 
+class OptTensor(C.Structure):
+    _fields_ = [("param", P), ("arena_off", LL), ("numel", LL), ("cta_begin", I), ("_pad", I)]
+
+
 # name -> argtypes (the trailing stream pointer included); mirrors include/osufusion_b200.h
 _SIGS = {
     "of_gemm": [C.POINTER(GemmArgs), P],
@@ -121,10 +125,12 @@ _SIGS = {
     "of_film_fwd": [P, I, I, P, I, I, P, P],
     "of_film_bwd": [P, P, I, P, P, I, I, P, P],
     "of_pack_weights": [P, I, I, P],
+    "of_grad_sumsq": [P, LL, P, P],
+    "of_adamw_step": [P, I, I, P, P, P, P, F, F, F, F, F, F, I, P],
     "of_dora_merge": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P],
     "of_dora_grad": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P, P, P],
 }
-_PLAIN = {"of_film_chunk_rows": [], "of_pack_seg_ctas": [I, I, I, I]}    # host-side helpers: no stream argument, return a value
+_PLAIN = {"of_film_chunk_rows": [], "of_pack_seg_ctas": [I, I, I, I], "of_opt_tensor_ctas": [LL]}    # host-side helpers: no stream argument, return a value
 EXPORTS = ["of_last_error", "of_version", "of_launch_count", "of_reset_launch_count", *_SIGS.keys(), *_PLAIN.keys()]
 
 

@@ -239,3 +239,117 @@ extern "C" int of_pack_seg_ctas(int Cout, int Cin, int k, int cin_pad) {
   if (k > 4) return -1;
   return Cout * ((cin_pad + kPackCi - 1) / kPackCi);
 }
+
+// ------------------------------------------------------------------------------------------------ fused optimizer step
+// (`accelerator.clip_grad_norm_(params, 1.0)` + `torch.optim.AdamW.step()` of trainer.py:302-309 without the
+//  per-tensor launches and the two host synchronisations.)  Gradients, exp_avg and exp_avg_sq are flat arenas with identical
+//  layout (the engine's gradient arena); only the parameters are separate tensors.
+namespace ofx {
+
+// sum of squares of the whole arena (padding between tensors is zero) -> out[0] (double, atomically accumulated)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(g + i);
+      s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+    } else {
+      for (long long j = i; j < n; ++j) s = fmaf(g[j], g[j], s);
+    }
+  }
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(out, (double)s);
+}
+
+constexpr int kOptChunk = 4096;   // elements per CTA
+
+// torch.optim.AdamW (amsgrad=False, maximize=False) on every tensor of the table; gradients are scaled by
+// clip = min(1, max_norm / (sqrt(sumsq) + 1e-6)) read from device memory (torch.nn.utils.clip_grad_norm_ semantics), without
+// being modified in place.
+__global__ void __launch_bounds__(256) adamw_kernel(const of_opt_tensor* __restrict__ tab, int num_tensors, const float* __restrict__ grads,
+                                                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                    const double* __restrict__ sumsq, float max_norm, float lr, float beta1, float beta2,
+                                                    float eps, float weight_decay, float bias_corr1, float bias_corr2_sqrt) {
+  int lo = 0, hi = num_tensors - 1;
+  const int cta = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].cta_begin <= cta) lo = mid;
+    else hi = mid - 1;
+  }
+  const of_opt_tensor t = tab[lo];
+  float clip = 1.0f;
+  if (sumsq != nullptr && max_norm > 0.f) {
+    const float nrm = (float)sqrt(*sumsq);
+    clip = fminf(1.0f, max_norm / (nrm + 1e-6f));
+  }
+  const long long base = (long long)(cta - t.cta_begin) * kOptChunk;
+  const float step_size = lr / bias_corr1;
+  const float decay = 1.0f - lr * weight_decay;
+#pragma unroll
+  for (int it = 0; it < kOptChunk / 1024; ++it) {
+    const long long e = base + (it * 256 + threadIdx.x) * 4;
+    if (e >= t.numel) break;
+    const long long a = t.arena_off + e;
+    if (e + 3 < t.numel && (t.numel & 3) == 0) {
+      float4 p = *reinterpret_cast<const float4*>(t.param + e);
+      const float4 g4 = *reinterpret_cast<const float4*>(grads + a);
+      float4 m = *reinterpret_cast<const float4*>(exp_avg + a), v = *reinterpret_cast<const float4*>(exp_avg_sq + a);
+      float pp[4] = {p.x, p.y, p.z, p.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g = gg[j] * clip;
+        pp[j] *= decay;
+        mm[j] = beta1 * mm[j] + (1.0f - beta1) * g;
+        vv[j] = beta2 * vv[j] + (1.0f - beta2) * g * g;
+        pp[j] -= step_size * mm[j] / (sqrtf(vv[j]) / bias_corr2_sqrt + eps);
+      }
+      *reinterpret_cast<float4*>(t.param + e) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      *reinterpret_cast<float4*>(exp_avg + a) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(exp_avg_sq + a) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    } else {
+      for (long long j = e; j < min(e + 4, t.numel); ++j) {
+        const float g = grads[t.arena_off + j] * clip;
+        float p = t.param[j] * decay;
+        const float m = beta1 * exp_avg[t.arena_off + j] + (1.0f - beta1) * g;
+        const float v = beta2 * exp_avg_sq[t.arena_off + j] + (1.0f - beta2) * g * g;
+        p -= step_size * m / (sqrtf(v) / bias_corr2_sqrt + eps);
+        t.param[j] = p;
+        exp_avg[t.arena_off + j] = m;
+        exp_avg_sq[t.arena_off + j] = v;
+      }
+    }
+  }
+}
+
+}  // namespace ofx
+
+extern "C" int of_grad_sumsq(const float* grads, long long n, double* out, void* stream) {
+  OF_REQUIRE(grads && out && n >= 0, "of_grad_sumsq: bad args");
+  OF_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), STREAM));
+  if (n > 0) {
+    long long want = (n / 4 + 255) / 256;
+    const int grid = (int)(want < 8LL * device_sm_count() ? (want < 1 ? 1 : want) : 8LL * device_sm_count());
+    sumsq_kernel<<<grid, 256, 0, STREAM>>>(grads, n, out);
+    OF_CHECK_CUDA(cudaGetLastError());
+  }
+  count_launch();
+  return OF_OK;
+}
+
+extern "C" int of_opt_tensor_ctas(long long numel) { return (int)((numel + kOptChunk - 1) / kOptChunk); }
+
+extern "C" int of_adamw_step(const of_opt_tensor* table_dev, int num_tensors, int total_ctas, const float* grads, float* exp_avg,
+                             float* exp_avg_sq, const double* sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int step, void* stream) {
+  OF_REQUIRE(table_dev && grads && exp_avg && exp_avg_sq && num_tensors >= 1 && total_ctas >= 1 && step >= 1, "of_adamw_step: bad args");
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+  adamw_kernel<<<total_ctas, 256, 0, STREAM>>>(table_dev, num_tensors, grads, exp_avg, exp_avg_sq, sumsq, max_norm, lr, beta1, beta2, eps,
+                                               weight_decay, bc1, bc2s);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}

@@ -239,6 +239,7 @@ class ParamStore:
         self.arena_key = None
         self.film_floats = None      # (start, end) floats of the FiLM-head block (written, never accumulated -> not zeroed)
         self.touched = set()
+        self.param_epoch = 0         # bumped by optimizers that update parameters through raw pointers (osufusion_b200/optim.py)
         self.pack_plan = None
         self.film_plans = {}
         # set by ddp.GradAllReducer
@@ -384,13 +385,13 @@ class ParamStore:
             if plan is None:
                 return
             plan["n_adapters"] = sum(1 for m in unet.modules() if hasattr(m, "base_layer"))
-        vers = tuple(p._version for _, ps, _ in plan["views"] for p in ps)
+        vers = tuple(p._version for _, ps, _ in plan["views"] for p in ps) + (self.param_epoch,)
         if not self.refresh and vers == plan["vers"]:
             return
         N.call("of_pack_weights", plan["table"].data_ptr(), plan["num_segs"], plan["ctas"])
         plan["vers"] = vers
         for key, params, view in plan["views"]:
-            self.cache[key] = (tuple((p.data_ptr(), p._version) for p in params), view, self.epoch)
+            self.cache[key] = (tuple((p.data_ptr(), p._version) for p in params) + (self.param_epoch,), view, self.epoch)
 
     # ---- grouped FiLM heads
     def film_plan(self, unet, B: int, with_grads: bool):
@@ -434,7 +435,7 @@ class ParamStore:
         return plan
 
     def _cached(self, key, params, build):
-        ver = tuple((p.data_ptr(), p._version) for p in params)
+        ver = tuple((p.data_ptr(), p._version) for p in params) + (self.param_epoch,)
         hit = self.cache.get(key)
         if hit is not None and hit[0] == ver and (not self.refresh or hit[2] == self.epoch):
             return hit[1]

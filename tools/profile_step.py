@@ -13,6 +13,10 @@ dev = "cuda"
 torch.manual_seed(0)
 model = DiffusionOsuFusion({"L": 512, "S": 128}[size]).to(dev)
 torch.nn.init.normal_(model.unet.final_conv.weight, std=0.02)
+if len(sys.argv) > 4 and sys.argv[4] == "lora":
+    from osufusion_b200 import lora
+    lora.inject_adapters(model, r=32, lora_alpha=32, use_dora=True)
+    model.to(dev)
 x, a, c = torch.randn(B, 6, n, device=dev), torch.randn(B, 96, n, device=dev), torch.randn(B, 5, device=dev)
 for _ in range(2):
     model.zero_grad(set_to_none=True)
