@@ -9,7 +9,8 @@
 namespace ofx {
 
 constexpr int kDoraE = 256;   // e-columns per CTA (one per thread)
-constexpr int kDoraCo = 16;   // output channels per CTA
+constexpr int kDoraCo = 16;   // output channels per CTA tile
+constexpr int kDoraEP = kDoraE + 4;   // padded row stride of the A / G tiles in shared memory (float4 reads down a column of rows)
 
 struct DoraArgs {
   const float* W;   // (Cout, E)   E = Cin*k, torch layout (ci-major, tap-minor)
@@ -20,68 +21,120 @@ struct DoraArgs {
   int Cout, Cin, k, r, Cin_pad;
 };
 
-__device__ __forceinline__ void dora_load_tiles(const DoraArgs& a, int e0, int co0, float* sA, float* sB) {
+constexpr int kDoraRMax = 128;   // rank limit (register tile of the A column is processed in chunks of 32)
+
+// d[c] = sum_r B[co0+c, r] * A[r, e] for the thread's column e and all kDoraCo rows of the CTA: the A column is held in
+// registers 32 ranks at a time and B is read as broadcast float4 (0.25 shared loads per FMA instead of 2).
+__device__ __forceinline__ void dora_ba_column(const DoraArgs& a, const float* sA, const float* sB, float (&d)[kDoraCo]) {
+#pragma unroll
+  for (int c = 0; c < kDoraCo; ++c) d[c] = 0.f;
+  for (int r0 = 0; r0 < a.r; r0 += 32) {
+    float av[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) av[r] = (r0 + r < a.r) ? sA[(r0 + r) * kDoraEP + threadIdx.x] : 0.f;
+    if ((a.r & 3) == 0) {
+#pragma unroll
+      for (int c = 0; c < kDoraCo; ++c) {
+#pragma unroll
+        for (int r4 = 0; r4 < 8; ++r4) {
+          if (r0 + r4 * 4 < a.r) {
+            const float4 b = *reinterpret_cast<const float4*>(sB + c * a.r + r0 + r4 * 4);
+            d[c] = fmaf(b.x, av[r4 * 4], fmaf(b.y, av[r4 * 4 + 1], fmaf(b.z, av[r4 * 4 + 2], fmaf(b.w, av[r4 * 4 + 3], d[c]))));
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < kDoraCo; ++c)
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (r0 + r < a.r) d[c] = fmaf(sB[c * a.r + r0 + r], av[r], d[c]);
+    }
+  }
+}
+
+__device__ __forceinline__ void dora_load_a_tile(const DoraArgs& a, int e0, float* sA) {
   const int E = a.Cin * a.k;
   for (int i = threadIdx.x; i < a.r * kDoraE; i += blockDim.x) {
     const int r = i / kDoraE, e = e0 + (i - r * kDoraE);
-    sA[i] = e < E ? a.A[(long long)r * E + e] : 0.f;
+    sA[r * kDoraEP + (i - r * kDoraE)] = e < E ? a.A[(long long)r * E + e] : 0.f;
   }
+}
+__device__ __forceinline__ void dora_load_b_tile(const DoraArgs& a, int co0, int co_end, float* sB) {
   for (int i = threadIdx.x; i < kDoraCo * a.r; i += blockDim.x) {
     const int c = i / a.r, co = co0 + c;
-    sB[i] = co < a.Cout ? a.B[(long long)co * a.r + (i - c * a.r)] : 0.f;
+    sB[i] = co < co_end ? a.B[(long long)co * a.r + (i - c * a.r)] : 0.f;
   }
-  __syncthreads();
 }
 
+// CTA = one 256-column e-tile x a range of output channels walked 16 at a time (the A tile is loaded once per CTA).
 // n2[co] += sum_e (W + scaling*BA)^2
-__global__ void __launch_bounds__(kDoraE) dora_norm_kernel(const DoraArgs a, float* __restrict__ n2) {
+__global__ void __launch_bounds__(kDoraE) dora_norm_kernel(const DoraArgs a, float* __restrict__ n2, int co_per_cta) {
   extern __shared__ float sm[];
   float* sA = sm;
-  float* sB = sA + a.r * kDoraE;
+  float* sB = sA + a.r * kDoraEP;
   float* sN = sB + kDoraCo * a.r;
   const int E = a.Cin * a.k;
-  const int e0 = blockIdx.x * kDoraE, co0 = blockIdx.y * kDoraCo;
-  if (threadIdx.x < kDoraCo) sN[threadIdx.x] = 0.f;
-  dora_load_tiles(a, e0, co0, sA, sB);
+  const int e0 = blockIdx.x * kDoraE;
+  const int co_begin = blockIdx.y * co_per_cta, co_end = min(co_begin + co_per_cta, a.Cout);
   const int e = e0 + threadIdx.x;
-  for (int c = 0; c < kDoraCo; ++c) {
-    const int co = co0 + c;
-    float sq = 0.f;
-    if (co < a.Cout && e < E) {
-      float d = 0.f;
-      for (int r = 0; r < a.r; ++r) d += sB[c * a.r + r] * sA[r * kDoraE + threadIdx.x];
-      const float v = a.W[(long long)co * E + e] + a.scaling * d;
-      sq = v * v;
+  dora_load_a_tile(a, e0, sA);
+  for (int co0 = co_begin; co0 < co_end; co0 += kDoraCo) {
+    __syncthreads();
+    dora_load_b_tile(a, co0, co_end, sB);
+    if (threadIdx.x < kDoraCo) sN[threadIdx.x] = 0.f;
+    float d[kDoraCo], w[kDoraCo];
+#pragma unroll
+    for (int c = 0; c < kDoraCo; ++c) w[c] = (co0 + c < co_end && e < E) ? a.W[(long long)(co0 + c) * E + e] : 0.f;
+    __syncthreads();
+    dora_ba_column(a, sA, sB, d);
+#pragma unroll
+    for (int c = 0; c < kDoraCo; ++c) {
+      float sq = 0.f;
+      if (co0 + c < co_end && e < E) {
+        const float v = w[c] + a.scaling * d[c];
+        sq = v * v;
+      }
+      sq = warp_sum(sq);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&sN[c], sq);
     }
-    sq = warp_sum(sq);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&sN[c], sq);
+    __syncthreads();
+    if (threadIdx.x < kDoraCo && co0 + threadIdx.x < co_end) atomicAdd(n2 + co0 + threadIdx.x, sN[threadIdx.x]);
   }
-  __syncthreads();
-  if (threadIdx.x < kDoraCo && co0 + threadIdx.x < a.Cout) atomicAdd(n2 + co0 + threadIdx.x, sN[threadIdx.x]);
 }
 
 // packed[t][co][ci] = bf16(s[co] * (W + scaling*BA)[co, ci, t]);  s_out[co] = s[co]
 __global__ void __launch_bounds__(kDoraE) dora_merge_kernel(const DoraArgs a, const float* __restrict__ n2,
                                                             __nv_bfloat16* __restrict__ packed, long long tap_stride,
-                                                            float* __restrict__ s_out) {
+                                                            float* __restrict__ s_out, int co_per_cta) {
   extern __shared__ float sm[];
   float* sA = sm;
-  float* sB = sA + a.r * kDoraE;
+  float* sB = sA + a.r * kDoraEP;
   const int E = a.Cin * a.k;
-  const int e0 = blockIdx.x * kDoraE, co0 = blockIdx.y * kDoraCo;
-  dora_load_tiles(a, e0, co0, sA, sB);
+  const int e0 = blockIdx.x * kDoraE;
+  const int co_begin = blockIdx.y * co_per_cta, co_end = min(co_begin + co_per_cta, a.Cout);
   const int e = e0 + threadIdx.x;
   const int ci = e / a.k, t = e - ci * a.k;
-  for (int c = 0; c < kDoraCo; ++c) {
-    const int co = co0 + c;
-    if (co >= a.Cout) break;
-    const float s = a.mag ? a.mag[co] * rsqrtf(n2[co]) : 1.0f;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && s_out) s_out[co] = s;
-    if (e < E) {
-      float d = 0.f;
-      for (int r = 0; r < a.r; ++r) d += sB[c * a.r + r] * sA[r * kDoraE + threadIdx.x];
-      const float v = a.W[(long long)co * E + e] + a.scaling * d;
-      packed[(long long)t * tap_stride + (long long)co * a.Cin_pad + ci] = __float2bfloat16_rn(s * v);
+  dora_load_a_tile(a, e0, sA);
+  for (int co0 = co_begin; co0 < co_end; co0 += kDoraCo) {
+    __syncthreads();
+    dora_load_b_tile(a, co0, co_end, sB);
+    float d[kDoraCo], w[kDoraCo];
+#pragma unroll
+    for (int c = 0; c < kDoraCo; ++c) w[c] = (co0 + c < co_end && e < E) ? a.W[(long long)(co0 + c) * E + e] : 0.f;
+    __syncthreads();
+    dora_ba_column(a, sA, sB, d);
+#pragma unroll
+    for (int c = 0; c < kDoraCo; ++c) {
+      const int co = co0 + c;
+      if (co < co_end) {
+        const float s = a.mag ? a.mag[co] * rsqrtf(n2[co]) : 1.0f;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && s_out) s_out[co] = s;
+        if (e < E) {
+          const float v = w[c] + a.scaling * d[c];
+          packed[(long long)t * tap_stride + (long long)co * a.Cin_pad + ci] = __float2bfloat16_rn(s * v);
+        }
+      }
     }
   }
 }
@@ -90,64 +143,125 @@ __global__ void __launch_bounds__(kDoraE) dora_merge_kernel(const DoraArgs a, co
 //   dB[co, r] += scaling * s[co] * sum_e dWp[co,e] * A[r,e]
 //   dA[r, e]  += scaling * sum_co B[co,r] * s[co] * dWp[co,e]
 //   dmag[co]  += sum_e dWp[co,e] * (W + scaling*BA)[co,e] / n[co]          (n = ||W + scaling*BA||, detached)
+// CTA = one 256-column e-tile x a RANGE of output channels (co_per_cta, walked 16 at a time): the dA partial of the whole range
+// stays in registers (r <= 32: 32 accumulators per thread) and is added to global memory once per CTA -- the first version issued
+// r*256 global atomics per 16-channel tile, ~2 atomics per weight element, and was bound by L2 atomic throughput.
 __global__ void __launch_bounds__(kDoraE) dora_grad_kernel(const DoraArgs a, const float* __restrict__ n2,
                                                            const float* __restrict__ dWp, long long tap_stride,
                                                            float* __restrict__ dA, float* __restrict__ dB,
-                                                           float* __restrict__ dmag) {
+                                                           float* __restrict__ dmag, int co_per_cta) {
   extern __shared__ float sm[];
-  float* sA = sm;                           // [r][kDoraE]
-  float* sB = sA + a.r * kDoraE;            // [kDoraCo][r]
-  float* sG = sB + kDoraCo * a.r;           // [kDoraCo][kDoraE]  G = scaling * s * dWp
-  float* sM = sG + kDoraCo * kDoraE;        // [kDoraCo]
+  float* sA = sm;                           // [r][kDoraEP]
+  float* sB = sA + a.r * kDoraEP;           // [kDoraCo][r]
+  float* sG = sB + kDoraCo * a.r;           // [kDoraCo][kDoraEP]  G = scaling * s * dWp
+  float* sM = sG + kDoraCo * kDoraEP;       // [kDoraCo]
   const int E = a.Cin * a.k;
-  const int e0 = blockIdx.x * kDoraE, co0 = blockIdx.y * kDoraCo;
-  if (threadIdx.x < kDoraCo) sM[threadIdx.x] = 0.f;
-  dora_load_tiles(a, e0, co0, sA, sB);
+  const int e0 = blockIdx.x * kDoraE;
+  const int co_begin = blockIdx.y * co_per_cta, co_end = min(co_begin + co_per_cta, a.Cout);
   const int e = e0 + threadIdx.x;
   const int ci = e / a.k, t = e - ci * a.k;
-  for (int c = 0; c < kDoraCo; ++c) {
-    const int co = co0 + c;
-    float g = 0.f, gv = 0.f, s = 1.f;
-    if (co < a.Cout && e < E) {
-      g = dWp[(long long)t * tap_stride + (long long)co * a.Cin_pad + ci];
-      if (a.mag) {
+  for (int i = threadIdx.x; i < a.r * kDoraE; i += blockDim.x) {
+    const int r = i / kDoraE, ee = e0 + (i - r * kDoraE);
+    sA[r * kDoraEP + (i - r * kDoraE)] = ee < E ? a.A[(long long)r * E + ee] : 0.f;
+  }
+  float dAacc[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) dAacc[r] = 0.f;
+  const bool fast_r = (a.r <= 32) && ((a.r & 3) == 0);
+  for (int co0 = co_begin; co0 < co_end; co0 += kDoraCo) {
+    __syncthreads();                        // previous tile's readers of sB / sG / sM are done (also orders the sA fill)
+    for (int i = threadIdx.x; i < kDoraCo * a.r; i += blockDim.x) {
+      const int c = i / a.r, co = co0 + c;
+      sB[i] = co < co_end ? a.B[(long long)co * a.r + (i - c * a.r)] : 0.f;
+    }
+    if (threadIdx.x < kDoraCo) sM[threadIdx.x] = 0.f;
+    float g[kDoraCo], w[kDoraCo], d[kDoraCo];
+#pragma unroll
+    for (int c = 0; c < kDoraCo; ++c) {
+      const bool ok = co0 + c < co_end && e < E;
+      g[c] = ok ? dWp[(long long)t * tap_stride + (long long)(co0 + c) * a.Cin_pad + ci] : 0.f;
+      w[c] = (ok && a.mag) ? a.W[(long long)(co0 + c) * E + e] : 0.f;
+    }
+    __syncthreads();
+    if (a.mag) dora_ba_column(a, sA, sB, d);
+#pragma unroll
+    for (int c = 0; c < kDoraCo; ++c) {
+      const int co = co0 + c;
+      float gv = 0.f, s = 1.f;
+      if (co < co_end && a.mag) {
         const float inv_n = rsqrtf(n2[co]);
         s = a.mag[co] * inv_n;
-        float d = 0.f;
-        for (int r = 0; r < a.r; ++r) d += sB[c * a.r + r] * sA[r * kDoraE + threadIdx.x];
-        gv = g * (a.W[(long long)co * E + e] + a.scaling * d) * inv_n;
+        gv = g[c] * (w[c] + a.scaling * d[c]) * inv_n;
+      }
+      g[c] *= a.scaling * s;                       // G = scaling * s * dWp
+      sG[c * kDoraEP + threadIdx.x] = g[c];
+      if (a.mag) {
+        gv = warp_sum(gv);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sM[c], gv);
       }
     }
-    sG[c * kDoraE + threadIdx.x] = a.scaling * s * g;
-    if (a.mag) {
-      gv = warp_sum(gv);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&sM[c], gv);
-    }
-  }
-  __syncthreads();
-  // dA: thread e, loop r, sum over the CTA's output channels
-  if (e < E) {
-    for (int r = 0; r < a.r; ++r) {
-      float acc = 0.f;
+    // dA partial: thread e keeps its G column in registers, B read as broadcast float4 along r
+    if (fast_r) {
 #pragma unroll
-      for (int c = 0; c < kDoraCo; ++c) acc += sB[c * a.r + r] * sG[c * kDoraE + threadIdx.x];
-      atomicAdd(dA + (long long)r * E + e, acc);
+      for (int r4 = 0; r4 < 8; ++r4) {
+        if (r4 * 4 < a.r) {
+#pragma unroll
+          for (int c = 0; c < kDoraCo; ++c) {
+            const float4 b = *reinterpret_cast<const float4*>(sB + c * a.r + r4 * 4);
+            dAacc[r4 * 4] = fmaf(b.x, g[c], dAacc[r4 * 4]); dAacc[r4 * 4 + 1] = fmaf(b.y, g[c], dAacc[r4 * 4 + 1]);
+            dAacc[r4 * 4 + 2] = fmaf(b.z, g[c], dAacc[r4 * 4 + 2]); dAacc[r4 * 4 + 3] = fmaf(b.w, g[c], dAacc[r4 * 4 + 3]);
+          }
+        }
+      }
+    } else if (e < E) {                       // general rank: per-tile atomics
+      for (int r = 0; r < a.r; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < kDoraCo; ++c) acc = fmaf(sB[c * a.r + r], g[c], acc);
+        atomicAdd(dA + (long long)r * E + e, acc);
+      }
     }
+    __syncthreads();
+    // dB: kDoraCo x r outputs, each a dot product over the CTA's 256 e-columns.  thread = (channel pair cp, rank rr): a warp
+    // shares its G rows (broadcast reads) and its lanes read 32 different A rows -- conflict-free thanks to the padded stride.
+    for (int o = threadIdx.x; o < (kDoraCo / 2) * a.r; o += blockDim.x) {
+      const int cp = o / a.r, rr = o - cp * a.r;
+      float acc0 = 0.f, acc1 = 0.f;
+      const float4* g0 = reinterpret_cast<const float4*>(sG + cp * kDoraEP);
+      const float4* g1 = reinterpret_cast<const float4*>(sG + (cp + kDoraCo / 2) * kDoraEP);
+      const float4* ap = reinterpret_cast<const float4*>(sA + rr * kDoraEP);
+#pragma unroll 8
+      for (int j = 0; j < kDoraE / 4; ++j) {
+        const float4 y = ap[j], x0 = g0[j], x1 = g1[j];
+        acc0 = fmaf(x0.x, y.x, fmaf(x0.y, y.y, fmaf(x0.z, y.z, fmaf(x0.w, y.w, acc0))));
+        acc1 = fmaf(x1.x, y.x, fmaf(x1.y, y.y, fmaf(x1.z, y.z, fmaf(x1.w, y.w, acc1))));
+      }
+      if (co0 + cp < co_end) atomicAdd(dB + (long long)(co0 + cp) * a.r + rr, acc0);
+      if (co0 + cp + kDoraCo / 2 < co_end) atomicAdd(dB + (long long)(co0 + cp + kDoraCo / 2) * a.r + rr, acc1);
+    }
+    if (a.mag && threadIdx.x < kDoraCo && co0 + threadIdx.x < co_end) atomicAdd(dmag + co0 + threadIdx.x, sM[threadIdx.x]);
   }
-  // dB: kDoraCo x r outputs, each a dot product over the CTA's e-columns
-  for (int o = threadIdx.x; o < kDoraCo * a.r; o += blockDim.x) {
-    const int c = o / a.r, r = o - c * a.r;
-    if (co0 + c >= a.Cout) continue;
-    float acc = 0.f;
-    for (int j = 0; j < kDoraE; ++j) acc += sG[c * kDoraE + j] * sA[r * kDoraE + j];
-    atomicAdd(dB + (long long)(co0 + c) * a.r + r, acc);
+  if (fast_r && e < E) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+      if (r < a.r) atomicAdd(dA + (long long)r * E + e, dAacc[r]);
   }
-  if (a.mag && threadIdx.x < kDoraCo && co0 + threadIdx.x < a.Cout) atomicAdd(dmag + co0 + threadIdx.x, sM[threadIdx.x]);
+}
+
+// output-channel range per CTA: enough CTAs for ~2 per SM, each walking its range 16 channels at a time
+static dim3 dora_grid(int E, int Cout, int* co_per_cta) {
+  const int etiles = (E + kDoraE - 1) / kDoraE;
+  int ychunks = (2 * device_sm_count() + etiles - 1) / etiles;
+  const int max_chunks = (Cout + kDoraCo - 1) / kDoraCo;
+  if (ychunks > max_chunks) ychunks = max_chunks;
+  if (ychunks < 1) ychunks = 1;
+  *co_per_cta = ((Cout + ychunks - 1) / ychunks + kDoraCo - 1) / kDoraCo * kDoraCo;
+  return dim3(etiles, (Cout + *co_per_cta - 1) / *co_per_cta);
 }
 
 static int dora_check(const float* W, const float* A, const float* B, int Cout, int Cin, int k, int r, const char* who) {
   OF_REQUIRE(W && A && B, "%s: null pointer", who);
-  OF_REQUIRE(Cout >= 1 && Cin >= 1 && k >= 1 && r >= 1 && r <= 128, "%s: bad sizes (r=%d)", who, r);
+  OF_REQUIRE(Cout >= 1 && Cin >= 1 && k >= 1 && r >= 1 && r <= kDoraRMax, "%s: bad sizes (r=%d)", who, r);
   return OF_OK;
 }
 
@@ -164,8 +278,9 @@ extern "C" int of_dora_merge(const float* W, const float* A, const float* B, con
   OF_REQUIRE(packed_bf16 && n2_ws && Cin_pad >= Cin, "of_dora_merge: bad outputs");
   DoraArgs a{W, A, B, mag, scaling, Cout, Cin, k, r, Cin_pad};
   const int E = Cin * k;
-  dim3 grid((E + kDoraE - 1) / kDoraE, (Cout + kDoraCo - 1) / kDoraCo);
-  size_t smem = ((size_t)r * kDoraE + (size_t)kDoraCo * r + kDoraCo) * sizeof(float);
+  int co_per_cta;
+  dim3 grid = dora_grid(E, Cout, &co_per_cta);
+  size_t smem = ((size_t)r * kDoraEP + (size_t)kDoraCo * r + kDoraCo) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     OF_CHECK_CUDA(cudaFuncSetAttribute(dora_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -175,11 +290,11 @@ extern "C" int of_dora_merge(const float* W, const float* A, const float* B, con
   }
   if (mag) {
     OF_CHECK_CUDA(cudaMemsetAsync(n2_ws, 0, (size_t)Cout * sizeof(float), stream));
-    dora_norm_kernel<<<grid, kDoraE, smem, stream>>>(a, n2_ws);
+    dora_norm_kernel<<<grid, kDoraE, smem, stream>>>(a, n2_ws, co_per_cta);
     OF_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
-  dora_merge_kernel<<<grid, kDoraE, smem, stream>>>(a, n2_ws, reinterpret_cast<__nv_bfloat16*>(packed_bf16), tap_stride, s_out);
+  dora_merge_kernel<<<grid, kDoraE, smem, stream>>>(a, n2_ws, reinterpret_cast<__nv_bfloat16*>(packed_bf16), tap_stride, s_out, co_per_cta);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;
@@ -194,9 +309,10 @@ extern "C" int of_dora_grad(const float* W, const float* A, const float* B, cons
   OF_REQUIRE(dW_packed && dA && dB && (!mag || (dmag && n2)), "of_dora_grad: null pointer");
   DoraArgs a{W, A, B, mag, scaling, Cout, Cin, k, r, Cin_pad};
   const int E = Cin * k;
-  dim3 grid((E + kDoraE - 1) / kDoraE, (Cout + kDoraCo - 1) / kDoraCo);
-  size_t smem = ((size_t)r * kDoraE + (size_t)kDoraCo * r + (size_t)kDoraCo * kDoraE + kDoraCo) * sizeof(float);
-  dora_grad_kernel<<<grid, kDoraE, smem, stream>>>(a, n2, dW_packed, tap_stride, dA, dB, dmag);
+  int co_per_cta;
+  dim3 grid = dora_grid(E, Cout, &co_per_cta);
+  size_t smem = ((size_t)r * kDoraEP + (size_t)kDoraCo * r + (size_t)kDoraCo * kDoraEP + kDoraCo) * sizeof(float);
+  dora_grad_kernel<<<grid, kDoraE, smem, stream>>>(a, n2, dW_packed, tap_stride, dA, dB, dmag, co_per_cta);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;
