@@ -55,15 +55,31 @@ __device__ __forceinline__ void dora_ba_column(const DoraArgs& a, const float* s
 
 __device__ __forceinline__ void dora_load_a_tile(const DoraArgs& a, int e0, float* sA) {
   const int E = a.Cin * a.k;
-  for (int i = threadIdx.x; i < a.r * kDoraE; i += blockDim.x) {
-    const int r = i / kDoraE, e = e0 + (i - r * kDoraE);
-    sA[r * kDoraEP + (i - r * kDoraE)] = e < E ? a.A[(long long)r * E + e] : 0.f;
+  const int e = e0 + threadIdx.x;            // blockDim.x == kDoraE: thread = column, loop = rank (16 loads in flight)
+  for (int r0 = 0; r0 < a.r; r0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (r0 + j < a.r && e < E) ? a.A[(long long)(r0 + j) * E + e] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (r0 + j < a.r) sA[(r0 + j) * kDoraEP + threadIdx.x] = v[j];
   }
 }
-__device__ __forceinline__ void dora_load_b_tile(const DoraArgs& a, int co0, int co_end, float* sB) {
-  for (int i = threadIdx.x; i < kDoraCo * a.r; i += blockDim.x) {
-    const int c = i / a.r, co = co0 + c;
-    sB[i] = co < co_end ? a.B[(long long)co * a.r + (i - c * a.r)] : 0.f;
+// B rows of the CTA's whole channel range [co_begin, co_begin + rows_pad) -> sB[rows_pad][r] (rows >= co_end are zero): loaded
+// once, so the tile loop needs no barrier and no global-load latency for B.
+__device__ __forceinline__ void dora_load_b_range(const DoraArgs& a, int co_begin, int co_end, int rows_pad, float* sB) {
+  const int n = rows_pad * a.r;
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * blockDim.x;
+      const int c = i / a.r;
+      v[j] = (i < n && co_begin + c < co_end) ? a.B[(long long)(co_begin + c) * a.r + (i - c * a.r)] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i0 + j * blockDim.x < n) sB[i0 + j * blockDim.x] = v[j];
   }
 }
 
@@ -72,22 +88,27 @@ __device__ __forceinline__ void dora_load_b_tile(const DoraArgs& a, int co0, int
 __global__ void __launch_bounds__(kDoraE) dora_norm_kernel(const DoraArgs a, float* __restrict__ n2, int co_per_cta) {
   extern __shared__ float sm[];
   float* sA = sm;
-  float* sB = sA + a.r * kDoraEP;
-  float* sN = sB + kDoraCo * a.r;
+  float* sBall = sA + a.r * kDoraEP;              // [co_per_cta][r]
+  float* sN = sBall + co_per_cta * a.r;           // [co_per_cta]
   const int E = a.Cin * a.k;
   const int e0 = blockIdx.x * kDoraE;
   const int co_begin = blockIdx.y * co_per_cta, co_end = min(co_begin + co_per_cta, a.Cout);
   const int e = e0 + threadIdx.x;
   dora_load_a_tile(a, e0, sA);
-  for (int co0 = co_begin; co0 < co_end; co0 += kDoraCo) {
-    __syncthreads();
-    dora_load_b_tile(a, co0, co_end, sB);
-    if (threadIdx.x < kDoraCo) sN[threadIdx.x] = 0.f;
-    float d[kDoraCo], w[kDoraCo];
+  dora_load_b_range(a, co_begin, co_end, co_per_cta, sBall);
+  for (int i = threadIdx.x; i < co_per_cta; i += blockDim.x) sN[i] = 0.f;
+  float w[kDoraCo], wn[kDoraCo];
 #pragma unroll
-    for (int c = 0; c < kDoraCo; ++c) w[c] = (co0 + c < co_end && e < E) ? a.W[(long long)(co0 + c) * E + e] : 0.f;
-    __syncthreads();
-    dora_ba_column(a, sA, sB, d);
+  for (int c = 0; c < kDoraCo; ++c) wn[c] = (co_begin + c < co_end && e < E) ? a.W[(long long)(co_begin + c) * E + e] : 0.f;
+  __syncthreads();
+  for (int co0 = co_begin; co0 < co_end; co0 += kDoraCo) {
+    float d[kDoraCo];
+#pragma unroll
+    for (int c = 0; c < kDoraCo; ++c) {
+      w[c] = wn[c];                            // the next tile's rows are fetched while this tile is computed
+      wn[c] = (co0 + kDoraCo + c < co_end && e < E) ? a.W[(long long)(co0 + kDoraCo + c) * E + e] : 0.f;
+    }
+    dora_ba_column(a, sA, sBall + (co0 - co_begin) * a.r, d);
 #pragma unroll
     for (int c = 0; c < kDoraCo; ++c) {
       float sq = 0.f;
@@ -96,11 +117,11 @@ __global__ void __launch_bounds__(kDoraE) dora_norm_kernel(const DoraArgs a, flo
         sq = v * v;
       }
       sq = warp_sum(sq);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&sN[c], sq);
+      if ((threadIdx.x & 31) == 0 && co0 + c < co_end) atomicAdd(&sN[co0 - co_begin + c], sq);
     }
-    __syncthreads();
-    if (threadIdx.x < kDoraCo && co0 + threadIdx.x < co_end) atomicAdd(n2 + co0 + threadIdx.x, sN[threadIdx.x]);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < co_end - co_begin; i += blockDim.x) atomicAdd(n2 + co_begin + i, sN[i]);
 }
 
 // packed[t][co][ci] = bf16(s[co] * (W + scaling*BA)[co, ci, t]);  s_out[co] = s[co]
@@ -116,14 +137,19 @@ __global__ void __launch_bounds__(kDoraE) dora_merge_kernel(const DoraArgs a, co
   const int e = e0 + threadIdx.x;
   const int ci = e / a.k, t = e - ci * a.k;
   dora_load_a_tile(a, e0, sA);
-  for (int co0 = co_begin; co0 < co_end; co0 += kDoraCo) {
-    __syncthreads();
-    dora_load_b_tile(a, co0, co_end, sB);
-    float d[kDoraCo], w[kDoraCo];
+  dora_load_b_range(a, co_begin, co_end, co_per_cta, sB);
+  float w[kDoraCo], wn[kDoraCo];
 #pragma unroll
-    for (int c = 0; c < kDoraCo; ++c) w[c] = (co0 + c < co_end && e < E) ? a.W[(long long)(co0 + c) * E + e] : 0.f;
-    __syncthreads();
-    dora_ba_column(a, sA, sB, d);
+  for (int c = 0; c < kDoraCo; ++c) wn[c] = (co_begin + c < co_end && e < E) ? a.W[(long long)(co_begin + c) * E + e] : 0.f;
+  __syncthreads();
+  for (int co0 = co_begin; co0 < co_end; co0 += kDoraCo) {
+    float d[kDoraCo];
+#pragma unroll
+    for (int c = 0; c < kDoraCo; ++c) {
+      w[c] = wn[c];
+      wn[c] = (co0 + kDoraCo + c < co_end && e < E) ? a.W[(long long)(co0 + kDoraCo + c) * E + e] : 0.f;
+    }
+    dora_ba_column(a, sA, sB + (co0 - co_begin) * a.r, d);
 #pragma unroll
     for (int c = 0; c < kDoraCo; ++c) {
       const int co = co0 + c;
@@ -152,28 +178,23 @@ __global__ void __launch_bounds__(kDoraE) dora_grad_kernel(const DoraArgs a, con
                                                            float* __restrict__ dmag, int co_per_cta) {
   extern __shared__ float sm[];
   float* sA = sm;                           // [r][kDoraEP]
-  float* sB = sA + a.r * kDoraEP;           // [kDoraCo][r]
-  float* sG = sB + kDoraCo * a.r;           // [kDoraCo][kDoraEP]  G = scaling * s * dWp
+  float* sBall = sA + a.r * kDoraEP;        // [co_per_cta][r]
+  float* sG = sBall + co_per_cta * a.r;     // [kDoraCo][kDoraEP]  G = scaling * s * dWp
   float* sM = sG + kDoraCo * kDoraEP;       // [kDoraCo]
   const int E = a.Cin * a.k;
   const int e0 = blockIdx.x * kDoraE;
   const int co_begin = blockIdx.y * co_per_cta, co_end = min(co_begin + co_per_cta, a.Cout);
   const int e = e0 + threadIdx.x;
   const int ci = e / a.k, t = e - ci * a.k;
-  for (int i = threadIdx.x; i < a.r * kDoraE; i += blockDim.x) {
-    const int r = i / kDoraE, ee = e0 + (i - r * kDoraE);
-    sA[r * kDoraEP + (i - r * kDoraE)] = ee < E ? a.A[(long long)r * E + ee] : 0.f;
-  }
+  dora_load_a_tile(a, e0, sA);
+  dora_load_b_range(a, co_begin, co_end, co_per_cta, sBall);
   float dAacc[32];
 #pragma unroll
   for (int r = 0; r < 32; ++r) dAacc[r] = 0.f;
   const bool fast_r = (a.r <= 32) && ((a.r & 3) == 0);
   for (int co0 = co_begin; co0 < co_end; co0 += kDoraCo) {
-    __syncthreads();                        // previous tile's readers of sB / sG / sM are done (also orders the sA fill)
-    for (int i = threadIdx.x; i < kDoraCo * a.r; i += blockDim.x) {
-      const int c = i / a.r, co = co0 + c;
-      sB[i] = co < co_end ? a.B[(long long)co * a.r + (i - c * a.r)] : 0.f;
-    }
+    __syncthreads();                        // previous tile's readers of sG / sM are done (also orders the sA / sBall fill)
+    const float* sB = sBall + (co0 - co_begin) * a.r;
     if (threadIdx.x < kDoraCo) sM[threadIdx.x] = 0.f;
     float g[kDoraCo], w[kDoraCo], d[kDoraCo];
 #pragma unroll
@@ -248,14 +269,16 @@ __global__ void __launch_bounds__(kDoraE) dora_grad_kernel(const DoraArgs a, con
   }
 }
 
-// output-channel range per CTA: enough CTAs for ~2 per SM, each walking its range 16 channels at a time
+// output-channel range per CTA: at most ONE wave of CTAs (register use allows one CTA per SM; a CTA pays a fixed ~2 us for its A
+// tile), each walking its range 16 channels at a time
 static dim3 dora_grid(int E, int Cout, int* co_per_cta) {
   const int etiles = (E + kDoraE - 1) / kDoraE;
-  int ychunks = (2 * device_sm_count() + etiles - 1) / etiles;
+  int ychunks = device_sm_count() / etiles;
   const int max_chunks = (Cout + kDoraCo - 1) / kDoraCo;
   if (ychunks > max_chunks) ychunks = max_chunks;
   if (ychunks < 1) ychunks = 1;
   *co_per_cta = ((Cout + ychunks - 1) / ychunks + kDoraCo - 1) / kDoraCo * kDoraCo;
+  if (*co_per_cta > 512) *co_per_cta = 512;      // the range's B rows live in shared memory
   return dim3(etiles, (Cout + *co_per_cta - 1) / *co_per_cta);
 }
 
@@ -280,12 +303,12 @@ extern "C" int of_dora_merge(const float* W, const float* A, const float* B, con
   const int E = Cin * k;
   int co_per_cta;
   dim3 grid = dora_grid(E, Cout, &co_per_cta);
-  size_t smem = ((size_t)r * kDoraEP + (size_t)kDoraCo * r + kDoraCo) * sizeof(float);
+  size_t smem = ((size_t)r * kDoraEP + (size_t)co_per_cta * r + co_per_cta) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    OF_CHECK_CUDA(cudaFuncSetAttribute(dora_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    OF_CHECK_CUDA(cudaFuncSetAttribute(dora_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    OF_CHECK_CUDA(cudaFuncSetAttribute(dora_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    OF_CHECK_CUDA(cudaFuncSetAttribute(dora_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    OF_CHECK_CUDA(cudaFuncSetAttribute(dora_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    OF_CHECK_CUDA(cudaFuncSetAttribute(dora_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
   if (mag) {
@@ -311,7 +334,7 @@ extern "C" int of_dora_grad(const float* W, const float* A, const float* B, cons
   const int E = Cin * k;
   int co_per_cta;
   dim3 grid = dora_grid(E, Cout, &co_per_cta);
-  size_t smem = ((size_t)r * kDoraEP + (size_t)kDoraCo * r + (size_t)kDoraCo * kDoraEP + kDoraCo) * sizeof(float);
+  size_t smem = ((size_t)r * kDoraEP + (size_t)co_per_cta * r + (size_t)kDoraCo * kDoraEP + kDoraCo) * sizeof(float);
   dora_grad_kernel<<<grid, kDoraE, smem, stream>>>(a, n2, dW_packed, tap_stride, dA, dB, dmag, co_per_cta);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
