@@ -42,6 +42,27 @@ __device__ __forceinline__ void red_add4(float* ptr, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// A thread holds one ROW (32 fp32 columns) of a 32x32 accumulator block; adding it to global memory directly makes every
+// red.v4 warp instruction touch 32 different 128-byte lines (measured: ~2.8 clk per line on the LSU -- this alone bounded the kernel
+// at ~5.7k clk per Q tile).  Staged through a swizzled 4 KB shared tile, one instruction covers 4 full lines.
+__device__ __forceinline__ void red_tile_32x32(uint8_t* stg, int lane, const uint32_t (&v)[32], float* base, long long ld,
+                                               int row0, int row_lim, int col_lim) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  __syncwarp();
+  const int rr = lane >> 3, gg = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rr;
+    if (row0 + r < row_lim && gg * 4 < col_lim) {
+      const float4 t = *reinterpret_cast<const float4*>(stg + r * 128 + ((gg ^ (r & 7)) << 4));
+      red_add4(base + (long long)(row0 + r) * ld + gg * 4, t.x, t.y, t.z, t.w);
+    }
+  }
+  __syncwarp();
+}
+
 // Software pipeline (per Q tile i; tensor core and softmax threads overlap):
 //   MMA   : dV+=P(i)^T dO | S(i+1)=Q K^T | dK+=dS(i)^T Q, dQ(i)=dS K | dP(i+1)=dO V^T
 //   threads: A(i): S -> P (regs + smem) | C(i-1): dQ(i-1) -> global atomics | B(i): dP -> dS (smem)
@@ -56,7 +77,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sQdO = sV + kTile;      // 2 stages x (Q 16 KB + dO 16 KB)
   uint8_t* sP = sQdO + 4 * kTile;  // 32 KB
   uint8_t* sdS = sP + 2 * kTile;   // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * kTile);
+  uint8_t* sStage = sdS + 2 * kTile;   // 8 softmax warps x 4 KB: coalescing buffer of the fp32 red.add tiles (dQ, dK, dV)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;    // [2]
   uint64_t* qdo_empty = bars + 3;   // [2]
@@ -218,6 +240,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const long long bh = (long long)b * p.H + h;
     const int key_base = k0 + half * 64;
+    uint8_t* stg = sStage + (warp - 2) * 4096;
 
     auto flush_dq = [&](int i) {   // stage C: dQ(i) tile -> global fp32 atomics
       mbar_wait(dq_full, i & 1);
@@ -228,15 +251,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
-      const int qrow = i * 128 + row;
-      if (qrow < p.L) {
-        float* dst = p.dq + (long long)b * p.dq_bs + (long long)qrow * p.dq_ld + (long long)h * p.D + half * 32;
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          if (half * 32 + g * 4 < p.D)
-            red_add4(dst + g * 4, __uint_as_float(dq[g * 4]), __uint_as_float(dq[g * 4 + 1]), __uint_as_float(dq[g * 4 + 2]),
-                     __uint_as_float(dq[g * 4 + 3]));
-      }
+      // rows i*128 + qd*32 .. +31 of dQ, columns half*32 .. +31 of head h
+      red_tile_32x32(stg, lane, dq, p.dq + (long long)b * p.dq_bs + (long long)h * p.D + half * 32, p.dq_ld, i * 128 + qd * 32, p.L,
+                     p.D - half * 32);
     };
 
     for (int i = 0; i < n; ++i) {
@@ -325,20 +342,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ---- dK / dV tiles -> global (fp32 atomics; summed over q heads); this warp owns d-columns [half*32, half*32+32)
     mbar_wait(acc_done, 0);
     tc_fence_after();
-    const int key = k0 + row;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       uint32_t a[32];
       tmem_ld_32x32b_x32((which == 0 ? tdV : tdK) + lane_off + half * 32, a);
       tmem_wait_ld();
-      if (key < p.L) {
-        float* dst = (which == 0 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)key * p.dkv_ld + (long long)kvh * p.D + half * 32;
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          if (half * 32 + g * 4 < p.D)
-            red_add4(dst + g * 4, __uint_as_float(a[g * 4]), __uint_as_float(a[g * 4 + 1]), __uint_as_float(a[g * 4 + 2]),
-                     __uint_as_float(a[g * 4 + 3]));
-      }
+      red_tile_32x32(stg, lane, a, (which == 0 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)kvh * p.D + half * 32, p.dkv_ld,
+                     k0 + qd * 32, p.L, p.D - half * 32);
     }
   }
 
@@ -410,7 +420,7 @@ extern "C" int of_attn_bwd(const of_attn_args* a, void* stream_) {
   p.delta = a->delta;
   p.dq = a->dq; p.dq_ld = a->dq_ld; p.dq_bs = a->dq_batch_stride;
   p.dk = a->dk; p.dv = a->dv; p.dkv_ld = a->dkv_ld; p.dkv_bs = a->dkv_batch_stride;
-  size_t smem_bytes = 1024 + kTile * 10 + 256;
+  size_t smem_bytes = 1024 + kTile * 10 + 8 * 4096 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     OF_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

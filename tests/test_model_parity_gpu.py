@@ -227,3 +227,30 @@ def test_sampler_update_kernel_matches_schedules():
     N.call("of_sampler_update", x.data_ptr(), cond.data_ptr(), None, 8, Lp * 8, 1.0, 1, dt, 1.0, 0.0, 0.0, B, 6, n, out.data_ptr(), None,
            Lp, 8, -1.0)
     assert nrel(out, x + c_ref * torch.tensor(dt)) < 2e-3
+
+
+def test_gradient_accumulation_without_zero_grad():
+    """`p.grad` aliases the engine's gradient arena after a backward pass; a second backward WITHOUT zero_grad must still
+    accumulate (torch semantics: p.grad = g1 + g2), and zero_grad(set_to_none=True) must give back a single gradient."""
+    from oracle.synth import TINY, synth_inputs
+    _, new = build_pair(TINY, "default")
+    x, a, c, t, noise, keep = (v.to(dev) for v in synth_inputs(2, 96, 11))
+
+    def bwd():
+        y = new(x, a, t, c, cond_mask=keep)
+        torch.nn.functional.mse_loss(y, noise).backward()
+
+    new.zero_grad(set_to_none=True)
+    bwd()
+    g1 = {k: p.grad.detach().clone() for k, p in new.named_parameters()}
+    live = [k for k in g1 if not k.endswith("se.to_k.bias") and g1[k].abs().max() > 1e-9]   # to_k.bias: true gradient is zero
+    assert len(live) > 300
+    bwd()                                   # no zero_grad: accumulate
+    for k, p in new.named_parameters():
+        if k in live:
+            assert nrel(p.grad, 2 * g1[k]) < 3e-2, k
+    new.zero_grad(set_to_none=True)
+    bwd()
+    for k, p in new.named_parameters():
+        if k in live:
+            assert nrel(p.grad, g1[k]) < 3e-2, k
