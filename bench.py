@@ -41,6 +41,19 @@ def peaks():
     return 1400.0, 6650.0, "fallback"
 
 
+def gemm_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step's most frequent GEMM shape, from the committed
+    `ncu --set full` capture (profiles/r01_gemm_ncu_full.json); None when the capture is absent."""
+    p = ROOT / "profiles" / "r01_gemm_ncu_full.json"
+    if not p.exists():
+        return None, None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    d = json.loads(p.read_text())["launches"][0]
+    t = d["dram_read"] * mult.get(d["dram_read_unit"], 1.0) + d["dram_write"] * mult.get(d["dram_write_unit"], 1.0)
+    return t, (f"bytes per launch of {d['shape']} ({d['duration_us']:.1f} us under ncu); algorithmic 35.1 MB = 16.8 MB activations + "
+               "1.5 MB weights read, 16.8 MB written (the write stays in the 126 MB L2 during the capture)")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -234,8 +247,10 @@ def run_ours(args) -> None:
         top = max(agg.items(), key=lambda kv: kv[1][0])
         name, (tms, fl, cnt) = top
         ach = fl / (tms * 1e-3) / 1e12
+        traffic, traffic_note = gemm_traffic()
         roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": None, "launches": cnt, "ms_per_step": tms, "peak_source": how + " (bf16_tflops_sustained)",
+                "traffic": traffic, "traffic_note": traffic_note, "launches": cnt, "ms_per_step": tms,
+                "peak_source": how + " (bf16_tflops_sustained)",
                 "families_ms": {k: round(v[0], 3) for k, v in agg.items()},
                 "families_tflops": {k: round(v[1] / (v[0] * 1e-3) / 1e12, 1) for k, v in agg.items() if v[0] > 0}}
 
