@@ -33,6 +33,11 @@ struct AttnBwdParams {
   long long dkv_ld, dkv_bs;
 };
 
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 __device__ __forceinline__ float ex2b(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -45,19 +50,19 @@ __device__ __forceinline__ void red_add4(float* ptr, float a, float b, float c, 
 // A thread holds one ROW (32 fp32 columns) of a 32x32 accumulator block; adding it to global memory directly makes every
 // red.v4 warp instruction touch 32 different 128-byte lines (measured: ~2.8 clk per line on the LSU -- this alone bounded the kernel
 // at ~5.7k clk per Q tile).  Staged through a swizzled 4 KB shared tile, one instruction covers 4 full lines.
-__device__ __forceinline__ void red_tile_32x32(uint8_t* stg, int lane, const uint32_t (&v)[32], float* base, long long ld,
+__device__ __forceinline__ void red_tile_32x32(uint32_t stg, int lane, const uint32_t (&v)[32], float* base, long long ld,
                                                int row0, int row_lim, int col_lim) {
 #pragma unroll
   for (int g = 0; g < 8; ++g)
-    *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    sts128(stg + lane * 128 + ((g ^ (lane & 7)) << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
   __syncwarp();
   const int rr = lane >> 3, gg = lane & 7;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + rr;
     if (row0 + r < row_lim && gg * 4 < col_lim) {
-      const float4 t = *reinterpret_cast<const float4*>(stg + r * 128 + ((gg ^ (r & 7)) << 4));
-      red_add4(base + (long long)(row0 + r) * ld + gg * 4, t.x, t.y, t.z, t.w);
+      const uint4 t = lds128(stg + r * 128 + ((gg ^ (r & 7)) << 4));
+      red_add4(base + (long long)(row0 + r) * ld + gg * 4, __uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
     }
   }
   __syncwarp();
@@ -240,7 +245,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const long long bh = (long long)b * p.H + h;
     const int key_base = k0 + half * 64;
-    uint8_t* stg = sStage + (warp - 2) * 4096;
+    const uint32_t stg = smem_u32(sStage + (warp - 2) * 4096);
 
     auto flush_dq = [&](int i) {   // stage C: dQ(i) tile -> global fp32 atomics
       mbar_wait(dq_full, i & 1);
@@ -256,12 +261,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                      p.D - half * 32);
     };
 
+    // per-row softmax statistics are fetched ONE tile ahead: a global load issued at the top of the tile that needs it put a full
+    // L2/DRAM round trip on the critical path of every iteration (long-scoreboard was the top stall of the first capture)
+    float lse_next = row < p.L ? p.lse[bh * p.L + row] : 0.f;
+    float dlt_next = row < p.L ? p.delta[bh * p.L + row] : 0.f;
     for (int i = 0; i < n; ++i) {
       const int qrow = i * 128 + row;
       const bool q_ok = qrow < p.L;
       const bool tile_full = (i * 128 + 128 <= p.L) && (k0 + 128 <= p.L);
-      const float lse2 = q_ok ? p.lse[bh * p.L + qrow] : 0.f;
-      const float dlt = q_ok ? p.delta[bh * p.L + qrow] : 0.f;
+      const float lse2 = lse_next, dlt = dlt_next;
+      if (i + 1 < n) {
+        const int qn = qrow + 128;
+        lse_next = qn < p.L ? p.lse[bh * p.L + qn] : 0.f;
+        dlt_next = qn < p.L ? p.delta[bh * p.L + qn] : 0.f;
+      }
       // ---- stage A: P = exp2(S*scale*log2e - lse2)
       uint32_t pk[32];  // 64 probabilities, packed bf16x2
       {
@@ -296,10 +309,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       mbar_wait(p_empty, (i & 1) ^ 1);   // dV MMA of the previous tile has finished reading sP
       {
-        uint8_t* prow = sP + half * kTile + row * 128;
+        const uint32_t prow = smem_u32(sP + half * kTile + row * 128);
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc)
-          *reinterpret_cast<uint4*>(prow + ((pc ^ (row & 7)) << 4)) = make_uint4(pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+        for (int pc = 0; pc < 8; ++pc) sts128(prow + ((pc ^ (row & 7)) << 4), pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -319,20 +331,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dp_empty);
+        // dS = P o ((dP - delta) * scale): the difference is formed in fp32 (it cancels), rounded to bf16 pairs and multiplied by
+        // the bf16 P pair with one packed multiply -- 2 instructions per element instead of 4.5 (unpack, sub, 2 mul, pack).
+        const float nds = -dlt * p.scale;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          float2 pp = unpack_bf16x2(pk[e]);
-          float ds0 = pp.x * (__uint_as_float(dp[2 * e]) - dlt) * p.scale;
-          float ds1 = pp.y * (__uint_as_float(dp[2 * e + 1]) - dlt) * p.scale;
-          pk[e] = pack_bf16x2(ds0, ds1);
+          const uint32_t t2 = pack_bf16x2(fmaf(__uint_as_float(dp[2 * e]), p.scale, nds), fmaf(__uint_as_float(dp[2 * e + 1]), p.scale, nds));
+          pk[e] = mul_bf16x2(pk[e], t2);
         }
       }
       mbar_wait(ds_empty, (i & 1) ^ 1);  // dK/dQ MMAs of the previous tile have finished reading sdS
       {
-        uint8_t* dsrow = sdS + half * kTile + row * 128;
+        const uint32_t dsrow = smem_u32(sdS + half * kTile + row * 128);
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc)
-          *reinterpret_cast<uint4*>(dsrow + ((pc ^ (row & 7)) << 4)) = make_uint4(pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+        for (int pc = 0; pc < 8; ++pc) sts128(dsrow + ((pc ^ (row & 7)) << 4), pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();

@@ -120,42 +120,43 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* x) {
 // A thread owns one accumulator ROW, so direct global accesses touch 32 different cache lines per warp instruction (measured:
 // ~2.8 clk per line on the LSU, the bound of every epilogue with fp32 streams); staged, an instruction covers 4 full 128-byte
 // lines (fp32) or 8 64-byte row segments (bf16).
-__device__ __forceinline__ uint8_t* stage_at(uint8_t* stg, int row, int grp) { return stg + row * 128 + ((grp ^ (row & 7)) << 4); }
+__device__ __forceinline__ uint32_t stage_at(uint32_t stg, int row, int grp) { return stg + row * 128 + ((grp ^ (row & 7)) << 4); }
 
 // f[32] = this lane's row of a 32-column chunk at column nb -> bf16 global rows (row_base + 0..31), coalesced.
 template <bool FULL>
-__device__ __forceinline__ void store_chunk_bf16(uint8_t* stg, int lane, const float (&f)[32], __nv_bfloat16* base, long long ld,
+__device__ __forceinline__ void store_chunk_bf16(uint32_t stg, int lane, const float (&f)[32], __nv_bfloat16* base, long long ld,
                                                  int row_base, int row_lim, int nb, int N) {
 #pragma unroll
   for (int g = 0; g < 4; ++g)
-    *reinterpret_cast<uint4*>(stage_at(stg, lane, g)) =
-        make_uint4(pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
-                   pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
+    sts128(stage_at(stg, lane, g), pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
+           pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
   __syncwarp();
   const int rr = lane >> 2, gg = lane & 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int mm = row_base + i * 8 + rr, nn = nb + gg * 8;
     if (mm < row_lim && (FULL || nn < N)) {
-      const uint4 t = *reinterpret_cast<const uint4*>(stage_at(stg, i * 8 + rr, gg));
+      const uint4 t = lds128(stage_at(stg, i * 8 + rr, gg));
       st_global_v4(base + (long long)mm * ld + nn, t.x, t.y, t.z, t.w);
     }
   }
   __syncwarp();
 }
 template <bool FULL, bool kRed>
-__device__ __forceinline__ void store_chunk_f32(uint8_t* stg, int lane, const float (&f)[32], float* base, long long ld, int row_base,
+__device__ __forceinline__ void store_chunk_f32(uint32_t stg, int lane, const float (&f)[32], float* base, long long ld, int row_base,
                                                 int row_lim, int nb, int N) {
 #pragma unroll
   for (int g = 0; g < 8; ++g)
-    *reinterpret_cast<float4*>(stage_at(stg, lane, g)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+    sts128(stage_at(stg, lane, g), __float_as_uint(f[4 * g]), __float_as_uint(f[4 * g + 1]), __float_as_uint(f[4 * g + 2]),
+           __float_as_uint(f[4 * g + 3]));
   __syncwarp();
   const int rr = lane >> 3, gg = lane & 7;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int mm = row_base + i * 4 + rr, nn = nb + gg * 4;
     if (mm < row_lim && (FULL || nn < N)) {
-      const float4 t = *reinterpret_cast<const float4*>(stage_at(stg, i * 4 + rr, gg));
+      const uint4 u = lds128(stage_at(stg, i * 4 + rr, gg));
+      const float4 t = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
       if (kRed) red_add_v4(base + (long long)mm * ld + nn, t.x, t.y, t.z, t.w);
       else *reinterpret_cast<float4*>(base + (long long)mm * ld + nn) = t;
     }
@@ -164,7 +165,7 @@ __device__ __forceinline__ void store_chunk_f32(uint8_t* stg, int lane, const fl
 }
 // Coalesced gather of a 32x32 fp32 / bf16 tile into this lane's row.
 template <bool FULL>
-__device__ __forceinline__ void load_chunk_f32(uint8_t* stg, int lane, float (&x)[32], const float* base, long long ld, int row_base,
+__device__ __forceinline__ void load_chunk_f32(uint32_t stg, int lane, float (&x)[32], const float* base, long long ld, int row_base,
                                                int row_lim, int nb, int N) {
   const int rr = lane >> 3, gg = lane & 7;
   float4 t[8];
@@ -175,17 +176,18 @@ __device__ __forceinline__ void load_chunk_f32(uint8_t* stg, int lane, float (&x
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stage_at(stg, i * 4 + rr, gg)) = t[i];
+  for (int i = 0; i < 8; ++i)
+    sts128(stage_at(stg, i * 4 + rr, gg), __float_as_uint(t[i].x), __float_as_uint(t[i].y), __float_as_uint(t[i].z), __float_as_uint(t[i].w));
   __syncwarp();
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
-    const float4 u = *reinterpret_cast<const float4*>(stage_at(stg, lane, g));
-    x[4 * g] = u.x; x[4 * g + 1] = u.y; x[4 * g + 2] = u.z; x[4 * g + 3] = u.w;
+    const uint4 u = lds128(stage_at(stg, lane, g));
+    x[4 * g] = __uint_as_float(u.x); x[4 * g + 1] = __uint_as_float(u.y); x[4 * g + 2] = __uint_as_float(u.z); x[4 * g + 3] = __uint_as_float(u.w);
   }
   __syncwarp();
 }
 template <bool FULL>
-__device__ __forceinline__ void load_chunk_bf16(uint8_t* stg, int lane, float (&x)[32], const __nv_bfloat16* base, long long ld,
+__device__ __forceinline__ void load_chunk_bf16(uint32_t stg, int lane, float (&x)[32], const __nv_bfloat16* base, long long ld,
                                                 int row_base, int row_lim, int nb, int N) {
   const int rr = lane >> 2, gg = lane & 3;
   uint4 t[4];
@@ -195,17 +197,17 @@ __device__ __forceinline__ void load_chunk_bf16(uint8_t* stg, int lane, float (&
     t[i] = (mm < row_lim && (FULL || nn < N)) ? *reinterpret_cast<const uint4*>(base + (long long)mm * ld + nn) : make_uint4(0u, 0u, 0u, 0u);
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage_at(stg, i * 8 + rr, gg)) = t[i];
+  for (int i = 0; i < 4; ++i) sts128(stage_at(stg, i * 8 + rr, gg), t[i].x, t[i].y, t[i].z, t[i].w);
   __syncwarp();
 #pragma unroll
-  for (int g = 0; g < 4; ++g) unpack8(*reinterpret_cast<const uint4*>(stage_at(stg, lane, g)), &x[8 * g]);
+  for (int g = 0; g < 4; ++g) unpack8(lds128(stage_at(stg, lane, g)), &x[8 * g]);
   __syncwarp();
 }
 
 // One 32-column chunk (columns nb..nb+31) of the 32 accumulator rows of this warp (thread = row row_base + lane).  Warp-collective.
 // FULL: all 32 columns are < N (no column predicates).  Base pointers are per batch (row 0, column 0).
 template <uint32_t F, bool FULL>
-__device__ __forceinline__ void epi_chunk(const GemmKParams& p, const EpiFlags<F>& e, uint8_t* stg, int lane, const uint32_t (&v)[32],
+__device__ __forceinline__ void epi_chunk(const GemmKParams& p, const EpiFlags<F>& e, uint32_t stg, int lane, const uint32_t (&v)[32],
                                           int row_base, int nb, const float* aux32, const __nv_bfloat16* aux16,
                                           __nv_bfloat16* pre16, __nv_bfloat16* o16, float* o32, float& s1, float& s2) {
   const int row_lim = p.rows;
@@ -420,7 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ------------------------------------------------------------------ epilogue warps (2..9)
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int chalf = (warp - 2) >> 2;   // the two warps of a quarter take alternate 32-column chunks
-    uint8_t* stg = staging + (warp - 2) * 4096;
+    const uint32_t stg = smem_u32(staging + (warp - 2) * 4096);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
