@@ -264,7 +264,11 @@ __device__ __forceinline__ void epi_chunk(const GemmKParams& p, const EpiFlags<F
 
 // kMC: launched as clusters of 2 CTAs that own two M-adjacent tiles with the same N tile; each CTA fetches half of the shared
 // B (weight / X) tile and TMA-multicasts it to both, cutting L2->SM operand traffic per CTA from A+B to A+B/2.
-template <bool kMC, uint32_t F>
+// kMC == 2: CTA PAIR (tcgen05 cta_group::2).  The two CTAs of a cluster own M-adjacent tiles with the same N tile, as in mode 1, but
+// the pair's leader issues ONE M=256 MMA for both: each CTA loads only its own 128 rows of A and its HALF of the B tile, so the
+// per-SM operand ingress per k-step drops from 48 KB to 32 KB (the main loop is bound by exactly that at 128x256 tiles) and a
+// pipeline stage shrinks from 48 KB to 32 KB (6 stages instead of 4).
+template <int kMC, uint32_t F>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmKParams p) {
@@ -291,17 +295,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < p.num_stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], kMC ? 2 : 1);   // cluster: both CTAs' MMA warps release a stage (it receives multicast data)
+      mbar_init(&empty_bar[i], kMC == 1 ? 2 : 1);   // multicast mode: both CTAs' MMA warps release a stage (it receives multicast data)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 8);
+      mbar_init(&tmem_empty_bar[i], kMC == 2 ? 16 : 8);   // pair mode: the leader's barrier collects the epilogue warps of BOTH CTAs
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_base_slot, kTmemCols);
-    tmem_relinquish();
+    if (kMC == 2) {
+      tmem_alloc_2sm(tmem_base_slot, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_base_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -330,7 +339,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + kABytes;
-          if (leader) {
+          if (leader && kMC == 2) {
+            // pair mode: both CTAs load (own A rows, own half of B) into their own ring; all bytes are credited to the LEADER's barrier
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * p.tx_bytes);
+            const int nch2 = p.BN / 128;    // 64-column chunks of this CTA's half of an MN-major B tile
+            if (!kWgrad) {
+              int t = it / p.k_chunks;
+              int kc = it - t * p.k_chunks;
+              tma_load_3d_2sm(sa, &tmap_a, &full_bar[stage], kc * kBK, tc.m0 + p.shift0 + t * p.shift_step, tc.b);
+              if (!b_mn) {
+                tma_load_3d_2sm(sb, &tmap_b, &full_bar[stage], kc * kBK, tc.n0 + crank * (p.BN / 2), t);
+              } else {
+                for (int j = 0; j < nch2; ++j)
+                  tma_load_3d_2sm(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + (crank * nch2 + j) * 64, kc * kBK, t);
+              }
+            } else {
+              int b = it / p.k_chunks;
+              int lc = it - b * p.k_chunks;
+              for (int j = 0; j < 2; ++j)
+                tma_load_3d_2sm(sa + j * 8192, &tmap_a, &full_bar[stage], tc.m0 + j * 64, lc * kBK, b);
+              int shift = p.shift0 + tc.tap * p.shift_step;
+              for (int j = 0; j < nch2; ++j)
+                tma_load_3d_2sm(sb + j * 8192, &tmap_b, &full_bar[stage], tc.n0 + (crank * nch2 + j) * 64, lc * kBK + shift, b);
+            }
+          } else if (leader) {
           mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
           if (!kWgrad) {
             int t = it / p.k_chunks;
@@ -380,8 +412,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
     const bool leader = elect_one();
-    {
-      const uint32_t idesc = make_idesc_bf16(kBM, p.BN, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
+    if (kMC != 2 || crank == 0) {      // pair mode: only the leader CTA issues (for both CTAs' accumulators)
+      const uint32_t idesc = make_idesc_bf16(kMC == 2 ? 2 * kBM : kBM, p.BN, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -401,9 +433,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int k = 0; k < kBK / 16; ++k) {
               uint64_t da = a_mn ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
               uint64_t db = b_mn ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-              umma_f16_ss(tmem_d, da, db, idesc, (it > tc.k_begin || k > 0) ? 1u : 0u);
+              if (kMC == 2) umma_f16_ss_2sm(tmem_d, da, db, idesc, (it > tc.k_begin || k > 0) ? 1u : 0u);
+              else umma_f16_ss(tmem_d, da, db, idesc, (it > tc.k_begin || k > 0) ? 1u : 0u);
             }
-            if (kMC) umma_commit_mc(&empty_bar[stage], 3);
+            if (kMC == 2) umma_commit_2sm(&empty_bar[stage], 3);
+            else if (kMC == 1) umma_commit_mc(&empty_bar[stage], 3);
             else umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
@@ -412,7 +446,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             phase ^= 1;
           }
         }
-        if (leader) umma_commit(&tmem_full_bar[acc]);
+        if (leader) {
+          if (kMC == 2) umma_commit_2sm(&tmem_full_bar[acc], 3);
+          else umma_commit(&tmem_full_bar[acc]);
+        }
         __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -478,7 +515,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // accumulator drained: the MMA warp may start the next tile into it
+      if (lane == 0) {   // accumulator drained: the MMA warp may start the next tile into it
+        if (kMC == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (!kWgrad) {
       if (F == kEpiRuntime ? (p.stats != nullptr) : ((F & E_STATS) != 0)) {
         // one pair of global double atomics per TILE: the 8 epilogue warps first combine in shared memory
@@ -510,7 +550,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncthreads();
   if (kMC) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it / arrive on its barriers
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) {
+    if (kMC == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -519,7 +562,7 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 namespace ofx {
 
-template <bool kMC, uint32_t F>
+template <int kMC, uint32_t F>
 static int launch_one(const GemmKParams& p, const CUtensorMap& ta, const CUtensorMap& tb, size_t smem_bytes, cudaStream_t stream) {
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
@@ -528,7 +571,7 @@ static int launch_one(const GemmKParams& p, const CUtensorMap& ta, const CUtenso
   }
   if (!kMC) {
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
-    gemm_kernel<false, F><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    gemm_kernel<0, F><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
   } else {
     int pairs = device_sm_count() / 2;
     if (p.num_tiles < pairs) pairs = p.num_tiles;
@@ -544,7 +587,7 @@ static int launch_one(const GemmKParams& p, const CUtensorMap& ta, const CUtenso
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true, F>, ta, tb, p));
+    OF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<kMC, F>, ta, tb, p));
   }
   return OF_OK;
 }
@@ -559,15 +602,18 @@ static int launch_one(const GemmKParams& p, const CUtensorMap& ta, const CUtenso
   X(E_AUX16_DSILU | E_O16)                                                             /* ff backward through SiLU */            \
   X(E_BIAS | E_AUX16_ADD | E_O16) X(E_AUX16_ADD | E_O16)                               /* Parallel sampler, Downsample fix-up */
 
-static int launch_gemm(uint32_t mask, bool mc, const GemmKParams& p, const CUtensorMap& ta, const CUtensorMap& tb, size_t smem_bytes,
+static int launch_gemm(uint32_t mask, int mc, const GemmKParams& p, const CUtensorMap& ta, const CUtensorMap& tb, size_t smem_bytes,
                        cudaStream_t stream) {
 #define OF_CASE(FLAGS)                                                                                   \
   if (mask == (uint32_t)(FLAGS))                                                                         \
-    return mc ? launch_one<true, (uint32_t)(FLAGS)>(p, ta, tb, smem_bytes, stream)                       \
-              : launch_one<false, (uint32_t)(FLAGS)>(p, ta, tb, smem_bytes, stream);
+    return mc == 2   ? launch_one<2, (uint32_t)(FLAGS)>(p, ta, tb, smem_bytes, stream)                   \
+           : mc == 1 ? launch_one<1, (uint32_t)(FLAGS)>(p, ta, tb, smem_bytes, stream)                   \
+                     : launch_one<0, (uint32_t)(FLAGS)>(p, ta, tb, smem_bytes, stream);
   OF_GEMM_EPILOGUES(OF_CASE)
 #undef OF_CASE
-  return mc ? launch_one<true, kEpiRuntime>(p, ta, tb, smem_bytes, stream) : launch_one<false, kEpiRuntime>(p, ta, tb, smem_bytes, stream);
+  return mc == 2   ? launch_one<2, kEpiRuntime>(p, ta, tb, smem_bytes, stream)
+         : mc == 1 ? launch_one<1, kEpiRuntime>(p, ta, tb, smem_bytes, stream)
+                   : launch_one<0, kEpiRuntime>(p, ta, tb, smem_bytes, stream);
 }
 
 }  // namespace ofx
@@ -614,20 +660,24 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
   OF_REQUIRE(BN % 32 == 0 && BN >= 32 && BN <= 256, "of_gemm: block_n=%d invalid", BN);
   if (b_mn) OF_REQUIRE(BN % 64 == 0, "of_gemm: block_n=%d must be a multiple of 64 for MN-major B", BN);
   p.BN = BN;
+  // cluster of 2 CTAs on M-adjacent tiles: needs two M tiles to pair and a B tile that splits into two swizzle-aligned halves.
+  //   mode 2 (default): CTA pair, tcgen05 cta_group::2 -- each CTA holds only its half of B;  mode 1: TMA multicast of the halves
+  const int m_tiles_real = wgrad ? ceil_div(a->K, kBM) : ceil_div(a->rows, kBM);
+  bool use_mc = (m_tiles_real >= 2) && (b_mn ? ((BN / 64) % 2 == 0) : (BN % 16 == 0 && BN >= 64));
+  int mc_mode = use_mc ? 2 : 0;
+  {
+    const char* e = getenv("OF_GEMM_NO_MULTICAST");
+    if (e && e[0] == '1') use_mc = false, mc_mode = 0;
+    const char* e2 = getenv("OF_GEMM_2CTA");
+    if (e2 && e2[0] == '0' && mc_mode == 2) mc_mode = 1;
+  }
   const uint32_t b_bytes = (uint32_t)BN * 128u;
-  p.stage_bytes = kABytes + b_bytes;
+  p.stage_bytes = kABytes + (mc_mode == 2 ? b_bytes / 2 : b_bytes);
   p.tx_bytes = p.stage_bytes;
   int stages = (int)((192u * 1024u) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
 
-  // cluster-of-2 multicast of the B tile: needs two M tiles to pair and a B tile that splits into two swizzle-aligned halves
-  const int m_tiles_real = wgrad ? ceil_div(a->K, kBM) : ceil_div(a->rows, kBM);
-  bool use_mc = (m_tiles_real >= 2) && (b_mn ? ((BN / 64) % 2 == 0) : (BN % 16 == 0 && BN >= 64));
-  {
-    const char* e = getenv("OF_GEMM_NO_MULTICAST");
-    if (e && e[0] == '1') use_mc = false;
-  }
   if (!wgrad) {
     p.m_tiles = use_mc ? ceil_div(m_tiles_real, 2) : m_tiles_real;
     p.n_tiles = ceil_div(a->N, BN);
@@ -727,7 +777,7 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
            (p.pre_bf16 ? E_PRE16 : 0u) | (p.act == OF_ACT_SILU ? E_SILU : 0u) | (p.out_bf16 ? E_O16 : 0u) |
            (p.out_f32 ? E_O32 : 0u) | (p.stats ? E_STATS : 0u);
   }
-  int rc2 = launch_gemm(mask, use_mc, p, ta, tb, smem_bytes, stream);
+  int rc2 = launch_gemm(mask, mc_mode, p, ta, tb, smem_bytes, stream);
   if (rc2 != OF_OK) return rc2;
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
