@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kBThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const AttnBwdParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -135,6 +136,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
 
@@ -374,6 +376,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, long long out_ld, long long out_bs,
                                   const __nv_bfloat16* __restrict__ dout, long long do_ld, long long do_bs,
                                   float* __restrict__ delta, int B, int H, int L, int D) {
+  pdl_launch_dependents();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * L * H;
   if (idx >= total) return;
@@ -439,7 +442,7 @@ extern "C" int of_attn_bwd(const of_attn_args* a, void* stream_) {
     attr_set = true;
   }
   dim3 grid((a->L + 127) / 128, a->H, a->B);
-  attn_bwd_kernel<<<grid, kBThreads, smem_bytes, stream>>>(tq, tk, tv, tdo, p);
+  OF_CHECK_CUDA(launch_pdl<1>(attn_bwd_kernel, grid, dim3(kBThreads), smem_bytes, stream, tq, tk, tv, tdo, p));
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

@@ -46,6 +46,7 @@ __device__ __forceinline__ float ex2(float x) {
 __global__ void __launch_bounds__(kAThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 2 x 16 KB
@@ -88,6 +89,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
@@ -350,7 +352,7 @@ extern "C" int of_attn_fwd(const of_attn_args* a, void* stream_) {
     attr_set = true;
   }
   dim3 grid((a->L + 255) / 256, a->H, a->B);
-  attn_fwd_kernel<<<grid, kAThreads, smem_bytes, stream>>>(tq, tk, tv, p);
+  OF_CHECK_CUDA(launch_pdl<1>(attn_fwd_kernel, grid, dim3(kAThreads), smem_bytes, stream, tq, tk, tv, p));
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

@@ -272,6 +272,7 @@ template <int kMC, uint32_t F>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmKParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned tile ring (SWIZZLE_128B atoms), barriers after it.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -316,6 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncthreads();
   if (kMC) cluster_sync_all();   // peer barriers must be initialised before any multicast can arrive
   tc_fence_after();
+  pdl_wait();                    // everything above overlapped the previous kernel's tail; its results are visible from here on
   const uint32_t tmem_base = *tmem_base_slot;
   const int crank = kMC ? (int)cluster_ctarank() : 0;
   const int tile_first = kMC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -569,26 +571,33 @@ static int launch_one(const GemmKParams& p, const CUtensorMap& ta, const CUtenso
     OF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kMC, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  const bool pdl = pdl_level() >= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (!kMC) {
-    int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
-    gemm_kernel<0, F><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    cfg.gridDim = dim3(p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count());
   } else {
     int pairs = device_sm_count() / 2;
     if (p.num_tiles < pairs) pairs = p.num_tiles;
-    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    OF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<kMC, F>, ta, tb, p));
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (pdl) {   // programmatic dependent launch: the kernel's prologue overlaps the previous kernel's tail (griddepcontrol.wait inside)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  OF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<kMC, F>, ta, tb, p));
   return OF_OK;
 }
 

@@ -30,6 +30,8 @@ __device__ __forceinline__ int find_group_by_row(const of_film_group* __restrict
 template <int MM>
 __global__ void __launch_bounds__(256) film_fwd_kernel(const of_film_group* __restrict__ groups, int num_groups, int total_rows,
                                                        const float* __restrict__ x, int M, int K, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * 8 + warp) * 4;
   if (row0 >= total_rows) return;
@@ -84,6 +86,8 @@ template <int MM>
 __global__ void __launch_bounds__(256) film_bwd_kernel(const of_film_group* __restrict__ groups, const int2* __restrict__ chunks,
                                                        const float* __restrict__ dss, const float* __restrict__ x, int M, int K,
                                                        float* __restrict__ d_emb) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sd[kFilmChunk][MM];
   const int2 ch = chunks[blockIdx.y];
   const of_film_group g = groups[ch.x];
@@ -140,6 +144,8 @@ constexpr int kPackFlat = 4096;   // elements per CTA of a flat cast segment
 constexpr int kPackCi = 1024;     // input channels per CTA of a conv segment (k <= 4)
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const of_pack_seg* __restrict__ segs, int num_segs) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_w[kPackCi * 4];
   int lo = 0, hi = num_segs - 1;
   const int cta = blockIdx.x;
@@ -200,9 +206,9 @@ extern "C" int of_film_fwd(const of_film_group* groups_dev, int num_groups, int 
   OF_REQUIRE(M >= 1 && M <= kFilmMaxM, "of_film_fwd: M=%d out of range (1..%d)", M, kFilmMaxM);
   OF_REQUIRE(K % 4 == 0 && total_rows % 4 == 0, "of_film_fwd: K=%d and every head's row count must be multiples of 4", K);
   const int grid = (total_rows + 31) / 32;
-  if (M <= 4) film_fwd_kernel<4><<<grid, 256, 0, STREAM>>>(groups_dev, num_groups, total_rows, x, M, K, out);
-  else if (M <= 8) film_fwd_kernel<8><<<grid, 256, 0, STREAM>>>(groups_dev, num_groups, total_rows, x, M, K, out);
-  else film_fwd_kernel<16><<<grid, 256, 0, STREAM>>>(groups_dev, num_groups, total_rows, x, M, K, out);
+  if (M <= 4) OF_CHECK_CUDA(launch_pdl(film_fwd_kernel<4>, dim3(grid), dim3(256), 0, STREAM, groups_dev, num_groups, total_rows, x, M, K, out));
+  else if (M <= 8) OF_CHECK_CUDA(launch_pdl(film_fwd_kernel<8>, dim3(grid), dim3(256), 0, STREAM, groups_dev, num_groups, total_rows, x, M, K, out));
+  else OF_CHECK_CUDA(launch_pdl(film_fwd_kernel<16>, dim3(grid), dim3(256), 0, STREAM, groups_dev, num_groups, total_rows, x, M, K, out));
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;
@@ -215,9 +221,9 @@ extern "C" int of_film_bwd(const of_film_group* groups_dev, const int* chunks_de
   OF_REQUIRE(K % 4 == 0, "of_film_bwd: K=%d must be a multiple of 4", K);
   dim3 grid((K / 4 + 255) / 256, num_chunks);
   const int2* ch = reinterpret_cast<const int2*>(chunks_dev);
-  if (M <= 4) film_bwd_kernel<4><<<grid, 256, 0, STREAM>>>(groups_dev, ch, dss, x, M, K, d_emb);
-  else if (M <= 8) film_bwd_kernel<8><<<grid, 256, 0, STREAM>>>(groups_dev, ch, dss, x, M, K, d_emb);
-  else film_bwd_kernel<16><<<grid, 256, 0, STREAM>>>(groups_dev, ch, dss, x, M, K, d_emb);
+  if (M <= 4) OF_CHECK_CUDA(launch_pdl(film_bwd_kernel<4>, dim3(grid), dim3(256), 0, STREAM, groups_dev, ch, dss, x, M, K, d_emb));
+  else if (M <= 8) OF_CHECK_CUDA(launch_pdl(film_bwd_kernel<8>, dim3(grid), dim3(256), 0, STREAM, groups_dev, ch, dss, x, M, K, d_emb));
+  else OF_CHECK_CUDA(launch_pdl(film_bwd_kernel<16>, dim3(grid), dim3(256), 0, STREAM, groups_dev, ch, dss, x, M, K, d_emb));
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;
@@ -227,7 +233,7 @@ extern "C" int of_film_chunk_rows(void) { return kFilmChunk; }
 
 extern "C" int of_pack_weights(const of_pack_seg* segs_dev, int num_segs, int total_ctas, void* stream) {
   OF_REQUIRE(segs_dev && num_segs >= 1 && total_ctas >= 1, "of_pack_weights: bad args");
-  pack_weights_kernel<<<total_ctas, 256, 0, STREAM>>>(segs_dev, num_segs);
+  OF_CHECK_CUDA(launch_pdl(pack_weights_kernel, dim3(total_ctas), dim3(256), 0, STREAM, segs_dev, num_segs));
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;
@@ -248,6 +254,8 @@ namespace ofx {
 
 // sum of squares of the whole arena (padding between tensors is zero) -> out[0] (double, atomically accumulated)
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[32];
   float s = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
@@ -272,6 +280,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const of_opt_tensor* __restr
                                                     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                     const double* __restrict__ sumsq, float max_norm, float lr, float beta1, float beta2,
                                                     float eps, float weight_decay, float bias_corr1, float bias_corr2_sqrt) {
+  pdl_launch_dependents();
+  pdl_wait();
   int lo = 0, hi = num_tensors - 1;
   const int cta = blockIdx.x;
   while (lo < hi) {
@@ -332,7 +342,7 @@ extern "C" int of_grad_sumsq(const float* grads, long long n, double* out, void*
   if (n > 0) {
     long long want = (n / 4 + 255) / 256;
     const int grid = (int)(want < 8LL * device_sm_count() ? (want < 1 ? 1 : want) : 8LL * device_sm_count());
-    sumsq_kernel<<<grid, 256, 0, STREAM>>>(grads, n, out);
+    OF_CHECK_CUDA(launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, STREAM, grads, n, out));
     OF_CHECK_CUDA(cudaGetLastError());
   }
   count_launch();
@@ -347,8 +357,8 @@ extern "C" int of_adamw_step(const of_opt_tensor* table_dev, int num_tensors, in
   OF_REQUIRE(table_dev && grads && exp_avg && exp_avg_sq && num_tensors >= 1 && total_ctas >= 1 && step >= 1, "of_adamw_step: bad args");
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
-  adamw_kernel<<<total_ctas, 256, 0, STREAM>>>(table_dev, num_tensors, grads, exp_avg, exp_avg_sq, sumsq, max_norm, lr, beta1, beta2, eps,
-                                               weight_decay, bc1, bc2s);
+  OF_CHECK_CUDA(launch_pdl(adamw_kernel, dim3(total_ctas), dim3(256), 0, STREAM, table_dev, num_tensors, grads, exp_avg, exp_avg_sq, sumsq, max_norm, lr, beta1, beta2, eps,
+                                               weight_decay, bc1, bc2s));
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

@@ -1,3 +1,4 @@
+#include <stdlib.h>
 #include "host_common.h"
 
 #include <string.h>
@@ -14,6 +15,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int pdl_level() {
+  static const int level = [] {
+    const char* e = getenv("OF_PDL");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }();
+  return level;
 }
 
 int device_sm_count() {

@@ -29,6 +29,25 @@ PFN_encodeTiled get_encode_tiled();
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box);
 
+// Launch with programmatic stream serialisation (PDL): the kernel may be scheduled while the previous kernel in the stream is
+// still draining; it must execute griddepcontrol.wait (ptx.cuh: pdl_wait) before touching global memory.  OF_PDL=0 disables it.
+// OF_PDL = 0: off; 1 (default): tensor-core kernels (GEMM, attention: they have a real prologue to hide); 2: every kernel.
+int pdl_level();
+template <int kLevel = 2, typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_level() >= kLevel ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define OF_CHECK_CUDA(expr)                                                                \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \

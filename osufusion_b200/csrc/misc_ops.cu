@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             float eps, float* __restrict__ out_f32,
                                                             __nv_bfloat16* __restrict__ out_bf16, long long out_ld,
                                                             float* __restrict__ mean_rstd) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ dx_bf16, long long dx_ld,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             int rows_per_warp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int vecs = C >> 3;
   V8 g[NV], dg[NV], db[NV];
@@ -180,6 +184,8 @@ __device__ __forceinline__ V8 ld_tab(const float* p) { return ld_f32x8(p); }
 template <typename TAB>
 __global__ void rope_fwd_kernel(__nv_bfloat16* qkv, long long ld, long long bs, int B, int L, int slots, int D,
                                 const TAB* __restrict__ cosT, const TAB* __restrict__ sinT) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tps = D >> 4;  // threads per slot (each handles 8 + 8 paired channels)
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * L * slots * tps;
@@ -215,6 +221,8 @@ __global__ void rope_bwd_kernel(const float* __restrict__ dq, long long dq_ld, l
                                 const float* __restrict__ dv, long long dkv_ld, long long dkv_bs, __nv_bfloat16* out,
                                 long long out_ld, long long out_bs, int B, int L, int H, int KVH, int D,
                                 const TAB* __restrict__ cosT, const TAB* __restrict__ sinT) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tps = D >> 4;
   const int slots = H + 2 * KVH;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,6 +266,8 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
                                                                const float* __restrict__ bias, int act, int round_bf16,
                                                                float* __restrict__ y, long long y_ld,
                                                                float* __restrict__ ypre) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + warp;
   if (n >= N) return;
@@ -321,6 +331,8 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
                                                                const float* __restrict__ W, long long w_ld, int round_bf16,
                                                                float* __restrict__ dW, float* __restrict__ dbias,
                                                                float* __restrict__ dx, long long dx_ld, int kthreads, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sdpre[kNChunk][kMaxM];
   const int n0 = blockIdx.y * kNChunk;
   const int nn = min(kNChunk, N - n0);
@@ -431,6 +443,8 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
 // db[n] += sum_rows bf16 dy[row, n].  256 threads = vecs 16-byte column vectors x rpar row-lanes; shared-memory combine.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, long long rows,
                                                           int N, float* __restrict__ db, int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_cs[];  // [min(vecs,256) * 8]
   const int vecs_total = N >> 3;
   const int v0 = blockIdx.y * 256;
@@ -470,6 +484,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 __global__ void pack_input_kernel(const float* __restrict__ x, const float* __restrict__ noise, const float* __restrict__ ca,
                                   const float* __restrict__ cb, int B, int C, int N, __nv_bfloat16* __restrict__ out, int Lp,
                                   int Cp, float pad_value) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cv = Cp >> 3;
   long long total = (long long)B * cv * Lp;
@@ -499,6 +515,8 @@ __global__ void pack_input_kernel(const float* __restrict__ x, const float* __re
 // (B, Lp, ld) bf16 channels-last -> (B, C, N) fp32 channel-first (first C channels, first N rows)
 __global__ void unpack_output_kernel(const __nv_bfloat16* __restrict__ y, long long ld, long long bs, int B, int C, int N,
                                      float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * C * N;
   if (idx >= total) return;
@@ -510,6 +528,8 @@ __global__ void unpack_output_kernel(const __nv_bfloat16* __restrict__ y, long l
 
 __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, long long x_bs, int B, int L, int C,
                                       __nv_bfloat16* __restrict__ out, long long o_ld, long long o_bs) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cv = C >> 3;
   long long total = (long long)B * L * cv;
@@ -525,6 +545,8 @@ __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, long 
 __global__ void upsample2x_bwd_kernel(const float* __restrict__ d, long long d_ld, long long d_bs, int B, int L, int C,
                                       float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long long o_ld,
                                       long long o_bs) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cv = C >> 3;
   long long total = (long long)B * L * cv;
@@ -544,6 +566,8 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ d, long long d_l
 __global__ void cast_copy_kernel(const float* __restrict__ src32, const __nv_bfloat16* __restrict__ src16, long long s_ld,
                                  long long s_bs, int B, int L, int C, float* __restrict__ dst32, __nv_bfloat16* __restrict__ dst16,
                                  long long d_ld, long long d_bs, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cv = C >> 3;
   long long total = (long long)B * L * cv;
@@ -566,6 +590,8 @@ __global__ void cast_copy_kernel(const float* __restrict__ src32, const __nv_bfl
 
 // sinusoidal embedding (unet.py:26-39): out[b, j] = sin(t_b f_j), out[b, half + j] = cos(t_b f_j), f_j = exp(-j ln(theta)/(half-1))
 __global__ void time_embed_kernel(const float* __restrict__ t, int B, int dim, float theta, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (idx >= B * half) return;
@@ -579,6 +605,8 @@ __global__ void time_embed_kernel(const float* __restrict__ t, int B, int dim, f
 
 // elementwise SiLU on small fp32 tensors: fwd y = silu(x); bwd dx = dy * silu'(x)
 __global__ void silu_small_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out[i] = dy ? dy[i] * dsilu_acc(x[i]) : silu_acc(x[i]);
@@ -590,6 +618,8 @@ __global__ void __launch_bounds__(256) mse_fwd_kernel(const __nv_bfloat16* __res
                                                       const float* __restrict__ x, const float* __restrict__ noise, float ta,
                                                       float tb, const long long* __restrict__ orig_len, int B, int C, int N,
                                                       float* __restrict__ accum) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[32];
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * C * N;
@@ -613,12 +643,16 @@ __global__ void __launch_bounds__(256) mse_fwd_kernel(const __nv_bfloat16* __res
     atomicAdd(accum + 1, cnt);
   }
 }
-__global__ void mse_finish_kernel(const float* __restrict__ accum, float* __restrict__ loss) { loss[0] = accum[0] / accum[1]; }
+__global__ void mse_finish_kernel(const float* __restrict__ accum, float* __restrict__ loss) {
+  pdl_launch_dependents();
+  pdl_wait(); loss[0] = accum[0] / accum[1]; }
 // dpred (B, Lp, Cp) bf16 channels-last = gscale * 2 * mask * (pred - target) / count ; zero elsewhere
 __global__ void mse_bwd_kernel(const __nv_bfloat16* __restrict__ pred, long long ld, long long bs, const float* __restrict__ x,
                                const float* __restrict__ noise, float ta, float tb, const long long* __restrict__ orig_len,
                                int B, int C, int N, int Lp, int Cp, const float* __restrict__ accum,
                                const float* __restrict__ gscale, __nv_bfloat16* __restrict__ dpred) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Lp * Cp;
   if (idx >= total) return;
@@ -645,6 +679,8 @@ __global__ void sampler_update_kernel(const float* __restrict__ xin, const __nv_
                                       float c_eps, float c_div, float c_x0, float c_dir, int B, int C, int N,
                                       float* __restrict__ xout, __nv_bfloat16* __restrict__ packed, int Lp, int Cp,
                                       float pad_value) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Lp * Cp;
   if (idx >= total) return;
@@ -683,6 +719,8 @@ constexpr int kPackChunk = 256;
 __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int k,
                                                                __nv_bfloat16* __restrict__ out, int Cin_pad, int tap_offset,
                                                                int taps_total) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_w[];  // [kPackChunk * k]
   const int co = blockIdx.x;
   const int ci0 = blockIdx.y * kPackChunk;
@@ -700,6 +738,8 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
 __global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(float* __restrict__ packed, int Cout, int Cin, int k,
                                                                 int Cin_pad, int tap_offset, float* __restrict__ dw,
                                                                 int accumulate, int rezero) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_w[];
   const int co = blockIdx.x;
   const int ci0 = blockIdx.y * kPackChunk;
@@ -715,6 +755,8 @@ __global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(float* __restric
   for (int i = threadIdx.x; i < nreal * k; i += blockDim.x) dst[i] = accumulate ? dst[i] + s_w[i] : s_w[i];
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -743,10 +785,10 @@ extern "C" int of_layernorm_fwd(const float* x, long long x_ld, int rows, int C,
   dim3 grid((rows + 7) / 8);
   const int nv = (C / 8 + 31) / 32;
   __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (nv <= 1) layernorm_fwd_kernel<1><<<grid, 256, 0, STREAM>>>(x, x_ld, rows, C, gamma, beta, eps, out_f32, o16, out_ld, mean_rstd);
-  else if (nv <= 2) layernorm_fwd_kernel<2><<<grid, 256, 0, STREAM>>>(x, x_ld, rows, C, gamma, beta, eps, out_f32, o16, out_ld, mean_rstd);
-  else if (nv <= 4) layernorm_fwd_kernel<4><<<grid, 256, 0, STREAM>>>(x, x_ld, rows, C, gamma, beta, eps, out_f32, o16, out_ld, mean_rstd);
-  else layernorm_fwd_kernel<8><<<grid, 256, 0, STREAM>>>(x, x_ld, rows, C, gamma, beta, eps, out_f32, o16, out_ld, mean_rstd);
+  if (nv <= 1) OF_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel<1>, dim3(grid), dim3(256), 0, STREAM, x, x_ld, rows, C, gamma, beta, eps, out_f32, o16, out_ld, mean_rstd));
+  else if (nv <= 2) OF_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel<2>, dim3(grid), dim3(256), 0, STREAM, x, x_ld, rows, C, gamma, beta, eps, out_f32, o16, out_ld, mean_rstd));
+  else if (nv <= 4) OF_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel<4>, dim3(grid), dim3(256), 0, STREAM, x, x_ld, rows, C, gamma, beta, eps, out_f32, o16, out_ld, mean_rstd));
+  else OF_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel<8>, dim3(grid), dim3(256), 0, STREAM, x, x_ld, rows, C, gamma, beta, eps, out_f32, o16, out_ld, mean_rstd));
   DONE()
 }
 
@@ -761,10 +803,10 @@ extern "C" int of_layernorm_bwd(const float* dy, long long dy_ld, const float* x
   const size_t red_smem = 2 * (size_t)C * sizeof(float);
   const int nv = (C / 8 + 31) / 32;
   __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-  if (nv <= 1) layernorm_bwd_kernel<1><<<grid, 256, red_smem, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
-  else if (nv <= 2) layernorm_bwd_kernel<2><<<grid, 256, red_smem, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
-  else if (nv <= 4) layernorm_bwd_kernel<4><<<grid, 256, red_smem, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
-  else layernorm_bwd_kernel<8><<<grid, 256, red_smem, STREAM>>>(dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw);
+  if (nv <= 1) OF_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<1>, dim3(grid), dim3(256), red_smem, STREAM, dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw));
+  else if (nv <= 2) OF_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), red_smem, STREAM, dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw));
+  else if (nv <= 4) OF_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<4>, dim3(grid), dim3(256), red_smem, STREAM, dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw));
+  else OF_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), red_smem, STREAM, dy, dy_ld, x, x_ld, rows, C, gamma, mean_rstd, dx_f32, o16, dx_ld, dgamma, dbeta, rpw));
   DONE()
 }
 
@@ -774,13 +816,13 @@ extern "C" int of_rope_fwd(void* qkv, long long ld, long long bs, int B, int L, 
   OF_REQUIRE(D % 16 == 0 && ld % 8 == 0, "of_rope_fwd: D=%d must be a multiple of 16", D);
   long long total = (long long)B * L * (H + KVH) * (D / 16);
   if (table_f32)
-    rope_fwd_kernel<float><<<blocks_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<__nv_bfloat16*>(qkv), ld, bs, B, L, H + KVH, D,
+    OF_CHECK_CUDA(launch_pdl(rope_fwd_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, reinterpret_cast<__nv_bfloat16*>(qkv), ld, bs, B, L, H + KVH, D,
                                                                        reinterpret_cast<const float*>(cos_tab),
-                                                                       reinterpret_cast<const float*>(sin_tab));
+                                                                       reinterpret_cast<const float*>(sin_tab)));
   else
-    rope_fwd_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, STREAM>>>(
+    OF_CHECK_CUDA(launch_pdl(rope_fwd_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, 
         reinterpret_cast<__nv_bfloat16*>(qkv), ld, bs, B, L, H + KVH, D, reinterpret_cast<const __nv_bfloat16*>(cos_tab),
-        reinterpret_cast<const __nv_bfloat16*>(sin_tab));
+        reinterpret_cast<const __nv_bfloat16*>(sin_tab)));
   DONE()
 }
 
@@ -791,14 +833,14 @@ extern "C" int of_rope_bwd(const float* dq, long long dq_ld, long long dq_bs, co
   OF_REQUIRE(D % 16 == 0, "of_rope_bwd: D=%d must be a multiple of 16", D);
   long long total = (long long)B * L * (H + 2 * KVH) * (D / 16);
   if (table_f32)
-    rope_bwd_kernel<float><<<blocks_for(total, 256), 256, 0, STREAM>>>(dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs,
+    OF_CHECK_CUDA(launch_pdl(rope_bwd_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs,
                                                                        reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), out_ld, out_bs, B, L,
                                                                        H, KVH, D, reinterpret_cast<const float*>(cos_tab),
-                                                                       reinterpret_cast<const float*>(sin_tab));
+                                                                       reinterpret_cast<const float*>(sin_tab)));
   else
-    rope_bwd_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, STREAM>>>(
+    OF_CHECK_CUDA(launch_pdl(rope_bwd_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, 
         dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), out_ld, out_bs, B, L, H, KVH, D,
-        reinterpret_cast<const __nv_bfloat16*>(cos_tab), reinterpret_cast<const __nv_bfloat16*>(sin_tab));
+        reinterpret_cast<const __nv_bfloat16*>(cos_tab), reinterpret_cast<const __nv_bfloat16*>(sin_tab)));
   DONE()
 }
 
@@ -807,9 +849,9 @@ extern "C" int of_linear_small_fwd(const float* x, long long x_ld, int M, int N,
                                    void* stream) {
   OF_REQUIRE(x && W && y, "of_linear_small_fwd: null pointer");
   OF_REQUIRE(M >= 1 && M <= kMaxM, "of_linear_small_fwd: M=%d out of range (1..%d)", M, kMaxM);
-  if (M <= 4) linear_small_fwd_kernel<4><<<(N + 7) / 8, 256, 0, STREAM>>>(x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre);
-  else if (M <= 8) linear_small_fwd_kernel<8><<<(N + 7) / 8, 256, 0, STREAM>>>(x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre);
-  else linear_small_fwd_kernel<16><<<(N + 7) / 8, 256, 0, STREAM>>>(x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre);
+  if (M <= 4) OF_CHECK_CUDA(launch_pdl(linear_small_fwd_kernel<4>, dim3((N + 7) / 8), dim3(256), 0, STREAM, x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre));
+  else if (M <= 8) OF_CHECK_CUDA(launch_pdl(linear_small_fwd_kernel<8>, dim3((N + 7) / 8), dim3(256), 0, STREAM, x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre));
+  else OF_CHECK_CUDA(launch_pdl(linear_small_fwd_kernel<16>, dim3((N + 7) / 8), dim3(256), 0, STREAM, x, x_ld, M, N, K, W, w_ld, bias, act, round_bf16, y, y_ld, ypre));
   DONE()
 }
 
@@ -826,9 +868,9 @@ extern "C" int of_linear_small_bwd(const float* dy, long long dy_ld, const float
   while (kthreads < kcols && kthreads < 256) kthreads <<= 1;
   dim3 grid((kcols + kthreads - 1) / kthreads, (N + kNChunk - 1) / kNChunk);
   const long long dxl = dx ? dx_ld : 4;
-  if (M <= 4) linear_small_bwd_kernel<4><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate);
-  else if (M <= 8) linear_small_bwd_kernel<8><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate);
-  else linear_small_bwd_kernel<16><<<grid, 256, 0, STREAM>>>(dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate);
+  if (M <= 4) OF_CHECK_CUDA(launch_pdl(linear_small_bwd_kernel<4>, dim3(grid), dim3(256), 0, STREAM, dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate));
+  else if (M <= 8) OF_CHECK_CUDA(launch_pdl(linear_small_bwd_kernel<8>, dim3(grid), dim3(256), 0, STREAM, dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate));
+  else OF_CHECK_CUDA(launch_pdl(linear_small_bwd_kernel<16>, dim3(grid), dim3(256), 0, STREAM, dy, dy_ld, ypre, act, x, x_ld, M, N, K, W, w_ld, round_bf16, dW, dbias, dx, dxl, kthreads, accumulate));
   DONE()
 }
 
@@ -838,7 +880,7 @@ extern "C" int of_colsum_bf16(const void* dy, long long ld, long long rows, int 
   if (rpc < 16) rpc = 16;
   if (rpc > 256) rpc = 256;
   dim3 grid((unsigned)((rows + rpc - 1) / rpc), (N / 8 + 255) / 256);
-  colsum_bf16_kernel<<<grid, 256, 256 * 8 * sizeof(float), STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc);
+  OF_CHECK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(256), 256 * 8 * sizeof(float), STREAM, reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc));
   DONE()
 }
 
@@ -846,15 +888,15 @@ extern "C" int of_pack_input(const float* x, const float* noise, const float* ca
                              int Lp, int Cp, float pad_value, void* stream) {
   OF_REQUIRE(x && out && Cp % 8 == 0 && Cp >= C && Lp >= N, "of_pack_input: bad args");
   long long total = (long long)B * (Cp / 8) * Lp;
-  pack_input_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(x, noise, ca, cb, B, C, N, reinterpret_cast<__nv_bfloat16*>(out), Lp,
-                                                                Cp, pad_value);
+  OF_CHECK_CUDA(launch_pdl(pack_input_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, x, noise, ca, cb, B, C, N, reinterpret_cast<__nv_bfloat16*>(out), Lp,
+                                                                Cp, pad_value));
   DONE()
 }
 
 extern "C" int of_unpack_output(const void* y, long long ld, long long bs, int B, int C, int N, float* out, void* stream) {
   OF_REQUIRE(y && out, "of_unpack_output: null pointer");
   long long total = (long long)B * C * N;
-  unpack_output_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(y), ld, bs, B, C, N, out);
+  OF_CHECK_CUDA(launch_pdl(unpack_output_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, reinterpret_cast<const __nv_bfloat16*>(y), ld, bs, B, C, N, out));
   DONE()
 }
 
@@ -862,16 +904,16 @@ extern "C" int of_upsample2x_fwd(const void* x, long long x_ld, long long x_bs, 
                                  long long o_bs, void* stream) {
   OF_REQUIRE(x && out && C % 8 == 0, "of_upsample2x_fwd: bad args");
   long long total = (long long)B * L * (C / 8);
-  upsample2x_fwd_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_ld, x_bs, B, L, C,
-                                                                    reinterpret_cast<__nv_bfloat16*>(out), o_ld, o_bs);
+  OF_CHECK_CUDA(launch_pdl(upsample2x_fwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, reinterpret_cast<const __nv_bfloat16*>(x), x_ld, x_bs, B, L, C,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out), o_ld, o_bs));
   DONE()
 }
 extern "C" int of_upsample2x_bwd(const float* d, long long d_ld, long long d_bs, int B, int L, int C, float* out_f32, void* out_bf16,
                                  long long o_ld, long long o_bs, void* stream) {
   OF_REQUIRE(d && (out_f32 || out_bf16) && C % 8 == 0, "of_upsample2x_bwd: bad args");
   long long total = (long long)B * L * (C / 8);
-  upsample2x_bwd_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(d, d_ld, d_bs, B, L, C, out_f32,
-                                                                    reinterpret_cast<__nv_bfloat16*>(out_bf16), o_ld, o_bs);
+  OF_CHECK_CUDA(launch_pdl(upsample2x_bwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, d, d_ld, d_bs, B, L, C, out_f32,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out_bf16), o_ld, o_bs));
   DONE()
 }
 
@@ -879,20 +921,20 @@ extern "C" int of_cast_copy(const float* src32, const void* src16, long long s_l
                             void* dst16, long long d_ld, long long d_bs, int accumulate, void* stream) {
   OF_REQUIRE((src32 || src16) && (dst32 || dst16) && C % 8 == 0, "of_cast_copy: bad args");
   long long total = (long long)B * L * (C / 8);
-  cast_copy_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(src32, reinterpret_cast<const __nv_bfloat16*>(src16), s_ld, s_bs, B, L, C,
-                                                               dst32, reinterpret_cast<__nv_bfloat16*>(dst16), d_ld, d_bs, accumulate);
+  OF_CHECK_CUDA(launch_pdl(cast_copy_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, src32, reinterpret_cast<const __nv_bfloat16*>(src16), s_ld, s_bs, B, L, C,
+                                                               dst32, reinterpret_cast<__nv_bfloat16*>(dst16), d_ld, d_bs, accumulate));
   DONE()
 }
 
 extern "C" int of_time_embed(const float* t, int B, int dim, float theta, float* out, void* stream) {
   OF_REQUIRE(t && out && dim >= 4 && dim % 2 == 0, "of_time_embed: bad args");
-  time_embed_kernel<<<blocks_for((long long)B * (dim / 2), 256), 256, 0, STREAM>>>(t, B, dim, theta, out);
+  OF_CHECK_CUDA(launch_pdl(time_embed_kernel, dim3(blocks_for((long long)B * (dim / 2), 256)), dim3(256), 0, STREAM, t, B, dim, theta, out));
   DONE()
 }
 
 extern "C" int of_silu_small(const float* x, const float* dy, float* out, long long n, void* stream) {
   OF_REQUIRE(x && out, "of_silu_small: null pointer");
-  silu_small_kernel<<<blocks_for(n, 256), 256, 0, STREAM>>>(x, dy, out, n);
+  OF_CHECK_CUDA(launch_pdl(silu_small_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, STREAM, x, dy, out, n));
   DONE()
 }
 
@@ -901,9 +943,9 @@ extern "C" int of_mse_fwd(const void* pred, long long ld, long long bs, const fl
   OF_REQUIRE(pred && noise && accum2 && loss && (ta == 0.f || x), "of_mse_fwd: null pointer");
   OF_CHECK_CUDA(cudaMemsetAsync(accum2, 0, 2 * sizeof(float), STREAM));
   long long total = (long long)B * C * N;
-  mse_fwd_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(pred), ld, bs, x, noise, ta, tb,
-                                                             orig_len, B, C, N, accum2);
-  mse_finish_kernel<<<1, 1, 0, STREAM>>>(accum2, loss);
+  OF_CHECK_CUDA(launch_pdl(mse_fwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, reinterpret_cast<const __nv_bfloat16*>(pred), ld, bs, x, noise, ta, tb,
+                                                             orig_len, B, C, N, accum2));
+  OF_CHECK_CUDA(launch_pdl(mse_finish_kernel, dim3(1), dim3(1), 0, STREAM, accum2, loss));
   count_launch();
   DONE()
 }
@@ -912,9 +954,9 @@ extern "C" int of_mse_bwd(const void* pred, long long ld, long long bs, const fl
                           void* dpred, void* stream) {
   OF_REQUIRE(pred && noise && accum2 && dpred, "of_mse_bwd: null pointer");
   long long total = (long long)B * Lp * Cp;
-  mse_bwd_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(pred), ld, bs, x, noise, ta, tb,
+  OF_CHECK_CUDA(launch_pdl(mse_bwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, reinterpret_cast<const __nv_bfloat16*>(pred), ld, bs, x, noise, ta, tb,
                                                              orig_len, B, C, N, Lp, Cp, accum2, gscale,
-                                                             reinterpret_cast<__nv_bfloat16*>(dpred));
+                                                             reinterpret_cast<__nv_bfloat16*>(dpred)));
   DONE()
 }
 
@@ -923,9 +965,9 @@ extern "C" int of_sampler_update(const float* xin, const void* cond, const void*
                                  void* packed, int Lp, int Cp, float pad_value, void* stream) {
   OF_REQUIRE(xin && cond && xout, "of_sampler_update: null pointer");
   long long total = (long long)B * Lp * Cp;
-  sampler_update_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(
+  OF_CHECK_CUDA(launch_pdl(sampler_update_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, 
       xin, reinterpret_cast<const __nv_bfloat16*>(cond), reinterpret_cast<const __nv_bfloat16*>(null_), ld, bs, cond_scale, mode, c_eps,
-      c_div, c_x0, c_dir, B, C, N, xout, reinterpret_cast<__nv_bfloat16*>(packed), Lp, Cp, pad_value);
+      c_div, c_x0, c_dir, B, C, N, xout, reinterpret_cast<__nv_bfloat16*>(packed), Lp, Cp, pad_value));
   DONE()
 }
 
@@ -934,8 +976,8 @@ extern "C" int of_pack_conv_weight(const float* w, int Cout, int Cin, int k, voi
   OF_REQUIRE(w && out && Cin_pad >= Cin && tap_offset + k <= taps_total, "of_pack_conv_weight: bad args");
   OF_REQUIRE(k <= 32, "of_pack_conv_weight: kernel size %d too large", k);
   dim3 grid(Cout, (Cin_pad + kPackChunk - 1) / kPackChunk);
-  pack_conv_weight_kernel<<<grid, 256, kPackChunk * k * sizeof(float), STREAM>>>(w, Cout, Cin, k, reinterpret_cast<__nv_bfloat16*>(out),
-                                                                                 Cin_pad, tap_offset, taps_total);
+  OF_CHECK_CUDA(launch_pdl(pack_conv_weight_kernel, dim3(grid), dim3(256), kPackChunk * k * sizeof(float), STREAM, w, Cout, Cin, k, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                                 Cin_pad, tap_offset, taps_total));
   DONE()
 }
 extern "C" int of_unpack_conv_wgrad(float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw,
@@ -943,12 +985,12 @@ extern "C" int of_unpack_conv_wgrad(float* packed, int Cout, int Cin, int k, int
   OF_REQUIRE(packed && dw, "of_unpack_conv_wgrad: null pointer");
   OF_REQUIRE(k <= 32, "of_unpack_conv_wgrad: kernel size %d too large", k);
   dim3 grid(Cout, (Cin + kPackChunk - 1) / kPackChunk);
-  unpack_conv_wgrad_kernel<<<grid, 256, kPackChunk * k * sizeof(float), STREAM>>>(packed, Cout, Cin, k, Cin_pad, tap_offset, dw,
-                                                                                  accumulate, rezero);
+  OF_CHECK_CUDA(launch_pdl(unpack_conv_wgrad_kernel, dim3(grid), dim3(256), kPackChunk * k * sizeof(float), STREAM, packed, Cout, Cin, k, Cin_pad, tap_offset, dw,
+                                                                                  accumulate, rezero));
   DONE()
 }
 extern "C" int of_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   OF_REQUIRE(src && dst, "of_cast_f32_bf16: null pointer");
-  cast_f32_bf16_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, STREAM>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  OF_CHECK_CUDA(launch_pdl(cast_f32_bf16_kernel, dim3(blocks_for((n + 3) / 4, 256)), dim3(256), 0, STREAM, src, reinterpret_cast<__nv_bfloat16*>(dst), n));
   DONE()
 }

@@ -35,6 +35,14 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Programmatic dependent launch (PDL).  Every kernel of the library signals `launch_dependents` as its first instruction; the
+// tensor-core kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization and execute `griddepcontrol.wait`
+// after their prologue (barrier init, TMEM allocation, descriptor prefetch), so that prologue and the launch latency overlap the
+// tail of the preceding kernel.  `wait` blocks until the preceding grid has completed and its memory is visible, so where the
+// trigger sits in the primary never affects correctness.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Explicit shared-space vector accesses.  Pointers derived from the 1024-byte re-aligned dynamic shared base go through an integer
 // round trip, so the compiler only knows them as GENERIC pointers and emits LD.E / ST.E (generic path, long scoreboard) instead of
 // LDS / STS; these helpers take the 32-bit shared address.

@@ -153,6 +153,8 @@ __device__ __forceinline__ void cta_channel_reduce(const Map& m, int C, const fl
 
 template <bool FILM>
 __global__ void __launch_bounds__(kRbThreads, 3) rb_apply_fwd_kernel(const of_rb_args a, const int rpc) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int R = 8;
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L, rpc);
@@ -174,6 +176,8 @@ __global__ void __launch_bounds__(kRbThreads, 3) rb_apply_fwd_kernel(const of_rb
 // Row-wise dot products dot(h[b,l,:], vec): channel-owner mapping (constants loaded once per thread), per-row partials
 // combined through shared memory (one shuffle-reduced atomic per warp when a warp lies inside one row).
 __global__ void __launch_bounds__(kRbThreads, 3) rb_rowdot_kernel(const of_rb_args a, const int rpc) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int R = 8;
   extern __shared__ float s_red[];   // [rpc] row accumulators
   GnCtx g = make_ctx(a);
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(kRbThreads, 3) rb_rowdot_kernel(const of_rb_ar
 
 // one CTA per sample: da = p * (rd - sum_l p*rd) in place on rd   (softmax backward with the fp32 probabilities)
 __global__ void __launch_bounds__(1024) softmax_bwd_rows_kernel(const float* __restrict__ p, float* rd, int L) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[32];
   const float* pr = p + (long long)blockIdx.x * L;
   float* r = rd + (long long)blockIdx.x * L;
@@ -232,6 +238,8 @@ __global__ void __launch_bounds__(1024) softmax_bwd_rows_kernel(const float* __r
 
 // one CTA per sample: p = softmax(logits) in place (fp32; consumers round to bf16 where the reference does)
 __global__ void __launch_bounds__(1024) softmax_rows_kernel(float* rows, int L) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[32];
   float* r = rows + (long long)blockIdx.x * L;
   float mx = -INFINITY;
@@ -245,6 +253,8 @@ __global__ void __launch_bounds__(1024) softmax_rows_kernel(float* rows, int L) 
 }
 
 __global__ void __launch_bounds__(kRbThreads, 3) rb_pool_kernel(const of_rb_args a, const int rpc) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int R = 8;
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
@@ -279,6 +289,8 @@ __global__ void __launch_bounds__(kRbThreads, 3) rb_pool_kernel(const of_rb_args
 }
 
 __global__ void __launch_bounds__(kRbThreads, 2) rb_gate_fwd_kernel(const of_rb_args a, const int rpc) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int R = 4;
   GnCtx g = make_ctx(a);
   Map m = make_map(a.C, a.L, rpc);
@@ -316,6 +328,8 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_gate_fwd_kernel(const of_rb_
 
 // ------------------------------------------------------------------------------------------------ backward
 __global__ void __launch_bounds__(kRbThreads, 3) rb_gate_bwd_reduce_kernel(const of_rb_args a, const int rpc) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int R = 4;
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
@@ -350,6 +364,8 @@ __global__ void __launch_bounds__(kRbThreads, 3) rb_gate_bwd_reduce_kernel(const
 
 template <int MODE, bool FILM>
 __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb_args a, const int rpc) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int R = MODE == 0 ? 2 : 4;
   __shared__ float sm[32];
   extern __shared__ float s_red[];
@@ -469,6 +485,8 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_bwd_pass1_kernel(const of_rb
 }
 
 __global__ void __launch_bounds__(kRbThreads, 3) rb_bwd_apply_kernel(const of_rb_args a, const int rpc) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int R = 4;
   extern __shared__ float s_red[];
   GnCtx g = make_ctx(a);
@@ -545,8 +563,8 @@ using namespace ofx;
 
 #define RB_LAUNCH(kernel, ctas_per_sm)                                                                                       \
   const int rpc = rb_rows_per_cta(a, ctas_per_sm);                                                                                      \
-  kernel<<<rb_grid(a, rpc), rb_threads(a), 5 * (size_t)a->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(*a, rpc); \
-  OF_CHECK_CUDA(cudaGetLastError());                                              \
+  OF_CHECK_CUDA(launch_pdl(kernel, rb_grid(a, rpc), dim3(rb_threads(a)), 5 * (size_t)a->C * sizeof(float),                     \
+                           reinterpret_cast<cudaStream_t>(stream), *a, rpc));                                              \
   count_launch();                                                                 \
   return OF_OK;
 
@@ -563,23 +581,20 @@ extern "C" int of_rb_rowdot(const of_rb_args* a, void* stream) {
   OF_REQUIRE(a->ss == nullptr, "of_rb_rowdot: FiLM (ss) is only supported by of_rb_apply_fwd / of_rb_bwd_pass1(mode 1)");
   OF_REQUIRE(a->vec && a->out_rows, "of_rb_rowdot: null vec/out_rows");
   const int rpc = rb_rows_per_cta(a, 3);
-  rb_rowdot_kernel<<<rb_grid(a, rpc), rb_threads(a), (size_t)(rpc > 5 * a->C ? rpc : 5 * a->C) * sizeof(float),
-                     reinterpret_cast<cudaStream_t>(stream)>>>(*a, rpc);
-  OF_CHECK_CUDA(cudaGetLastError());
+  OF_CHECK_CUDA(launch_pdl(rb_rowdot_kernel, rb_grid(a, rpc), dim3(rb_threads(a)), (size_t)(rpc > 5 * a->C ? rpc : 5 * a->C) * sizeof(float),
+                           reinterpret_cast<cudaStream_t>(stream), *a, rpc));
   count_launch();
   return OF_OK;
 }
 extern "C" int of_softmax_rows(float* rows, int B, int L, void* stream) {
   OF_REQUIRE(rows && B >= 1 && L >= 1, "of_softmax_rows: bad args");
-  softmax_rows_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rows, L);
-  OF_CHECK_CUDA(cudaGetLastError());
+  OF_CHECK_CUDA(launch_pdl(softmax_rows_kernel, dim3(B), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), rows, L));
   count_launch();
   return OF_OK;
 }
 extern "C" int of_softmax_bwd_rows(const float* p, float* rd, int B, int L, void* stream) {
   OF_REQUIRE(p && rd && B >= 1 && L >= 1, "of_softmax_bwd_rows: bad args");
-  softmax_bwd_rows_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, rd, L);
-  OF_CHECK_CUDA(cudaGetLastError());
+  OF_CHECK_CUDA(launch_pdl(softmax_bwd_rows_kernel, dim3(B), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), p, rd, L));
   count_launch();
   return OF_OK;
 }
