@@ -33,6 +33,9 @@ const char* of_last_error(void);
 int of_version(void);
 /* Number of kernel launches issued through this library since load (for bench.py `gpu_launches`). */
 long long of_launch_count(void);
+/* Upper bound on the SMs persistent kernels may assume (0 = all).  Used by the data-parallel wrapper to leave room for the NCCL
+ * all-reduce kernels that overlap backward (torch DDP gives the reference the same overlap: trainer.py:211-220,301). */
+int of_set_sm_limit(int n);
 void of_reset_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------

@@ -25,7 +25,18 @@ int pdl_level() {
   return level;
 }
 
+static std::atomic<int> g_sm_limit{0};
+
+// Persistent kernels (the GEMM) size their grids from this.  When NCCL collectives overlap the backward pass their CTAs occupy
+// SMs for a millisecond at a time; a persistent grid that assumes all 148 SMs then runs as TWO waves (the CTAs that found no SM
+// start only when the first ones exit).  The data-parallel wrapper therefore reserves SMs for the collective through this limit.
+extern "C" int of_set_sm_limit(int n) {
+  g_sm_limit.store(n < 0 ? 0 : n, std::memory_order_relaxed);
+  return OF_OK;
+}
+
 int device_sm_count() {
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
@@ -34,6 +45,7 @@ int device_sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cached[dev] = n;
   }
+  if (lim > 0 && lim < cached[dev]) return lim;
   return cached[dev];
 }
 

@@ -23,7 +23,8 @@ from .engine import backward_param_order  # noqa: E402,F401  (re-exported: the a
 class GradAllReducer:
     """Owns the gradient arena of `model.unet` and all-reduces (averages) it bucket by bucket during backward."""
 
-    def __init__(self, model: torch.nn.Module, bucket_bytes: int = 256 << 20, group=None, overlap: bool = True) -> None:
+    def __init__(self, model: torch.nn.Module, bucket_bytes: int = 256 << 20, group=None, overlap: bool = True,
+                 reserve_sms: int = 0) -> None:
         unet = model.unet if hasattr(model, "unet") else model
         self.unet, self.group, self.overlap = unet, group, overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -52,6 +53,12 @@ class GradAllReducer:
         unet.grad_sync = self._after_op
         unet.grad_finish = self.finish
         self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        # leave `reserve_sms` SMs to the NCCL kernels: the persistent GEMM grid shrinks accordingly (see of_set_sm_limit)
+        self.reserve_sms = reserve_sms
+        if reserve_sms > 0 and dev.type == "cuda" and self.world > 1:
+            from . import _native as N
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            N.lib().of_set_sm_limit(max(2, (sms - reserve_sms) // 2 * 2))
         self._touch_log = {}
         self._op = None
         self._launched = set()
