@@ -33,6 +33,16 @@ SIZES = {"L": 512, "S": 128}
 FWD_TFLOP = {"L": 2.500, "S": 0.974}
 
 
+ATTN_TFLOP_4096 = 0.8246   # 4*H*D*sum_layers L_l^2 at N=4096 (16 heads x 64, 39 attention layers): quadratic in N, the rest is linear
+
+
+def fwd_tflop(size: str, frames: int) -> float:
+    """Algorithmic forward TFLOP of one sample of `frames` frames (SURVEY.md §8d figures at 4096, split into the linear and the
+    quadratic (attention) part)."""
+    r = frames / 4096.0
+    return (FWD_TFLOP[size] - ATTN_TFLOP_4096) * r + ATTN_TFLOP_4096 * r * r
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -128,8 +138,11 @@ def run_reference(args) -> None:
         return
     frames = args.ref_frames
     sec, cores, loss = cpu_reference_step_time(args.size, frames, args.steps, min(args.warmup, 1))
-    value = 1.0 / sec
-    sample = f"batch 1 x {frames} frames per step (workload: batch {args.batch} x {args.frames} frames per GPU), fp32, oracle port of the reference"
+    # one bounded step = batch 1 x `frames` frames; expressed in the workload's unit (samples of args.frames frames) by algorithmic FLOPs
+    equiv = fwd_tflop(args.size, frames) / fwd_tflop(args.size, args.frames)
+    value = equiv / sec
+    sample = (f"batch 1 x {frames} frames per step = {equiv:.3f} workload samples by algorithmic FLOPs (workload: batch {args.batch} x "
+              f"{args.frames} frames per GPU), fp32, oracle port of the reference, {sec:.2f} s per step")
     line = {
         "impl": "reference", "metric": "denoiser fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -277,12 +290,14 @@ def run_ours(args) -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cores, _ = cpu_reference_step_time(size, args.ref_frames, 1, 0)
-        cpu = {"value": 1.0 / sec, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"1 step of batch 1 x {args.ref_frames} frames, fp32 oracle port on the host CPU ({sec:.1f} s)"}
+        equiv = fwd_tflop(size, args.ref_frames) / fwd_tflop(size, n)
+        cpu = {"value": equiv / sec, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"1 step of batch 1 x {args.ref_frames} frames = {equiv:.3f} workload samples by algorithmic FLOPs, fp32 oracle "
+                         f"port on the host CPU ({sec:.1f} s)"}
 
     if rank == 0:
         tf_peak, _, _ = peaks()
-        step_tflop = 3 * FWD_TFLOP[size] * (n / 4096.0) * B   # linear-in-N approximation is exact only at N=4096
+        step_tflop = 3 * fwd_tflop(size, n) * B
         line = {
             "metric": "denoiser fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
 
 // =================================================================================================== column sum (bias grads)
 // db[n] += sum_rows bf16 dy[row, n].  256 threads = vecs 16-byte column vectors x rpar row-lanes; shared-memory combine.
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, long long rows,
+__global__ void __launch_bounds__(1024) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long ld, long long rows,
                                                           int N, float* __restrict__ db, int rows_per_cta) {
   pdl_launch_dependents();
   pdl_wait();
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   const int vecs_total = N >> 3;
   const int v0 = blockIdx.y * 256;
   const int vecs = min(256, vecs_total - v0);
-  const int rpar = 256 / vecs;
+  const int rpar = blockDim.x / vecs;      // row lanes: few, large CTAs keep the number of same-address global atomics per channel low
   const int vi = threadIdx.x % vecs, rsub = threadIdx.x / vecs;
   const bool active = rsub < rpar;
   for (int c = threadIdx.x; c < vecs * 8; c += blockDim.x) s_cs[c] = 0.f;
@@ -876,11 +876,15 @@ extern "C" int of_linear_small_bwd(const float* dy, long long dy_ld, const float
 
 extern "C" int of_colsum_bf16(const void* dy, long long ld, long long rows, int N, float* db, void* stream) {
   OF_REQUIRE(dy && db && N % 8 == 0 && ld % 8 == 0, "of_colsum_bf16: bad args");
-  int rpc = (int)((rows + 2 * device_sm_count() - 1) / (2 * device_sm_count()));
-  if (rpc < 16) rpc = 16;
-  if (rpc > 256) rpc = 256;
-  dim3 grid((unsigned)((rows + rpc - 1) / rpc), (N / 8 + 255) / 256);
-  OF_CHECK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(256), 256 * 8 * sizeof(float), STREAM, reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc));
+  // one 1024-thread CTA per SM: every CTA ends with one global atomic per channel, and same-address atomics serialise in L2
+  // (~27 clk each), so the CTA count -- not the byte count -- set the duration of the 256-thread / 2-CTAs-per-SM version
+  const int ychunks = (N / 8 + 255) / 256;
+  int ctas_x = device_sm_count() / ychunks;
+  if (ctas_x < 1) ctas_x = 1;
+  int rpc = (int)((rows + ctas_x - 1) / ctas_x);
+  if (rpc < 64) rpc = 64;
+  dim3 grid((unsigned)((rows + rpc - 1) / rpc), ychunks);
+  OF_CHECK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(1024), 256 * 8 * sizeof(float), STREAM, reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc));
   DONE()
 }
 

@@ -94,6 +94,14 @@ def test_small_cfg_s_forward_backward():
     check(SMALL, 2, 1024, "default", True)
 
 
+def test_cfg_l_forward_backward():
+    """The headline configuration (dim_h=512, 1.28 B parameters, all 1239 gradients) at a reduced length: exercises the 256-wide
+    tiles, the CTA-pair GEMM mode and every deep-level shape of the benchmark."""
+    from oracle.synth import LARGE
+    check(LARGE, 1, 1024, "default", True)
+    torch.cuda.empty_cache()
+
+
 def test_golden_reference_outputs():
     """Engine output vs golden vectors produced by the REAL reference (CPU fp32) — tests/golden/unet_tiny_ref.pt."""
     from oracle.denoiser import UNet as OracleUNet
