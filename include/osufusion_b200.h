@@ -191,6 +191,12 @@ typedef struct {
 
 int of_rb_apply_fwd(const of_rb_args* a, void* stream);
 int of_rb_rowdot(const of_rb_args* a, void* stream);
+/* GlobalContext forward fused (residual.py:29-32): logits = to_k(h) (bf16-rounded, written to out_rows), softmax over L and the
+ * pooled channel sums in ONE pass over y with a CTA-local online softmax; a finishing launch combines the per-CTA records
+ * part[B][of_rb_pool_parts()][C+2], writes pooled[B][C] and converts out_rows to the fp32 probabilities.  Replaces
+ * of_rb_rowdot(mode 0) + of_softmax_rows + of_rb_pool (one pass over y less). */
+int of_rb_pool_parts(const of_rb_args* a);
+int of_rb_logit_pool(const of_rb_args* a, float* part, float* pooled, void* stream);
 int of_rb_pool(const of_rb_args* a, void* stream);
 int of_rb_gate_fwd(const of_rb_args* a, void* stream);
 int of_rb_gate_bwd_reduce(const of_rb_args* a, void* stream);

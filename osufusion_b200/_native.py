@@ -96,6 +96,7 @@ _SIGS = {
     "of_rb_apply_fwd": [C.POINTER(RbArgs), P],
     "of_rb_rowdot": [C.POINTER(RbArgs), P],
     "of_rb_pool": [C.POINTER(RbArgs), P],
+    "of_rb_logit_pool": [C.POINTER(RbArgs), P, P, P],
     "of_rb_gate_fwd": [C.POINTER(RbArgs), P],
     "of_rb_gate_bwd_reduce": [C.POINTER(RbArgs), P],
     "of_rb_bwd_pass1": [C.POINTER(RbArgs), P],
@@ -130,7 +131,7 @@ _SIGS = {
     "of_dora_merge": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P],
     "of_dora_grad": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P, P, P],
 }
-_PLAIN = {"of_set_sm_limit": [I], "of_film_chunk_rows": [], "of_pack_seg_ctas": [I, I, I, I], "of_opt_tensor_ctas": [LL]}    # host-side helpers: no stream argument, return a value
+_PLAIN = {"of_set_sm_limit": [I], "of_rb_pool_parts": [C.POINTER(RbArgs)], "of_film_chunk_rows": [], "of_pack_seg_ctas": [I, I, I, I], "of_opt_tensor_ctas": [LL]}    # host-side helpers: no stream argument, return a value
 EXPORTS = ["of_last_error", "of_version", "of_launch_count", "of_reset_launch_count", *_SIGS.keys(), *_PLAIN.keys()]
 
 

@@ -223,6 +223,138 @@ __global__ void __launch_bounds__(kRbThreads, 3) rb_rowdot_kernel(const of_rb_ar
   }
 }
 
+// GlobalContext forward in ONE pass over y (residual.py:29-32): logits = to_k(h) per row, then softmax-weighted channel sums with a
+// CTA-local ONLINE softmax (running maximum, rescaled partial sums) -- the separate pooling pass over y and the softmax launch
+// disappear.  Each CTA writes (acc[C], m, z) to `part`; rb_pool_finish_kernel combines the CTAs of a sample and turns the logits
+// into the fp32 probabilities the backward pass uses.
+__global__ void __launch_bounds__(kRbThreads, 2) rb_logit_pool_kernel(const of_rb_args a, const int rpc, float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int R = 4;
+  extern __shared__ float s_red[];              // [C] channel combine | then [rpc] row logits | [2] z, spare
+  float* s_log = s_red + a.C;
+  float* s_z = s_log + rpc;
+  GnCtx g = make_ctx(a);
+  Map m = make_map(a.C, a.L, rpc);
+  for (int i = threadIdx.x; i < rpc; i += blockDim.x) s_log[i] = 0.f;
+  if (threadIdx.x == 0) s_z[0] = 0.f;
+  __syncthreads();
+  const float bias = a.vec_bias ? *a.vec_bias : 0.f;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float m_run = -INFINITY, z = 0.f;
+  ChanConst<false> k;
+  V8 w;
+  if (m.active) {
+    k = load_consts<false>(g, m.b, m.c0);
+    w = ld_f32x8(a.vec + m.c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w.v[j] = bf16_round(w.v[j]);
+  }
+  const bool warp_in_row = (m.vecs & 31) == 0;
+  const __nv_bfloat16* yb = g.y + m.b * g.y_bs + m.c0;
+  const int rows_here = m.l_end - m.l_begin;
+  for (int base = 0; base < rows_here; base += R * m.rpar) {     // all threads run the same number of batches (barriers inside)
+    V8 h[R];
+    if (m.active) {
+      uint4 raw[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int l = m.l_begin + base + m.rsub + r * m.rpar;
+        if (l < m.l_end) raw[r] = ldg16(yb + (long long)l * g.y_ld);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int li = base + m.rsub + r * m.rpar;
+        if (m.l_begin + li < m.l_end) {
+          h[r] = gn_h(k, cvt_bf16x8(raw[r]));
+          float d = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            h[r].v[j] = bf16_round(h[r].v[j]);       // einsum / conv operands are bf16 under autocast
+            d = fmaf(h[r].v[j], w.v[j], d);
+          }
+          if (warp_in_row) {
+            d = warp_sum(d);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_log[li], d);
+          } else {
+            atomicAdd(&s_log[li], d);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // logits of this batch are complete: running maximum over the batch (every thread reads the same values)
+    const int nb = min(R * m.rpar, rows_here - base);
+    float mb = -INFINITY;
+    for (int i = 0; i < nb; ++i) mb = fmaxf(mb, bf16_round(s_log[base + i] + bias));
+    const float m_new = fmaxf(m_run, mb);
+    const float sc = __expf(m_run - m_new);           // 0 on the first batch (m_run = -inf)
+    z *= sc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= sc;
+    if (m.active) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int li = base + m.rsub + r * m.rpar;
+        if (m.l_begin + li < m.l_end) {
+          const float lg = bf16_round(s_log[li] + bias);
+          const float wgt = __expf(lg - m_new);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, h[r].v[j], acc[j]);
+          if (m.vi == 0) {
+            z += wgt;
+            a.out_rows[(long long)m.b * a.L + m.l_begin + li] = lg;
+          }
+        }
+      }
+    }
+    m_run = m_new;
+  }
+  // CTA combine: channel sums through shared memory, z of the row lanes, then plain stores of the partial record
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_red[c] = 0.f;
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_red[m.c0 + j], acc[j]);
+    if (m.vi == 0) atomicAdd(&s_z[0], z);
+  }
+  __syncthreads();
+  float* rec = part + ((long long)m.b * gridDim.x + blockIdx.x) * (a.C + 2);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) rec[c] = s_red[c];
+  if (threadIdx.x == 0) {
+    rec[a.C] = m_run;
+    rec[a.C + 1] = s_z[0];
+  }
+}
+
+// one CTA per sample: combine the per-CTA records -> pooled[C] (fp32) and logits -> probabilities in place
+__global__ void __launch_bounds__(1024) rb_pool_finish_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ rows,
+                                                              int L, float* __restrict__ pooled) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sm[32];
+  __shared__ float s_scale[1024];
+  const float* pb = part + (long long)blockIdx.x * nparts * (C + 2);
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) mx = fmaxf(mx, pb[(long long)i * (C + 2) + C]);
+  mx = block_max(mx, sm);
+  float zz = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    const float sc = __expf(pb[(long long)i * (C + 2) + C] - mx);
+    s_scale[i] = sc;
+    zz += sc * pb[(long long)i * (C + 2) + C + 1];
+  }
+  zz = block_sum(zz, sm);       // (contains the barriers that publish s_scale)
+  const float inv = 1.0f / zz;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < nparts; ++i) s = fmaf(s_scale[i], pb[(long long)i * (C + 2) + c], s);
+    pooled[(long long)blockIdx.x * C + c] = s * inv;
+  }
+  float* r = rows + (long long)blockIdx.x * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] = __expf(r[i] - mx) * inv;
+}
+
 // one CTA per sample: da = p * (rd - sum_l p*rd) in place on rd   (softmax backward with the fp32 probabilities)
 __global__ void __launch_bounds__(1024) softmax_bwd_rows_kernel(const float* __restrict__ p, float* rd, int L) {
   pdl_launch_dependents();
@@ -583,6 +715,28 @@ extern "C" int of_rb_rowdot(const of_rb_args* a, void* stream) {
   const int rpc = rb_rows_per_cta(a, 3);
   OF_CHECK_CUDA(launch_pdl(rb_rowdot_kernel, rb_grid(a, rpc), dim3(rb_threads(a)), (size_t)(rpc > 5 * a->C ? rpc : 5 * a->C) * sizeof(float),
                            reinterpret_cast<cudaStream_t>(stream), *a, rpc));
+  count_launch();
+  return OF_OK;
+}
+// Number of per-CTA partial records per sample of of_rb_logit_pool (the caller allocates part[B][n][C+2] floats).
+extern "C" int of_rb_pool_parts(const of_rb_args* a) {
+  if (a == nullptr || a->C < 8) return -1;
+  const int rpc = rb_rows_per_cta(a, 2);
+  return (a->L + rpc - 1) / rpc;
+}
+extern "C" int of_rb_logit_pool(const of_rb_args* a, float* part, float* pooled, void* stream) {
+  int rc = check_common(a, "of_rb_logit_pool");
+  if (rc) return rc;
+  OF_REQUIRE(a->ss == nullptr, "of_rb_logit_pool: FiLM (ss) is not supported on block2");
+  OF_REQUIRE(a->vec && a->out_rows && part && pooled, "of_rb_logit_pool: null vec/out_rows/part/pooled");
+  const int rpc = rb_rows_per_cta(a, 2);
+  const dim3 grid = rb_grid(a, rpc);
+  OF_REQUIRE(grid.x <= 1024, "of_rb_logit_pool: too many partial records (%u)", grid.x);
+  OF_CHECK_CUDA(launch_pdl(rb_logit_pool_kernel, grid, dim3(rb_threads(a)), ((size_t)a->C + rpc + 2) * sizeof(float),
+                           reinterpret_cast<cudaStream_t>(stream), *a, rpc, part));
+  count_launch();
+  OF_CHECK_CUDA(launch_pdl(rb_pool_finish_kernel, dim3(a->B), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream),
+                           (const float*)part, (int)grid.x, a->C, a->out_rows, a->L, pooled));
   count_launch();
   return OF_OK;
 }
