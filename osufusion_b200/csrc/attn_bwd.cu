@@ -17,7 +17,16 @@ namespace ofx {
 int make_head_tmap(CUtensorMap* m, const void* base, int D, int heads, int L, int B, long long ld, long long bs,
                    unsigned box_rows);
 
-constexpr int kBThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax/epilogue (two per TMEM lane quarter)
+// Softmax / epilogue warps: kNP warps per TMEM lane quarter, each owning 128/kNP key columns of S and dP (and 64/kNP d-columns of
+// dQ, dK, dV).  kNP = 4 (16 warps, twice the warps per scheduler at half the work per thread) was measured: 1063 us vs 1030 us for
+// kNP = 2 at B4 H16 L4096 -- the kernel is not bound by softmax issue slots but by shared-memory bandwidth: every MMA takes both
+// operands from shared memory (the N=64 ones need 192 B/clk against 128 B/clk), plus 64 KB of P/dS stores and 64 KB of dQ
+// staging per 128x128 tile: ~2.7 k clk of shared-memory time per tile against 1.3 k clk of tensor work.
+constexpr int kNP = 2;
+constexpr int kCW = 128 / kNP;            // S / dP columns per thread
+constexpr int kDW = 64 / kNP;             // dQ / dK / dV columns per thread
+constexpr int kSoftWarps = 4 * kNP;
+constexpr int kBThreads = 64 + 32 * kSoftWarps;  // warp 0 TMA, warp 1 MMA, then the softmax/epilogue warps
 constexpr uint32_t kTile = 128 * 64 * 2;  // 16 KB
 
 struct AttnBwdParams {
@@ -50,22 +59,35 @@ __device__ __forceinline__ void red_add4(float* ptr, float a, float b, float c, 
 // A thread holds one ROW (32 fp32 columns) of a 32x32 accumulator block; adding it to global memory directly makes every
 // red.v4 warp instruction touch 32 different 128-byte lines (measured: ~2.8 clk per line on the LSU -- this alone bounded the kernel
 // at ~5.7k clk per Q tile).  Staged through a swizzled 4 KB shared tile, one instruction covers 4 full lines.
-__device__ __forceinline__ void red_tile_32x32(uint32_t stg, int lane, const uint32_t (&v)[32], float* base, long long ld,
-                                               int row0, int row_lim, int col_lim) {
+template <int W>
+__device__ __forceinline__ void red_tile_32xW(uint32_t stg, int lane, const uint32_t (&v)[W], float* base, long long ld, int row0,
+                                              int row_lim, int col_lim) {
+  constexpr int G = W / 4;          // 16-byte groups per row (8 for 32 columns, 4 for 16)
+  constexpr int RPI = 32 / G;       // rows covered by one warp instruction
 #pragma unroll
-  for (int g = 0; g < 8; ++g)
-    sts128(stg + lane * 128 + ((g ^ (lane & 7)) << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  for (int g = 0; g < G; ++g) sts128(stg + lane * 128 + ((g ^ (lane & 7)) << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
   __syncwarp();
-  const int rr = lane >> 3, gg = lane & 7;
+  const int rr = lane / G, gg = lane % G;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rr;
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int r = i * RPI + rr;
     if (row0 + r < row_lim && gg * 4 < col_lim) {
       const uint4 t = lds128(stg + r * 128 + ((gg ^ (r & 7)) << 4));
       red_add4(base + (long long)(row0 + r) * ld + gg * 4, __uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
     }
   }
   __syncwarp();
+}
+template <int W>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[W]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<64>(uint32_t taddr, uint32_t (&r)[64]) {
+  tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t (*)[32]>(&r[0]));
+  tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t (*)[32]>(&r[32]));
 }
 
 // Software pipeline (per Q tile i; tensor core and softmax threads overlap):
@@ -83,8 +105,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sQdO = sV + kTile;      // 2 stages x (Q 16 KB + dO 16 KB)
   uint8_t* sP = sQdO + 4 * kTile;  // 32 KB
   uint8_t* sdS = sP + 2 * kTile;   // 32 KB
-  uint8_t* sStage = sdS + 2 * kTile;   // 8 softmax warps x 4 KB: coalescing buffer of the fp32 red.add tiles (dQ, dK, dV)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
+  uint8_t* sStage = sdS + 2 * kTile;   // per softmax warp a 32-row x 128-byte coalescing buffer for the fp32 red.add tiles (dQ, dK, dV)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kSoftWarps * 4096);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;    // [2]
   uint64_t* qdo_empty = bars + 3;   // [2]
@@ -117,15 +139,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 8);
+    mbar_init(s_empty, kSoftWarps);
     mbar_init(dp_full, 1);
-    mbar_init(dp_empty, 8);
-    mbar_init(p_full, 8);
+    mbar_init(dp_empty, kSoftWarps);
+    mbar_init(p_full, kSoftWarps);
     mbar_init(p_empty, 1);
-    mbar_init(ds_full, 8);
+    mbar_init(ds_full, kSoftWarps);
     mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 8);
+    mbar_init(dq_empty, kSoftWarps);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -242,25 +264,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     __syncwarp();
   } else {
     const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;     // which 64 keys (S/dP columns) / which 32 d-columns (dQ, dK, dV) this warp owns
+    const int part = (warp - 2) >> 2;     // which kCW keys (S/dP columns) / which kDW d-columns (dQ, dK, dV) this warp owns
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const long long bh = (long long)b * p.H + h;
-    const int key_base = k0 + half * 64;
+    const int key_base = k0 + part * kCW;
     const uint32_t stg = smem_u32(sStage + (warp - 2) * 4096);
+    // P / dS tiles in shared memory: [64-key half][row][128 bytes]; this thread's kCW keys are 16-byte chunks pc0 .. pc0+kCW/8-1
+    const int khalf = (part * kCW) / 64, pc0 = ((part * kCW) % 64) / 8;
+    constexpr int kChunks = kCW / 8;
 
     auto flush_dq = [&](int i) {   // stage C: dQ(i) tile -> global fp32 atomics
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-      uint32_t dq[32];
-      tmem_ld_32x32b_x32(tdQ + lane_off + half * 32, dq);
+      uint32_t dq[kDW];
+      tmem_ld_cols<kDW>(tdQ + lane_off + part * kDW, dq);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
-      // rows i*128 + qd*32 .. +31 of dQ, columns half*32 .. +31 of head h
-      red_tile_32x32(stg, lane, dq, p.dq + (long long)b * p.dq_bs + (long long)h * p.D + half * 32, p.dq_ld, i * 128 + qd * 32, p.L,
-                     p.D - half * 32);
+      // rows i*128 + qd*32 .. +31 of dQ, columns part*kDW .. of head h
+      red_tile_32xW<kDW>(stg, lane, dq, p.dq + (long long)b * p.dq_bs + (long long)h * p.D + part * kDW, p.dq_ld, i * 128 + qd * 32, p.L,
+                         p.D - part * kDW);
     };
 
     // per-row softmax statistics are fetched ONE tile ahead: a global load issued at the top of the tile that needs it put a full
@@ -278,29 +303,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         dlt_next = qn < p.L ? p.delta[bh * p.L + qn] : 0.f;
       }
       // ---- stage A: P = exp2(S*scale*log2e - lse2)
-      uint32_t pk[32];  // 64 probabilities, packed bf16x2
+      uint32_t pk[kCW / 2];  // kCW probabilities, packed bf16x2
       {
-        uint32_t s[64];
+        uint32_t s[kCW];
         mbar_wait(s_full, i & 1);
         tc_fence_after();
-        uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
-        uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
-        tmem_ld_32x32b_x32(tS + lane_off + half * 64, s0);
-        tmem_ld_32x32b_x32(tS + lane_off + half * 64 + 32, s1);
+        tmem_ld_cols<kCW>(tS + lane_off + part * kCW, s);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
         if (tile_full) {   // whole 128x128 tile valid: no per-element masking on the hot path
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < kCW / 2; ++e) {
             const float p0 = ex2b(fmaf(__uint_as_float(s[2 * e]), p.scale_log2, -lse2));
             const float p1 = ex2b(fmaf(__uint_as_float(s[2 * e + 1]), p.scale_log2, -lse2));
             pk[e] = pack_bf16x2(p0, p1);
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < kCW / 2; ++e) {
             float p0 = ex2b(fmaf(__uint_as_float(s[2 * e]), p.scale_log2, -lse2));
             float p1 = ex2b(fmaf(__uint_as_float(s[2 * e + 1]), p.scale_log2, -lse2));
             if (!q_ok || key_base + 2 * e >= p.L) p0 = 0.f;
@@ -311,9 +333,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       mbar_wait(p_empty, (i & 1) ^ 1);   // dV MMA of the previous tile has finished reading sP
       {
-        const uint32_t prow = smem_u32(sP + half * kTile + row * 128);
+        const uint32_t prow = smem_u32(sP + khalf * kTile + row * 128);
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) sts128(prow + ((pc ^ (row & 7)) << 4), pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+        for (int c = 0; c < kChunks; ++c)
+          sts128(prow + (((pc0 + c) ^ (row & 7)) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -322,13 +345,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (i > 0) flush_dq(i - 1);
       // ---- stage B: dS = P o (dP - delta) * scale
       {
-        uint32_t dp[64];
+        uint32_t dp[kCW];
         mbar_wait(dp_full, i & 1);
         tc_fence_after();
-        uint32_t (&d0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dp[0]);
-        uint32_t (&d1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dp[32]);
-        tmem_ld_32x32b_x32(tdP + lane_off + half * 64, d0);
-        tmem_ld_32x32b_x32(tdP + lane_off + half * 64 + 32, d1);
+        tmem_ld_cols<kCW>(tdP + lane_off + part * kCW, dp);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
@@ -337,32 +357,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // the bf16 P pair with one packed multiply -- 2 instructions per element instead of 4.5 (unpack, sub, 2 mul, pack).
         const float nds = -dlt * p.scale;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
+        for (int e = 0; e < kCW / 2; ++e) {
           const uint32_t t2 = pack_bf16x2(fmaf(__uint_as_float(dp[2 * e]), p.scale, nds), fmaf(__uint_as_float(dp[2 * e + 1]), p.scale, nds));
           pk[e] = mul_bf16x2(pk[e], t2);
         }
       }
       mbar_wait(ds_empty, (i & 1) ^ 1);  // dK/dQ MMAs of the previous tile have finished reading sdS
       {
-        const uint32_t dsrow = smem_u32(sdS + half * kTile + row * 128);
+        const uint32_t dsrow = smem_u32(sdS + khalf * kTile + row * 128);
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) sts128(dsrow + ((pc ^ (row & 7)) << 4), pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+        for (int c = 0; c < kChunks; ++c)
+          sts128(dsrow + (((pc0 + c) ^ (row & 7)) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
     }
     flush_dq(n - 1);
-    // ---- dK / dV tiles -> global (fp32 atomics; summed over q heads); this warp owns d-columns [half*32, half*32+32)
+    // ---- dK / dV tiles -> global (fp32 atomics; summed over q heads); this warp owns d-columns [part*kDW, +kDW)
     mbar_wait(acc_done, 0);
     tc_fence_after();
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      uint32_t a[32];
-      tmem_ld_32x32b_x32((which == 0 ? tdV : tdK) + lane_off + half * 32, a);
+      uint32_t a[kDW];
+      tmem_ld_cols<kDW>((which == 0 ? tdV : tdK) + lane_off + part * kDW, a);
       tmem_wait_ld();
-      red_tile_32x32(stg, lane, a, (which == 0 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)kvh * p.D + half * 32, p.dkv_ld,
-                     k0 + qd * 32, p.L, p.D - half * 32);
+      red_tile_32xW<kDW>(stg, lane, a, (which == 0 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)kvh * p.D + part * kDW, p.dkv_ld,
+                         k0 + qd * 32, p.L, p.D - part * kDW);
     }
   }
 
@@ -435,7 +456,7 @@ extern "C" int of_attn_bwd(const of_attn_args* a, void* stream_) {
   p.delta = a->delta;
   p.dq = a->dq; p.dq_ld = a->dq_ld; p.dq_bs = a->dq_batch_stride;
   p.dk = a->dk; p.dv = a->dv; p.dkv_ld = a->dkv_ld; p.dkv_bs = a->dkv_batch_stride;
-  size_t smem_bytes = 1024 + kTile * 10 + 8 * 4096 + 256;
+  size_t smem_bytes = 1024 + kTile * 10 + kSoftWarps * 4096 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     OF_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
