@@ -241,6 +241,8 @@ class ParamStore:
         self.touched = set()
         self.param_epoch = 0         # bumped by optimizers that update parameters through raw pointers (osufusion_b200/optim.py)
         self.pack_plan = None
+        self._film_heads = None
+        self._n_adapters = None
         self.film_plans = {}
         # set by ddp.GradAllReducer
         self.on_backward_begin = None
@@ -376,15 +378,19 @@ class ParamStore:
 
     def refresh_operands(self, unet) -> None:
         plan = self.pack_plan
+        n_params = sum(1 for _ in unet.parameters())          # adapter injection / merge_and_unload changes the parameter count
+        if self._n_adapters is None or self._n_adapters[0] != n_params:
+            self._n_adapters = (n_params, sum(1 for m in unet.modules() if hasattr(m, "base_layer")))
+        n_adapters = self._n_adapters[1]
         if plan is not None:
             ptrs = tuple(p.data_ptr() for _, ps, _ in plan["views"] for p in ps)
-            if ptrs != plan["ptrs"] or plan.get("n_adapters") != sum(1 for m in unet.modules() if hasattr(m, "base_layer")):
+            if ptrs != plan["ptrs"] or plan.get("n_adapters") != n_adapters:
                 plan = None
         if plan is None:
             plan = self.pack_plan = self._build_pack_plan(unet)
             if plan is None:
                 return
-            plan["n_adapters"] = sum(1 for m in unet.modules() if hasattr(m, "base_layer"))
+            plan["n_adapters"] = n_adapters
         vers = tuple(p._version for _, ps, _ in plan["views"] for p in ps) + (self.param_epoch,)
         if not self.refresh and vers == plan["vers"]:
             return
@@ -398,7 +404,9 @@ class ParamStore:
         """Descriptor tables of every `ResidualBlock.mlp[1]` head for batch size B (device-resident, built once)."""
         key = (B, with_grads)
         plan = self.film_plans.get(key)
-        heads = [m for m in unet.modules() if type(m).__name__ == "ResidualBlock" and m.mlp is not None]
+        heads = self._film_heads
+        if heads is None:        # the module tree is static (adapter injection never touches the FiLM heads)
+            heads = self._film_heads = [m for m in unet.modules() if type(m).__name__ == "ResidualBlock" and m.mlp is not None]
         if not heads:
             return None
         ptrs = tuple(h.mlp[1].weight.data_ptr() for h in heads) + (self.arena.data_ptr() if (with_grads and self.arena is not None) else 0,)
