@@ -60,3 +60,14 @@ def test_state_dict_layout_matches_oracle():
     a, b = UNet(6, 96, 5, **TINY).state_dict(), OracleUNet(6, 96, 5, **TINY).state_dict()
     assert list(a.keys()) == list(b.keys())
     assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+
+
+def test_host_side_helpers_run_without_a_gpu():
+    """Entry points that only touch host state: SM limit for the data-parallel overlap, grouped-kernel sizing helpers."""
+    from osufusion_b200 import _native
+    lib = _native.lib()
+    assert lib.of_set_sm_limit(132) == 0 and lib.of_set_sm_limit(0) == 0
+    assert lib.of_film_chunk_rows() > 0
+    assert lib.of_pack_seg_ctas(512, 512, 3, 512) == 512 and lib.of_pack_seg_ctas(1024, 512, 1, 512) == 128
+    assert lib.of_pack_seg_ctas(8, 8, 15, 8) == -1            # wide kernels use the per-tensor path
+    assert lib.of_opt_tensor_ctas(4097) == 2

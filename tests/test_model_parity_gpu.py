@@ -254,11 +254,15 @@ def test_gradient_accumulation_without_zero_grad():
     live = [k for k in g1 if not k.endswith("se.to_k.bias") and g1[k].abs().max() > 1e-9]   # to_k.bias: true gradient is zero
     assert len(live) > 300
     bwd()                                   # no zero_grad: accumulate
-    for k, p in new.named_parameters():
-        if k in live:
-            assert nrel(p.grad, 2 * g1[k]) < 3e-2, k
+
+    def compare(scale):
+        # the engine's fp32 atomics make gradients differ slightly from run to run (cancellation-dominated reductions by up to a
+        # few percent): nearly all tensors must agree to 3e-2, none may be off by more than 0.15 -- a missed accumulation is off by 0.5
+        errs = {k: nrel(p.grad, scale * g1[k]) for k, p in new.named_parameters() if k in live}
+        assert max(errs.values()) < 0.15, max(errs.items(), key=lambda kv: kv[1])
+        assert sum(e > 3e-2 for e in errs.values()) <= max(1, len(errs) // 100), sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+
+    compare(2.0)
     new.zero_grad(set_to_none=True)
     bwd()
-    for k, p in new.named_parameters():
-        if k in live:
-            assert nrel(p.grad, g1[k]) < 3e-2, k
+    compare(1.0)
