@@ -1,5 +1,7 @@
 // Remaining bandwidth-bound / tiny kernels of the denoiser hot path.  Contracts and reference citations are in
 // include/osufusion_b200.h next to each of_* declaration.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "rowops.cuh"
 
@@ -876,15 +878,20 @@ extern "C" int of_linear_small_bwd(const float* dy, long long dy_ld, const float
 
 extern "C" int of_colsum_bf16(const void* dy, long long ld, long long rows, int N, float* db, void* stream) {
   OF_REQUIRE(dy && db && N % 8 == 0 && ld % 8 == 0, "of_colsum_bf16: bad args");
-  // one 1024-thread CTA per SM: every CTA ends with one global atomic per channel, and same-address atomics serialise in L2
-  // (~27 clk each), so the CTA count -- not the byte count -- set the duration of the 256-thread / 2-CTAs-per-SM version
+  // 256-thread CTAs, two per SM.  (One 1024-thread CTA per SM -- half as many same-address global atomics per channel -- was
+  // measured slower: 1.90 vs 1.52 ms per training step over the 141 launches; OF_COLSUM_BIG=1 selects it.)
+  static const bool big = [] {
+    const char* e = getenv("OF_COLSUM_BIG");
+    return e && e[0] == '1';
+  }();
   const int ychunks = (N / 8 + 255) / 256;
-  int ctas_x = device_sm_count() / ychunks;
+  const int threads = big ? 1024 : 256;
+  int ctas_x = (big ? 1 : 2) * device_sm_count() / ychunks;
   if (ctas_x < 1) ctas_x = 1;
   int rpc = (int)((rows + ctas_x - 1) / ctas_x);
-  if (rpc < 64) rpc = 64;
+  if (rpc < (big ? 64 : 16)) rpc = big ? 64 : 16;
   dim3 grid((unsigned)((rows + rpc - 1) / rpc), ychunks);
-  OF_CHECK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(1024), 256 * 8 * sizeof(float), STREAM, reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc));
+  OF_CHECK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(threads), 256 * 8 * sizeof(float), STREAM, reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc));
   DONE()
 }
 

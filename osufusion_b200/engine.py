@@ -11,6 +11,7 @@ fp32 accumulation, fp32 residual stream, fp32 norms; rounding points of the refe
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -19,6 +20,8 @@ from . import _native as N
 from . import ops_raw as R
 
 BF16, F32, F64 = torch.bfloat16, torch.float32, torch.float64
+# GlobalContext forward: one-pass online-softmax pooling (of_rb_logit_pool) vs logits / softmax / pooling as three launches
+GCTX_FUSED = os.environ.get("OF_GCTX_FUSED", "1") != "0"
 
 
 def _p(t):
@@ -766,11 +769,18 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
     a2.mode = 0
     a2.vec, a2.vec_bs, a2.vec_bias = wk.data_ptr(), 0, se.to_k.bias.data_ptr()
     a2.out_rows = p.data_ptr()
-    pooled = empty((B, Cout), F32, dev)
-    nparts = N.lib().of_rb_pool_parts(C.byref(a2))
-    part = empty((B, nparts, Cout + 2), F32, dev)
-    N.call("of_rb_logit_pool", C.byref(a2), part.data_ptr(), pooled.data_ptr())   # logits -> softmax -> pooled in one pass over y2
-    a2.p = p.data_ptr()
+    if GCTX_FUSED:
+        pooled = empty((B, Cout), F32, dev)
+        nparts = N.lib().of_rb_pool_parts(C.byref(a2))
+        part = empty((B, nparts, Cout + 2), F32, dev)
+        N.call("of_rb_logit_pool", C.byref(a2), part.data_ptr(), pooled.data_ptr())   # logits -> softmax -> pooled in one pass over y2
+        a2.p = p.data_ptr()
+    else:
+        N.call("of_rb_rowdot", C.byref(a2))
+        N.call("of_softmax_rows", _p(p), B, L)
+        pooled = zeros((B, Cout), F32, dev)
+        a2.p, a2.acc_bc = p.data_ptr(), pooled.data_ptr()
+        N.call("of_rb_pool", C.byref(a2))
     Wa, Wb = se.layers[0].weight, se.layers[2].weight
     g1, g1pre = linear_small_fwd(pooled, Wa.view(Wa.shape[0], -1), se.layers[0].bias, act=1, want_pre=True)
     gate, gatepre = linear_small_fwd(g1, Wb.view(Wb.shape[0], -1), se.layers[2].bias, act=2, want_pre=True)
