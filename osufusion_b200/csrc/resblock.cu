@@ -327,32 +327,44 @@ __global__ void __launch_bounds__(kRbThreads, 2) rb_logit_pool_kernel(const of_r
   }
 }
 
-// one CTA per sample: combine the per-CTA records -> pooled[C] (fp32) and logits -> probabilities in place
-__global__ void __launch_bounds__(1024) rb_pool_finish_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ rows,
-                                                              int L, float* __restrict__ pooled) {
+// gridDim.y CTAs per sample: combine the per-CTA records -> pooled[C] (fp32) and logits -> probabilities in place.  Every CTA
+// recomputes the (cheap) global max / normaliser and owns a slice of the channels and of the rows; the record loop keeps four
+// independent loads in flight (the first version, one CTA per sample with a serial loop, took 17 us).
+__global__ void __launch_bounds__(256) rb_pool_finish_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ rows,
+                                                             int L, float* __restrict__ pooled) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sm[32];
   __shared__ float s_scale[1024];
   const float* pb = part + (long long)blockIdx.x * nparts * (C + 2);
+  const int stride = C + 2;
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < nparts; i += blockDim.x) mx = fmaxf(mx, pb[(long long)i * (C + 2) + C]);
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) mx = fmaxf(mx, pb[(long long)i * stride + C]);
   mx = block_max(mx, sm);
   float zz = 0.f;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
-    const float sc = __expf(pb[(long long)i * (C + 2) + C] - mx);
+    const float sc = __expf(pb[(long long)i * stride + C] - mx);
     s_scale[i] = sc;
-    zz += sc * pb[(long long)i * (C + 2) + C + 1];
+    zz += sc * pb[(long long)i * stride + C + 1];
   }
   zz = block_sum(zz, sm);       // (contains the barriers that publish s_scale)
   const float inv = 1.0f / zz;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < nparts; ++i) s = fmaf(s_scale[i], pb[(long long)i * (C + 2) + c], s);
-    pooled[(long long)blockIdx.x * C + c] = s * inv;
+  const int c_per = (C + gridDim.y - 1) / gridDim.y, c0 = blockIdx.y * c_per, c1 = min(c0 + c_per, C);
+  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = 0;
+    for (; i + 3 < nparts; i += 4) {
+      const float v0 = pb[(long long)i * stride + c], v1 = pb[(long long)(i + 1) * stride + c];
+      const float v2 = pb[(long long)(i + 2) * stride + c], v3 = pb[(long long)(i + 3) * stride + c];
+      s0 = fmaf(s_scale[i], v0, s0); s1 = fmaf(s_scale[i + 1], v1, s1);
+      s2 = fmaf(s_scale[i + 2], v2, s2); s3 = fmaf(s_scale[i + 3], v3, s3);
+    }
+    for (; i < nparts; ++i) s0 = fmaf(s_scale[i], pb[(long long)i * stride + c], s0);
+    pooled[(long long)blockIdx.x * C + c] = ((s0 + s1) + (s2 + s3)) * inv;
   }
+  const int l_per = (L + gridDim.y - 1) / gridDim.y, l0 = blockIdx.y * l_per, l1 = min(l0 + l_per, L);
   float* r = rows + (long long)blockIdx.x * L;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] = __expf(r[i] - mx) * inv;
+  for (int i = l0 + threadIdx.x; i < l1; i += blockDim.x) r[i] = __expf(r[i] - mx) * inv;
 }
 
 // one CTA per sample: da = p * (rd - sum_l p*rd) in place on rd   (softmax backward with the fp32 probabilities)
@@ -735,7 +747,7 @@ extern "C" int of_rb_logit_pool(const of_rb_args* a, float* part, float* pooled,
   OF_CHECK_CUDA(launch_pdl(rb_logit_pool_kernel, grid, dim3(rb_threads(a)), ((size_t)a->C + rpc + 2) * sizeof(float),
                            reinterpret_cast<cudaStream_t>(stream), *a, rpc, part));
   count_launch();
-  OF_CHECK_CUDA(launch_pdl(rb_pool_finish_kernel, dim3(a->B), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream),
+  OF_CHECK_CUDA(launch_pdl(rb_pool_finish_kernel, dim3(a->B, 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
                            (const float*)part, (int)grid.x, a->C, a->out_rows, a->L, pooled));
   count_launch();
   return OF_OK;
