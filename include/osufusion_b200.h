@@ -249,6 +249,10 @@ int of_linear_small_bwd(const float* dy, long long dy_ld, const float* ypre, int
                         int N, int K, const float* W, long long w_ld, int round_bf16, float* dW, float* dbias, float* dx,
                         long long dx_ld, int accumulate, void* stream);
 int of_colsum_bf16(const void* dy, long long ld, long long rows, int N, float* db, void* stream);
+/* out[n] += sum_rows dy[row,n] * (y[row,n] - bias[n]): the DoRA magnitude gradient taken from the activations,
+ * d mag[co] = sum_l dy[l,co] * conv(x, V)[l,co] / ||V_co|| = sum_l dy * (y - b) / mag   (lora_layers.py:76-90 with the norm detached). */
+int of_coldot_bf16(const void* dy, long long dy_ld, const void* y, long long y_ld, long long rows, int N, const float* bias, float* out,
+                   void* stream);
 int of_pack_input(const float* x, const float* noise, const float* ca, const float* cb, int B, int C, int N, void* out, int Lp,
                   int Cp, float pad_value, void* stream);
 int of_unpack_output(const void* y, long long ld, long long bs, int B, int C, int N, float* out, void* stream);
@@ -284,6 +288,13 @@ int of_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
  * ------------------------------------------------------------------------------------------------ */
 int of_dora_merge(const float* W, const float* A, const float* B, const float* mag, float scaling, int Cout, int Cin, int k, int r,
                   float* n2_ws, void* packed_bf16, int Cin_pad, long long tap_stride, float* s_out, void* stream);
+/* Rank-r backward glue (no full weight gradient of the frozen base; see engine._adapter_backward_rank_r):
+ *   of_dora_rankr_prep   : rowscale[co] = scaling * s[co] (s = mag / sqrt(n2), 1 without magnitude);  Bst[j][co] = bf16(rowscale[co] * B[co][j])
+ *   of_dora_rankr_finish : gB[co][j] += rowscale[co] * dBraw[co][j];  gmag[co] += dm[co] / mag[co] */
+int of_dora_rankr_prep(const float* B, const float* mag, const float* n2, float scaling, int Cout, int r, void* Bst_bf16,
+                       float* rowscale, void* stream);
+int of_dora_rankr_finish(const float* dBraw, const float* rowscale, float* gB, const float* dm, const float* mag, float* gmag, int Cout,
+                         int r, void* stream);
 int of_dora_grad(const float* W, const float* A, const float* B, const float* mag, float scaling, int Cout, int Cin, int k, int r,
                  const float* n2, const float* dW_packed, int Cin_pad, long long tap_stride, float* dA, float* dB, float* dmag,
                  void* stream);

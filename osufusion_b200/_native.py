@@ -110,6 +110,7 @@ _SIGS = {
     "of_linear_small_fwd": [P, LL, I, I, I, P, LL, P, I, I, P, LL, P, P],
     "of_linear_small_bwd": [P, LL, P, I, P, LL, I, I, I, P, LL, I, P, P, P, LL, I, P],
     "of_colsum_bf16": [P, LL, LL, I, P, P],
+    "of_coldot_bf16": [P, LL, P, LL, LL, I, P, P, P],
     "of_pack_input": [P, P, P, P, I, I, I, P, I, I, F, P],
     "of_unpack_output": [P, LL, LL, I, I, I, P, P],
     "of_upsample2x_fwd": [P, LL, LL, I, I, I, P, LL, LL, P],
@@ -128,6 +129,8 @@ _SIGS = {
     "of_pack_weights": [P, I, I, P],
     "of_grad_sumsq": [P, LL, P, P],
     "of_adamw_step": [P, I, I, P, P, P, P, F, F, F, F, F, F, I, P],
+    "of_dora_rankr_prep": [P, P, P, F, I, I, P, P, P],
+    "of_dora_rankr_finish": [P, P, P, P, P, P, I, I, P],
     "of_dora_merge": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P],
     "of_dora_grad": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P, P, P],
 }

@@ -269,6 +269,28 @@ __global__ void __launch_bounds__(kDoraE) dora_grad_kernel(const DoraArgs a, con
   }
 }
 
+// ---- rank-r backward helpers (engine._adapter_backward_rank_r): the tiny per-module glue as two launches instead of ~10 torch ops
+// rowscale[co] = scaling * s[co];  Bst[j][co] = bf16(rowscale[co] * B[co][j])   (the [N = r][K = Cout] operand of e = dy @ (s B))
+__global__ void dora_rankr_prep_kernel(const float* __restrict__ B, const float* __restrict__ mag, const float* __restrict__ n2,
+                                       float scaling, int Cout, int r, __nv_bfloat16* __restrict__ Bst, float* __restrict__ rowscale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * r) return;
+  const int j = idx / Cout, co = idx - j * Cout;        // consecutive threads -> consecutive co: coalesced Bst stores
+  const float rs = scaling * (mag ? mag[co] * rsqrtf(n2[co]) : 1.0f);
+  Bst[(long long)j * Cout + co] = __float2bfloat16_rn(rs * B[(long long)co * r + j]);
+  if (j == 0) rowscale[co] = rs;
+}
+// gB[co][j] += rowscale[co] * dBraw[co][j];  gmag[co] += dm[co] / mag[co]
+__global__ void dora_rankr_finish_kernel(const float* __restrict__ dBraw, const float* __restrict__ rowscale, float* __restrict__ gB,
+                                         const float* __restrict__ dm, const float* __restrict__ mag, float* __restrict__ gmag, int Cout,
+                                         int r) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * r) return;
+  const int co = idx / r, j = idx - co * r;
+  gB[idx] += rowscale[co] * dBraw[idx];
+  if (j == 0 && mag) gmag[co] += dm[co] / mag[co];
+}
+
 // output-channel range per CTA: at most ONE wave of CTAs (register use allows one CTA per SM; a CTA pays a fixed ~2 us for its A
 // tile), each walking its range 16 channels at a time
 static dim3 dora_grid(int E, int Cout, int* co_per_cta) {
@@ -336,6 +358,29 @@ extern "C" int of_dora_grad(const float* W, const float* A, const float* B, cons
   dim3 grid = dora_grid(E, Cout, &co_per_cta);
   size_t smem = ((size_t)r * kDoraEP + (size_t)co_per_cta * r + (size_t)kDoraCo * kDoraEP + kDoraCo) * sizeof(float);
   dora_grad_kernel<<<grid, kDoraE, smem, stream>>>(a, n2, dW_packed, tap_stride, dA, dB, dmag, co_per_cta);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
+
+extern "C" int of_dora_rankr_prep(const float* B, const float* mag, const float* n2, float scaling, int Cout, int r, void* Bst_bf16,
+                                  float* rowscale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(B && Bst_bf16 && rowscale && Cout >= 1 && r >= 1 && (!mag || n2), "of_dora_rankr_prep: bad args");
+  const int n = Cout * r;
+  dora_rankr_prep_kernel<<<(n + 255) / 256, 256, 0, stream>>>(B, mag, n2, scaling, Cout, r, reinterpret_cast<__nv_bfloat16*>(Bst_bf16),
+                                                              rowscale);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
+
+extern "C" int of_dora_rankr_finish(const float* dBraw, const float* rowscale, float* gB, const float* dm, const float* mag, float* gmag,
+                                    int Cout, int r, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(dBraw && rowscale && gB && Cout >= 1 && r >= 1 && (!mag || (dm && gmag)), "of_dora_rankr_finish: bad args");
+  const int n = Cout * r;
+  dora_rankr_finish_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dBraw, rowscale, gB, dm, mag, gmag, Cout, r);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

@@ -480,6 +480,48 @@ __global__ void __launch_bounds__(1024) colsum_bf16_kernel(const __nv_bfloat16* 
   for (int c = threadIdx.x; c < vecs * 8; c += blockDim.x) atomicAdd(db + (long long)v0 * 8 + c, s_cs[c]);
 }
 
+// out[n] += sum_rows dy[row, n] * (y[row, n] - bias[n])   (DoRA magnitude gradient from activations: d mag = this / mag)
+__global__ void __launch_bounds__(256) coldot_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld,
+                                                          const __nv_bfloat16* __restrict__ y, long long y_ld, long long rows, int N,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_cs[];  // [min(vecs,256) * 8]
+  const int vecs_total = N >> 3;
+  const int v0 = blockIdx.y * 256;
+  const int vecs = min(256, vecs_total - v0);
+  const int rpar = blockDim.x / vecs;
+  const int vi = threadIdx.x % vecs, rsub = threadIdx.x / vecs;
+  const bool active = rsub < rpar;
+  for (int c = threadIdx.x; c < vecs * 8; c += blockDim.x) s_cs[c] = 0.f;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, rows);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    const long long c0 = (long long)(v0 + vi) * 8;
+    V8 bz;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bz.v[j] = bias ? bias[c0 + j] : 0.f;
+    long long r = r0 + rsub;
+    for (; r + rpar < r1; r += 2 * rpar) {
+      V8 d0 = ld_bf16x8(dy + r * dy_ld + c0), y0 = ld_bf16x8(y + r * y_ld + c0);
+      V8 d1 = ld_bf16x8(dy + (r + rpar) * dy_ld + c0), y1 = ld_bf16x8(y + (r + rpar) * y_ld + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += d0.v[j] * (y0.v[j] - bz.v[j]) + d1.v[j] * (y1.v[j] - bz.v[j]);
+    }
+    for (; r < r1; r += rpar) {
+      V8 d0 = ld_bf16x8(dy + r * dy_ld + c0), y0 = ld_bf16x8(y + r * y_ld + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += d0.v[j] * (y0.v[j] - bz.v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_cs[vi * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < vecs * 8; c += blockDim.x) atomicAdd(out + (long long)v0 * 8 + c, s_cs[c]);
+}
+
 // =================================================================================================== layout / elementwise
 // (B, C, N) fp32 channel-first -> (B, Lp, Cp) bf16 channels-last; out = bf16(ca[b]*x + cb[b]*noise) for l < N, pad_value for
 // N <= l < Lp (channels >= C are zero).
@@ -892,6 +934,21 @@ extern "C" int of_colsum_bf16(const void* dy, long long ld, long long rows, int 
   if (rpc < (big ? 64 : 16)) rpc = big ? 64 : 16;
   dim3 grid((unsigned)((rows + rpc - 1) / rpc), ychunks);
   OF_CHECK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(threads), 256 * 8 * sizeof(float), STREAM, reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows, N, db, rpc));
+  DONE()
+}
+
+extern "C" int of_coldot_bf16(const void* dy, long long dy_ld, const void* y, long long y_ld, long long rows, int N, const float* bias,
+                              float* out, void* stream) {
+  OF_REQUIRE(dy && y && out && N % 8 == 0 && dy_ld % 8 == 0 && y_ld % 8 == 0, "of_coldot_bf16: bad args");
+  const int ychunks = (N / 8 + 255) / 256;
+  int ctas_x = 2 * device_sm_count() / ychunks;
+  if (ctas_x < 1) ctas_x = 1;
+  int rpc = (int)((rows + ctas_x - 1) / ctas_x);
+  if (rpc < 16) rpc = 16;
+  dim3 grid((unsigned)((rows + rpc - 1) / rpc), ychunks);
+  OF_CHECK_CUDA(launch_pdl(coldot_bf16_kernel, dim3(grid), dim3(256), 256 * 8 * sizeof(float), STREAM,
+                           reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(y), y_ld, rows, N, bias,
+                           out, rpc));
   DONE()
 }
 

@@ -22,6 +22,8 @@ from . import ops_raw as R
 BF16, F32, F64 = torch.bfloat16, torch.float32, torch.float64
 # GlobalContext forward: one-pass online-softmax pooling (of_rb_logit_pool) vs logits / softmax / pooling as three launches
 GCTX_FUSED = os.environ.get("OF_GCTX_FUSED", "1") != "0"
+# LoRA / DoRA backward through the rank-r activations (no full weight gradient of the frozen base) vs full wgrad + projection
+LORA_RANK_R = os.environ.get("OF_LORA_RANK_R", "1") != "0"
 
 
 def _p(t):
@@ -629,10 +631,71 @@ def _dora_backward(store: ParamStore, ad, dW_packed: torch.Tensor, cin_pad: int,
            tap_stride, store.grad(A).data_ptr(), store.grad(Bm).data_ptr(), _p(store.grad(mag)) if mag is not None else None)
 
 
-def _wgrad_conv_mod(store: ParamStore, conv, dy16, x16, taps, shift0):
+def _coldot(dy16: torch.Tensor, y16: torch.Tensor, bias, out: torch.Tensor) -> None:
+    """out[n] += sum over all rows of dy[., n] * (y[., n] - bias[n]) on (B, L, N) bf16 views."""
+    B, L, Nn = dy16.shape
+    d_bs, d_ld = _bl(dy16)
+    y_bs, y_ld = _bl(y16)
+    if B > 1 and (d_bs != L * d_ld or y_bs != L * y_ld):
+        for b in range(B):
+            N.call("of_coldot_bf16", _p(dy16[b]), d_ld, _p(y16[b]), y_ld, L, Nn, _p(bias), _p(out))
+    else:
+        N.call("of_coldot_bf16", _p(dy16), d_ld, _p(y16), y_ld, B * L, Nn, _p(bias), _p(out))
+
+
+def _adapter_backward_rank_r(store: ParamStore, ad, dy16, x16, y16, taps, shift0):
+    """Adapter gradients WITHOUT the full weight gradient: every term goes through the rank-r activations, on the tensor cores
+    (the frozen base weight needs no gradient; the reference gets the same structure from autograd, lora_layers.py:80-90):
+        u  = conv(x, A)                                  (B, L, r)        -- what `lora_A(x)` is in the reference
+        dB = scaling * s (.) (dy^T u)                    (Cout, r)
+        e  = dy @ (scaling * s (.) B)                    (B, L, r)
+        dA = e^T * x   (a rank-r conv weight gradient)   (r, Cin, k)
+        d mag = sum_l dy (y - b) / mag                   (Cout)           -- y = s (.) conv(x, V) + b is the saved layer output
+    s = mag / ||W + scaling B A|| (detached; 1 for plain LoRA)."""
+    base = ad.base_layer
+    W = base.weight
+    Cout, Cin = W.shape[0], W.shape[1]
+    k = W.shape[2] if W.dim() == 3 else 1
+    r, sc, dev = ad.r, float(ad.scaling), dy16.device
+    A, Bm, mag = ad.lora_A["default"].weight, ad.lora_B["default"].weight, ad.magnitude()
+    cp = (Cin + 7) // 8 * 8
+    Bsz, L = x16.shape[0], x16.shape[1]
+    n2 = store.dora_n2(ad) if mag is not None else None
+    # scaled B^T operand and the per-row factor scaling * s in one tiny launch
+    Bst = empty((r, Cout), BF16, dev)
+    rowscale = empty((Cout,), F32, dev)
+    N.call("of_dora_rankr_prep", _p(Bm), _p(mag), _p(n2), sc, Cout, r, _p(Bst), _p(rowscale))
+    # u = conv(x, A): A packed like any conv weight
+    Apk = (zeros if cp != Cin else empty)((k, r, cp), BF16, dev)
+    N.call("of_pack_conv_weight", _p(A), r, Cin, k, _p(Apk), cp, 0, k)
+    u = empty((Bsz, L, r), BF16, dev)
+    R.gemm_fwd(x16, Apk, N_out=r, K=cp, taps=k, shift0=shift0, shift_step=1 if k > 1 else 0, out_bf16=u)
+    # dB_raw = dy^T u
+    dBraw = zeros((1, Cout, r), F32, dev)
+    R.gemm_wgrad(dy16, u, dBraw, M=Cout, N_out=r)
+    # e = dy @ (scaling * s (.) B): B operand [N = r][K = Cout], K-major
+    e = empty((Bsz, L, r), BF16, dev)
+    R.gemm_fwd(dy16, Bst.view(1, r, Cout), N_out=r, K=Cout, out_bf16=e)
+    # dA = e^T * x
+    tmp = zeros((k, r, cp), F32, dev)
+    R.gemm_wgrad(e, x16, tmp, M=r, N_out=cp, taps=taps, shift0=shift0, shift_step=1 if k > 1 else 0)
+    acc = 0 if store.touch(A) else 1
+    N.call("of_unpack_conv_wgrad", _p(tmp), r, Cin, k, cp, 0, _p(store.grad(A)), acc, 0)
+    # d magnitude from the activations, then dB / d mag accumulated into the arena
+    dm = None
+    if mag is not None:
+        dm = zeros((Cout,), F32, dev)
+        _coldot(dy16, y16, base.bias, dm)
+    N.call("of_dora_rankr_finish", _p(dBraw), _p(rowscale), _p(store.grad(Bm)), _p(dm), _p(mag),
+           _p(store.grad(mag)) if mag is not None else None, Cout, r)
+
+
+def _wgrad_conv_mod(store: ParamStore, conv, dy16, x16, taps, shift0, y16=None):
     ad = _adapter(conv)
     if ad is None:
         return _wgrad_conv(store, conv.weight, dy16, x16, taps, shift0)
+    if LORA_RANK_R and (y16 is not None or not ad.use_dora) and ad.r % 8 == 0:
+        return _adapter_backward_rank_r(store, ad, dy16, x16, y16, taps, shift0)
     Cout, Cin, k = ad.base_layer.weight.shape
     cp = (Cin + 7) // 8 * 8
     tmp = zeros((k, Cout, cp), F32, dy16.device)
@@ -640,10 +703,12 @@ def _wgrad_conv_mod(store: ParamStore, conv, dy16, x16, taps, shift0):
     _dora_backward(store, ad, tmp, cp, Cout * cp)
 
 
-def _wgrad_linear_mod(store: ParamStore, lin, dy16, x16):
+def _wgrad_linear_mod(store: ParamStore, lin, dy16, x16, y16=None):
     ad = _adapter(lin)
     if ad is None:
         return _wgrad_linear(store, lin.weight, dy16, x16)
+    if LORA_RANK_R and (y16 is not None or not ad.use_dora) and ad.r % 8 == 0:
+        return _adapter_backward_rank_r(store, ad, dy16, x16, y16, 1, 0)
     Nn, K = ad.base_layer.weight.shape
     tmp = zeros((1, Nn, K), F32, dy16.device)
     R.gemm_wgrad(dy16, x16, tmp, M=Nn, N_out=K)
@@ -721,9 +786,9 @@ def conv3(ctx: Ctx, x16, conv, *, stats=None, out=None):
     return y
 
 
-def conv3_bwd(ctx: Ctx, conv, x: Act, x16, dy16, need_dx=True, want_bf16=False, want_f32=True):
+def conv3_bwd(ctx: Ctx, conv, x: Act, x16, dy16, need_dx=True, want_bf16=False, want_f32=True, y16=None):
     Cout, Cin, k = _base(conv).weight.shape
-    _wgrad_conv_mod(ctx.store, conv, dy16, x16, taps=k, shift0=-(k // 2))
+    _wgrad_conv_mod(ctx.store, conv, dy16, x16, taps=k, shift0=-(k // 2), y16=y16)
     if need_dx:
         w = ctx.store.conv_w_mod(conv)
         return _dgrad_into(x, dy16, w, N_out=Cin, K=Cout, taps=k, shift0=k // 2, shift_step=-1, b_ld=w.shape[2],
@@ -854,7 +919,7 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             N.call("of_rb_bwd_apply", C.byref(b2))
             # conv2 backward
             h1a = Act(None, h1)
-            dh1 = conv3_bwd(ctx, m.block2.proj, h1a, h1, dy2, want_bf16=True, want_f32=False)
+            dh1 = conv3_bwd(ctx, m.block2.proj, h1a, h1, dy2, want_bf16=True, want_f32=False, y16=y2)
             # GroupNorm-1 (+FiLM) backward
             b1 = _rb_args(B, L, Cout, y1, stats1, m.block1.norm, ss)
             b1.mode = 1
@@ -881,7 +946,7 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
                 _dgrad_into(x, dout16, st.linear_w(m.res_conv.weight), N_out=Cin, K=Cout)
             else:
                 x.add_grad(dout)
-            conv3_bwd(ctx, m.block1.proj, x, x16, dy1)
+            conv3_bwd(ctx, m.block1.proj, x, x16, dy1, y16=y1)
         ctx.tape.push(backward)
     return out
 
@@ -924,6 +989,9 @@ def transformer_block(ctx: Ctx, m, x: Act) -> Act:
     R.gemm_fwd(xn16, wqkv, N_out=HD + 2 * KD, K=Cc, out_bf16=qkv)
     ad_q = _adapter(at.to_q)
     rope_f32 = ad_q is not None and ad_q.use_dora
+    ad_kv = _adapter(at.to_kv)
+    need_pre = ctx.tape is not None and LORA_RANK_R and any(a_ is not None and a_.use_dora for a_ in (ad_q, ad_kv))
+    qkv_pre = qkv.clone() if need_pre else None    # the DoRA magnitude gradient needs the projection output before RoPE rotates it
     cosT, sinT = rope_tables(ctx, L, D, at.rotary_emb.scale_base, rope_f32)
     q_bs, q_ld = _bl(qkv)
     N.call("of_rope_fwd", _p(qkv), q_ld, q_bs, B, L, H, KVH, D, _p(cosT), _p(sinT), int(rope_f32))
@@ -980,8 +1048,8 @@ def transformer_block(ctx: Ctx, m, x: Act) -> Act:
                    _p(dqkv), o_ld, o_bs, B, L, H, KVH, D, _p(cosT), _p(sinT), int(rope_f32))
             # q/kv projections: d(xn) = residual grad (x2.grad) + dqkv W
             _dgrad_into(x2, dqkv, wqkv, N_out=Cc, K=HD + 2 * KD)
-            _wgrad_linear_mod(st, at.to_q, dqkv[:, :, :HD], xn16)
-            _wgrad_linear_mod(st, at.to_kv, dqkv[:, :, HD:], xn16)
+            _wgrad_linear_mod(st, at.to_q, dqkv[:, :, :HD], xn16, y16=None if qkv_pre is None else qkv_pre[:, :, :HD])
+            _wgrad_linear_mod(st, at.to_kv, dqkv[:, :, HD:], xn16, y16=None if qkv_pre is None else qkv_pre[:, :, HD:])
             # LayerNorm
             dxn = x2.grad
             assert dxn.stride(0) == L * dxn.stride(1)
