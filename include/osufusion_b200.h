@@ -295,6 +295,12 @@ int of_dora_rankr_prep(const float* B, const float* mag, const float* n2, float 
                        float* rowscale, void* stream);
 int of_dora_rankr_finish(const float* dBraw, const float* rowscale, float* gB, const float* dm, const float* mag, float* gmag, int Cout,
                          int r, void* stream);
+/* Tensor-core merge: V = W + scaling*B*A is an of_gemm call (M = Cout, N = Cin*k, K = r, fp32 W as aux_f32, fp32 V out);
+ *   of_dora_scale_pack      : per output channel n2 = ||V_co||^2, s = mag/sqrt(n2) (1 without mag), packed[t][co][ci] = bf16(s*V)
+ *   of_scale_cast_f32_bf16  : dst = bf16(scale * src)   (the scaling*B operand) */
+int of_dora_scale_pack(const float* V, const float* mag, int Cout, int Cin, int k, float* n2_out, void* packed_bf16, int cin_pad,
+                       long long tap_stride, void* stream);
+int of_scale_cast_f32_bf16(const float* src, float scale, void* dst, long long n, void* stream);
 int of_dora_grad(const float* W, const float* A, const float* B, const float* mag, float scaling, int Cout, int Cin, int k, int r,
                  const float* n2, const float* dW_packed, int Cin_pad, long long tap_stride, float* dA, float* dB, float* dmag,
                  void* stream);

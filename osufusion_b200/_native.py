@@ -131,6 +131,8 @@ _SIGS = {
     "of_adamw_step": [P, I, I, P, P, P, P, F, F, F, F, F, F, I, P],
     "of_dora_rankr_prep": [P, P, P, F, I, I, P, P, P],
     "of_dora_rankr_finish": [P, P, P, P, P, P, I, I, P],
+    "of_dora_scale_pack": [P, P, I, I, I, P, P, I, LL, P],
+    "of_scale_cast_f32_bf16": [P, F, P, LL, P],
     "of_dora_merge": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P],
     "of_dora_grad": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P, P, P],
 }

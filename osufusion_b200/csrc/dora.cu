@@ -291,6 +291,43 @@ __global__ void dora_rankr_finish_kernel(const float* __restrict__ dBraw, const 
   if (j == 0 && mag) gmag[co] += dm[co] / mag[co];
 }
 
+// ---- tensor-core merge: V = W + scaling * B A comes from of_gemm (K = r, fp32 W as residual); this kernel turns one row of V
+// into the GEMM operand: n2[co] = sum_e V^2, s = mag / sqrt(n2) (1 without magnitude), packed[t][co][ci] = bf16(s * V[co][ci*k + t]).
+// One CTA per output channel; the row (<= 8192 elements) stays in registers between the norm and the store.
+constexpr int kScalePackMaxPerThread = 32;
+__global__ void __launch_bounds__(256) dora_scale_pack_kernel(const float* __restrict__ V, const float* __restrict__ mag, int Cin, int k,
+                                                              float* __restrict__ n2_out, __nv_bfloat16* __restrict__ packed,
+                                                              int cin_pad, long long tap_stride) {
+  __shared__ float sm[32];
+  const int co = blockIdx.x;
+  const int E = Cin * k;
+  const float* row = V + (long long)co * E;
+  float v[kScalePackMaxPerThread];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kScalePackMaxPerThread; ++i) {
+    const int e = i * 256 + threadIdx.x;
+    v[i] = e < E ? row[e] : 0.f;
+    sq = fmaf(v[i], v[i], sq);
+  }
+  sq = block_sum(sq, sm);
+  if (threadIdx.x == 0 && n2_out) n2_out[co] = sq;
+  const float s = mag ? mag[co] * rsqrtf(sq) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < kScalePackMaxPerThread; ++i) {
+    const int e = i * 256 + threadIdx.x;
+    if (e < E) {
+      const int ci = e / k, t = e - ci * k;
+      packed[(long long)t * tap_stride + (long long)co * cin_pad + ci] = __float2bfloat16_rn(s * v[i]);
+    }
+  }
+}
+// dst = bf16(scale * src)
+__global__ void scale_cast_bf16_kernel(const float* __restrict__ src, float scale, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(scale * src[i]);
+}
+
 // output-channel range per CTA: at most ONE wave of CTAs (register use allows one CTA per SM; a CTA pays a fixed ~2 us for its A
 // tile), each walking its range 16 channels at a time
 static dim3 dora_grid(int E, int Cout, int* co_per_cta) {
@@ -381,6 +418,27 @@ extern "C" int of_dora_rankr_finish(const float* dBraw, const float* rowscale, f
   OF_REQUIRE(dBraw && rowscale && gB && Cout >= 1 && r >= 1 && (!mag || (dm && gmag)), "of_dora_rankr_finish: bad args");
   const int n = Cout * r;
   dora_rankr_finish_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dBraw, rowscale, gB, dm, mag, gmag, Cout, r);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
+
+extern "C" int of_dora_scale_pack(const float* V, const float* mag, int Cout, int Cin, int k, float* n2_out, void* packed_bf16, int cin_pad,
+                                  long long tap_stride, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(V && packed_bf16 && Cout >= 1 && Cin >= 1 && k >= 1 && cin_pad >= Cin, "of_dora_scale_pack: bad args");
+  OF_REQUIRE((long long)Cin * k <= 256LL * kScalePackMaxPerThread, "of_dora_scale_pack: row of %d x %d elements is too long", Cin, k);
+  dora_scale_pack_kernel<<<Cout, 256, 0, stream>>>(V, mag, Cin, k, n2_out, reinterpret_cast<__nv_bfloat16*>(packed_bf16), cin_pad,
+                                                    tap_stride);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
+
+extern "C" int of_scale_cast_f32_bf16(const float* src, float scale, void* dst, long long n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(src && dst && n >= 0, "of_scale_cast_f32_bf16: bad args");
+  if (n > 0) scale_cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, scale, reinterpret_cast<__nv_bfloat16*>(dst), n);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

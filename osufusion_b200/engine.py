@@ -24,6 +24,8 @@ BF16, F32, F64 = torch.bfloat16, torch.float32, torch.float64
 GCTX_FUSED = os.environ.get("OF_GCTX_FUSED", "1") != "0"
 # LoRA / DoRA backward through the rank-r activations (no full weight gradient of the frozen base) vs full wgrad + projection
 LORA_RANK_R = os.environ.get("OF_LORA_RANK_R", "1") != "0"
+# effective-weight merge W + scaling*B*A as a K = r tensor-core GEMM (+ a row-wise norm/scale/pack kernel) vs the CUDA-core kernel
+LORA_MERGE_TC = os.environ.get("OF_LORA_MERGE_TC", "1") != "0"
 
 
 def _p(t):
@@ -524,6 +526,19 @@ class ParamStore:
         k = W.shape[2] if W.dim() == 3 else 1
         A, Bm, mag = ad.lora_A["default"].weight, ad.lora_B["default"].weight, ad.magnitude()
         n2 = empty((Cout,), F32, W.device)
+        E = Cin * k
+        if LORA_MERGE_TC and ad.r % 8 == 0 and E % 8 == 0 and cin_pad == Cin and E <= 8192 and W.is_contiguous():
+            # V = W + scaling * B A on the tensor cores (K = r GEMM with the fp32 weight as residual), then norm + scale + pack per row
+            r = ad.r
+            A16 = empty((r, E), BF16, W.device)
+            N.call("of_cast_f32_bf16", _p(A), _p(A16), r * E)
+            B16 = empty((Cout, r), BF16, W.device)
+            N.call("of_scale_cast_f32_bf16", _p(Bm), float(ad.scaling), _p(B16), Cout * r)
+            V = empty((1, Cout, E), F32, W.device)
+            R.gemm_fwd(B16.view(1, Cout, r), A16.view(1, r, E), N_out=E, K=r, b_mn_major=True, aux_f32=W.detach().view(1, Cout, E),
+                       out_f32=V)
+            N.call("of_dora_scale_pack", _p(V), _p(mag), Cout, Cin, k, _p(n2), out_rows.data_ptr(), cin_pad, tap_stride)
+            return n2
         N.call("of_dora_merge", _p(W), _p(A), _p(Bm), _p(mag), float(ad.scaling), Cout, Cin, k, ad.r, _p(n2), out_rows.data_ptr(),
                cin_pad, tap_stride, None)
         return n2
