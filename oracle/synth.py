@@ -27,12 +27,14 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0) -> torch.Tenso
         return torch.randn(shape, generator=g)
     if leaf == "bias":
         return 0.05 * torch.randn(shape, generator=g)
-    if leaf == "weight" and len(shape) == 1:  # norm gains
+    if leaf == "gamma" or (leaf == "weight" and len(shape) == 1):  # norm gains (incl. the DiT / MMDiT per-head RMS-norm gamma)
         return 1.0 + 0.1 * torch.randn(shape, generator=g)
     fan_in = 1
     for s in shape[1:]:
         fan_in *= s
     std = 1.0 / (3.0 * max(fan_in, 1)) ** 0.5   # same second moment as torch's default kaiming-uniform(a=sqrt(5)) init
+    if key in ("postprocess.weight", "out.weight"):
+        std = 0.05  # zero-initialised 6-channel output convs of DiT / MMDiT (dit.py:250, mmdit.py:326): re-randomise likewise
     if "final_conv" in key:
         std = 0.05  # the reference zero-inits final_conv (unet.py:354), which makes parity vacuous: re-randomise
     return std * torch.randn(shape, generator=g)
