@@ -366,6 +366,36 @@ int of_adamw_step(const of_opt_tensor* table_dev, int num_tensors, int total_cta
                   float* exp_avg_sq, const double* sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * DiT / MMDiT backbones (osu_fusion/modules/dit.py, mmdit.py).  Their GEMMs, attention, adaLN LayerNorm
+ * (of_layernorm_* called per sample with gamma = 1 + scale_b, beta = shift_b: `modulate(norm(x), shift, scale)`, dit.py:13-15,150-152)
+ * and small conditioning MLPs reuse the entry points above; these cover what the UNet path has no counterpart for.
+ *   of_gate_residual_fwd : `x + gate.unsqueeze(1) * y` (dit.py:151-152, mmdit.py:199-204): out (B,L,C) fp32 residual stream =
+ *                          x (fp32 or bf16) + gate[b,:] * y (bf16); round_bf16 = the product is a bf16 x bf16 multiplication under
+ *                          autocast.  Bytes/element: 4 (or 2) + 2 read, 4 written.
+ *   of_gate_mul_bwd      : backward of the product: dx16 = bf16(d), dy16 = bf16(gate * d) for the incoming fp32 stream gradient d
+ *                          (both are GEMM / of_coldot_bf16 operands: d gate[b,c] = sum_l dx16 * y).  Bytes/element: 4 read, 4 written.
+ *   of_headnorm_fwd/bwd  : `MultiHeadRMSNorm` (dit.py:62-69, mmdit.py:55-62) = F.normalize(x, dim=-1) * gamma * sqrt(D) on the q and k
+ *                          heads of a fused [Hq*D q | Hk*D k | Hv*D v] projection row (bf16), v copied through; strided in/out views
+ *                          so the two modality streams of JointAttention (mmdit.py:98-129) are written straight into the joint
+ *                          [audio ; beatmap] sequence.  bwd takes the fp32 dq/dk/dv of of_attn_bwd and the PRE-norm projection, emits
+ *                          the bf16 [dq | dk | dv] operand and accumulates dgamma_q (Hq*D) / dgamma_k (Hk*D).
+ *   of_row_mean_std      : statistic audio pooling `cat([a.mean(-1), a.std(-1)])` (dit.py:279-282, mmdit.py:352-355) of the fp32
+ *                          (B, C, N) spectrogram -> (B, 2C) fp32 (unbiased std).
+ * ------------------------------------------------------------------------------------------------ */
+int of_gate_residual_fwd(const float* x32, const void* x16, long long x_ld, long long x_bs, const void* y16, long long y_ld,
+                         long long y_bs, const float* gate, long long gate_ld, int round_bf16, int B, int L, int C, float* out32,
+                         long long o_ld, long long o_bs, void* stream);
+int of_gate_mul_bwd(const float* dx32, long long d_ld, long long d_bs, const float* gate, long long gate_ld, int round_bf16, int B,
+                    int L, int C, void* dx16, void* dy16, long long o_ld, long long o_bs, void* stream);
+int of_headnorm_fwd(const void* in16, long long in_ld, long long in_bs, int B, int L, int Hq, int Hk, int Hv, int D,
+                    const float* gamma_q, const float* gamma_k, float scale, void* out16, long long o_ld, long long o_bs, void* stream);
+int of_headnorm_bwd(const float* dq, long long dq_ld, long long dq_bs, const float* dk, const float* dv, long long dkv_ld,
+                    long long dkv_bs, const void* in16, long long in_ld, long long in_bs, int B, int L, int Hq, int Hk, int Hv, int D,
+                    const float* gamma_q, const float* gamma_k, float scale, void* dqkv16, long long o_ld, long long o_bs,
+                    float* dgamma_q, float* dgamma_k, void* stream);
+int of_row_mean_std(const float* a, int B, int C, int N, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,288 @@
+// Bandwidth-bound kernels of the DiT / MMDiT backbones (reference osu_fusion/modules/dit.py, mmdit.py)
+// that the UNet path does not already provide: adaLN-Zero gated residual, per-head q/k RMS norm, audio statistics pooling.
+// Contracts and reference citations are in include/osufusion_b200.h next to each of_* declaration.
+#include "host_common.h"
+#include "rowops.cuh"
+
+namespace ofx {
+
+__device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// out[b,l,:] = x[b,l,:] + gate[b,:] * y[b,l,:]   (16-byte vectors; x fp32 or bf16)
+__global__ void __launch_bounds__(256) gate_residual_fwd_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16,
+                                                                long long x_ld, long long x_bs, const __nv_bfloat16* __restrict__ y16,
+                                                                long long y_ld, long long y_bs, const float* __restrict__ gate,
+                                                                long long gate_ld, int round_bf16, int B, int L, int C,
+                                                                float* __restrict__ out32, long long o_ld, long long o_bs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cv = C >> 3;
+  const long long total = (long long)B * L * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % cv);
+    const long long r = idx / cv;
+    const int l = (int)(r % L), b = (int)(r / L);
+    const V8 xv = x32 ? ld_f32x8(x32 + b * x_bs + (long long)l * x_ld + v * 8) : ld_bf16x8(x16 + b * x_bs + (long long)l * x_ld + v * 8);
+    const V8 yv = ld_bf16x8(y16 + b * y_bs + (long long)l * y_ld + v * 8);
+    const V8 g = ld_f32x8(gate + b * gate_ld + v * 8);
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p = g.v[j] * yv.v[j];
+      if (round_bf16) p = bf16r(p);
+      o.v[j] = xv.v[j] + p;
+    }
+    st_f32x8(out32 + b * o_bs + (long long)l * o_ld + v * 8, o);
+  }
+}
+
+// dx16 = bf16(dx);  dy16 = bf16(gate * dx)   (the product's incoming gradient is rounded to bf16 first when the forward product was)
+__global__ void __launch_bounds__(256) gate_mul_bwd_kernel(const float* __restrict__ dx32, long long d_ld, long long d_bs,
+                                                           const float* __restrict__ gate, long long gate_ld, int round_bf16, int B,
+                                                           int L, int C, __nv_bfloat16* __restrict__ dx16,
+                                                           __nv_bfloat16* __restrict__ dy16, long long o_ld, long long o_bs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cv = C >> 3;
+  const long long total = (long long)B * L * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % cv);
+    const long long r = idx / cv;
+    const int l = (int)(r % L), b = (int)(r / L);
+    const V8 d = ld_f32x8(dx32 + b * d_bs + (long long)l * d_ld + v * 8);
+    const V8 g = ld_f32x8(gate + b * gate_ld + v * 8);
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = g.v[j] * (round_bf16 ? bf16r(d.v[j]) : d.v[j]);
+    const long long off = b * o_bs + (long long)l * o_ld + v * 8;
+    st_bf16x8(dx16 + off, d);
+    st_bf16x8(dy16 + off, o);
+  }
+}
+
+// One thread per (row, head) of the fused [q | k | v] projection row: F.normalize(x, dim=-1) * gamma * sqrt(D) on the q and k heads
+// with the reference's bf16 rounding points (norm, quotient, result); v heads are copied.  kMaxVec 16-byte vectors per head.
+constexpr int kHeadVecs = 8;   // D <= 64
+
+__global__ void __launch_bounds__(256) headnorm_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long in_ld, long long in_bs, int B,
+                                                           int L, int Hq, int Hk, int Hv, int D, const float* __restrict__ gq,
+                                                           const float* __restrict__ gk, float scale,
+                                                           __nv_bfloat16* __restrict__ out, long long o_ld, long long o_bs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Ht = Hq + Hk + Hv, dv = D >> 3;
+  const long long total = (long long)B * L * Ht;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(idx % Ht);
+    const long long r = idx / Ht;
+    const int l = (int)(r % L), b = (int)(r / L);
+    const __nv_bfloat16* src = in + b * in_bs + (long long)l * in_ld + (long long)h * D;
+    __nv_bfloat16* dst = out + b * o_bs + (long long)l * o_ld + (long long)h * D;
+    V8 x[kHeadVecs];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHeadVecs; ++i)
+      if (i < dv) {
+        x[i] = ld_bf16x8(src + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += x[i].v[j] * x[i].v[j];
+      }
+    if (h >= Hq + Hk) {   // v: copy
+#pragma unroll
+      for (int i = 0; i < kHeadVecs; ++i)
+        if (i < dv) st_bf16x8(dst + i * 8, x[i]);
+      continue;
+    }
+    const float* g = h < Hq ? gq + (long long)h * D : gk + (long long)(h - Hq) * D;
+    const float n = fmaxf(bf16r(sqrtf(ss)), 1e-12f);
+#pragma unroll
+    for (int i = 0; i < kHeadVecs; ++i)
+      if (i < dv) {
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = (bf16r(x[i].v[j] / n) * g[i * 8 + j]) * scale;
+        st_bf16x8(dst + i * 8, o);
+      }
+  }
+}
+
+// Backward of the above (roundings treated as identity): with xh = x/|x|, dxh = dy * gamma * scale,
+//   dx = (dxh - xh <dxh, xh>) / |x|,   dgamma[h, d] += sum_rows dy * xh * scale.
+// dq/dk/dv arrive as fp32 (attention backward accumulates them atomically); the result is the bf16 [dq | dk | dv] GEMM operand.
+// gamma gradients: shared-memory accumulation per CTA (grid-stride rows), then one global atomic per element per CTA.
+__global__ void __launch_bounds__(256) headnorm_bwd_kernel(const float* __restrict__ dq, long long dq_ld, long long dq_bs,
+                                                           const float* __restrict__ dk, const float* __restrict__ dvp, long long dkv_ld,
+                                                           long long dkv_bs, const __nv_bfloat16* __restrict__ in, long long in_ld,
+                                                           long long in_bs, int B, int L, int Hq, int Hk, int Hv, int D,
+                                                           const float* __restrict__ gq, const float* __restrict__ gk, float scale,
+                                                           __nv_bfloat16* __restrict__ out, long long o_ld, long long o_bs,
+                                                           float* __restrict__ dgq, float* __restrict__ dgk) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_dg[];   // [(Hq + Hk) * D]
+  const int Ht = Hq + Hk + Hv, dv = D >> 3, ng = (Hq + Hk) * D;
+  for (int i = threadIdx.x; i < ng; i += blockDim.x) s_dg[i] = 0.f;
+  __syncthreads();
+  const long long total = (long long)B * L * Ht;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(idx % Ht);
+    const long long r = idx / Ht;
+    const int l = (int)(r % L), b = (int)(r / L);
+    __nv_bfloat16* dst = out + b * o_bs + (long long)l * o_ld + (long long)h * D;
+    const float* dsrc;
+    if (h < Hq) dsrc = dq + b * dq_bs + (long long)l * dq_ld + (long long)h * D;
+    else if (h < Hq + Hk) dsrc = dk + b * dkv_bs + (long long)l * dkv_ld + (long long)(h - Hq) * D;
+    else dsrc = dvp + b * dkv_bs + (long long)l * dkv_ld + (long long)(h - Hq - Hk) * D;
+    V8 d[kHeadVecs];
+#pragma unroll
+    for (int i = 0; i < kHeadVecs; ++i)
+      if (i < dv) d[i] = ld_f32x8(dsrc + i * 8);
+    if (h >= Hq + Hk) {   // v: cast
+#pragma unroll
+      for (int i = 0; i < kHeadVecs; ++i)
+        if (i < dv) st_bf16x8(dst + i * 8, d[i]);
+      continue;
+    }
+    const __nv_bfloat16* src = in + b * in_bs + (long long)l * in_ld + (long long)h * D;
+    const float* g = h < Hq ? gq + (long long)h * D : gk + (long long)(h - Hq) * D;
+    V8 x[kHeadVecs];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHeadVecs; ++i)
+      if (i < dv) {
+        x[i] = ld_bf16x8(src + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += x[i].v[j] * x[i].v[j];
+      }
+    const float n = fmaxf(sqrtf(ss), 1e-12f), rn = 1.0f / n;
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHeadVecs; ++i)
+      if (i < dv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = x[i].v[j] * rn;
+          const float dy = d[i].v[j];
+          atomicAdd(&s_dg[h * D + i * 8 + j], dy * xh * scale);
+          const float dxh = dy * g[i * 8 + j] * scale;
+          dot += dxh * xh;
+          x[i].v[j] = xh;
+          d[i].v[j] = dxh;
+        }
+      }
+#pragma unroll
+    for (int i = 0; i < kHeadVecs; ++i)
+      if (i < dv) {
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = (d[i].v[j] - x[i].v[j] * dot) * rn;
+        st_bf16x8(dst + i * 8, o);
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ng; i += blockDim.x) {
+    const float v = s_dg[i];
+    if (v != 0.f) atomicAdd(i < Hq * D ? dgq + i : dgk + (i - Hq * D), v);
+  }
+}
+
+// out[b, c] = mean_n a[b, c, n], out[b, C + c] = unbiased std_n a[b, c, n]; one CTA per (b, c) row, two passes (mean, then centred squares).
+__global__ void __launch_bounds__(256) row_mean_std_kernel(const float* __restrict__ a, int C, int N, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sm[32];
+  const int row = blockIdx.x, b = row / C, c = row % C;
+  const float* p = a + (long long)row * N;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += p[i];
+  const float mean = block_sum(s, sm) / N;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float dlt = p[i] - mean;
+    q += dlt * dlt;
+  }
+  q = block_sum(q, sm);
+  if (threadIdx.x == 0) {
+    out[(long long)b * 2 * C + c] = mean;
+    out[(long long)b * 2 * C + C + c] = sqrtf(q / (float)(N - 1));
+  }
+}
+
+static unsigned grid_for(long long total, int threads) {
+  long long need = (total + threads - 1) / threads;
+  long long cap = (long long)device_sm_count() * 8;
+  return (unsigned)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+}  // namespace ofx
+
+using namespace ofx;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+#define DONE()                        \
+  OF_CHECK_CUDA(cudaGetLastError()); \
+  count_launch();                    \
+  return OF_OK;
+
+extern "C" int of_gate_residual_fwd(const float* x32, const void* x16, long long x_ld, long long x_bs, const void* y16, long long y_ld,
+                                    long long y_bs, const float* gate, long long gate_ld, int round_bf16, int B, int L, int C,
+                                    float* out32, long long o_ld, long long o_bs, void* stream) {
+  OF_REQUIRE((x32 || x16) && y16 && gate && out32, "of_gate_residual_fwd: null pointer");
+  OF_REQUIRE(B >= 1 && L >= 1 && C >= 8 && C % 8 == 0, "of_gate_residual_fwd: C=%d must be a positive multiple of 8", C);
+  OF_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && o_ld % 4 == 0 && gate_ld % 4 == 0 && x_bs % 4 == 0 && y_bs % 8 == 0 && o_bs % 4 == 0,
+             "of_gate_residual_fwd: strides must keep 16-byte alignment");
+  OF_CHECK_CUDA(launch_pdl(gate_residual_fwd_kernel, dim3(grid_for((long long)B * L * (C / 8), 256)), dim3(256), 0, STREAM, x32,
+                           reinterpret_cast<const __nv_bfloat16*>(x16), x_ld, x_bs, reinterpret_cast<const __nv_bfloat16*>(y16), y_ld, y_bs,
+                           gate, gate_ld, round_bf16, B, L, C, out32, o_ld, o_bs));
+  DONE()
+}
+
+extern "C" int of_gate_mul_bwd(const float* dx32, long long d_ld, long long d_bs, const float* gate, long long gate_ld, int round_bf16,
+                               int B, int L, int C, void* dx16, void* dy16, long long o_ld, long long o_bs, void* stream) {
+  OF_REQUIRE(dx32 && gate && dx16 && dy16, "of_gate_mul_bwd: null pointer");
+  OF_REQUIRE(B >= 1 && L >= 1 && C >= 8 && C % 8 == 0, "of_gate_mul_bwd: C=%d must be a positive multiple of 8", C);
+  OF_REQUIRE(d_ld % 4 == 0 && d_bs % 4 == 0 && gate_ld % 4 == 0 && o_ld % 8 == 0 && o_bs % 8 == 0,
+             "of_gate_mul_bwd: strides must keep 16-byte alignment");
+  OF_CHECK_CUDA(launch_pdl(gate_mul_bwd_kernel, dim3(grid_for((long long)B * L * (C / 8), 256)), dim3(256), 0, STREAM, dx32, d_ld, d_bs, gate,
+                           gate_ld, round_bf16, B, L, C, reinterpret_cast<__nv_bfloat16*>(dx16), reinterpret_cast<__nv_bfloat16*>(dy16), o_ld,
+                           o_bs));
+  DONE()
+}
+
+extern "C" int of_headnorm_fwd(const void* in16, long long in_ld, long long in_bs, int B, int L, int Hq, int Hk, int Hv, int D,
+                               const float* gamma_q, const float* gamma_k, float scale, void* out16, long long o_ld, long long o_bs,
+                               void* stream) {
+  OF_REQUIRE(in16 && out16 && gamma_q && gamma_k, "of_headnorm_fwd: null pointer");
+  OF_REQUIRE(D >= 8 && D <= 8 * kHeadVecs && D % 8 == 0, "of_headnorm_fwd: head dim %d unsupported (8..64, multiple of 8)", D);
+  OF_REQUIRE(B >= 1 && L >= 1 && Hq >= 1 && Hk >= 1 && Hv >= 0, "of_headnorm_fwd: bad sizes");
+  OF_REQUIRE(in_ld % 8 == 0 && in_bs % 8 == 0 && o_ld % 8 == 0 && o_bs % 8 == 0, "of_headnorm_fwd: strides must be multiples of 8");
+  OF_CHECK_CUDA(launch_pdl(headnorm_fwd_kernel, dim3(grid_for((long long)B * L * (Hq + Hk + Hv), 256)), dim3(256), 0, STREAM,
+                           reinterpret_cast<const __nv_bfloat16*>(in16), in_ld, in_bs, B, L, Hq, Hk, Hv, D, gamma_q, gamma_k, scale,
+                           reinterpret_cast<__nv_bfloat16*>(out16), o_ld, o_bs));
+  DONE()
+}
+
+extern "C" int of_headnorm_bwd(const float* dq, long long dq_ld, long long dq_bs, const float* dk, const float* dv, long long dkv_ld,
+                               long long dkv_bs, const void* in16, long long in_ld, long long in_bs, int B, int L, int Hq, int Hk, int Hv,
+                               int D, const float* gamma_q, const float* gamma_k, float scale, void* dqkv16, long long o_ld,
+                               long long o_bs, float* dgamma_q, float* dgamma_k, void* stream) {
+  OF_REQUIRE(dq && dk && (dv || Hv == 0) && in16 && dqkv16 && gamma_q && gamma_k && dgamma_q && dgamma_k, "of_headnorm_bwd: null pointer");
+  OF_REQUIRE(D >= 8 && D <= 8 * kHeadVecs && D % 8 == 0, "of_headnorm_bwd: head dim %d unsupported (8..64, multiple of 8)", D);
+  OF_REQUIRE(B >= 1 && L >= 1 && Hq >= 1 && Hk >= 1 && Hv >= 0, "of_headnorm_bwd: bad sizes");
+  OF_REQUIRE(dq_ld % 4 == 0 && dq_bs % 4 == 0 && dkv_ld % 4 == 0 && dkv_bs % 4 == 0 && in_ld % 8 == 0 && in_bs % 8 == 0 && o_ld % 8 == 0 &&
+                 o_bs % 8 == 0, "of_headnorm_bwd: strides must keep 16-byte alignment");
+  const size_t smem = (size_t)(Hq + Hk) * D * sizeof(float);
+  OF_REQUIRE(smem <= 48 * 1024, "of_headnorm_bwd: (Hq + Hk) * D = %d too large", (Hq + Hk) * D);
+  long long need = ((long long)B * L * (Hq + Hk + Hv) + 255) / 256;
+  long long cap = (long long)device_sm_count() * 2;   // few CTAs: each ends with (Hq + Hk) * D global atomics
+  const unsigned grid = (unsigned)(need < cap ? need : cap);
+  OF_CHECK_CUDA(launch_pdl(headnorm_bwd_kernel, dim3(grid), dim3(256), smem, STREAM, dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs,
+                           reinterpret_cast<const __nv_bfloat16*>(in16), in_ld, in_bs, B, L, Hq, Hk, Hv, D, gamma_q, gamma_k, scale,
+                           reinterpret_cast<__nv_bfloat16*>(dqkv16), o_ld, o_bs, dgamma_q, dgamma_k));
+  DONE()
+}
+
+extern "C" int of_row_mean_std(const float* a, int B, int C, int N, float* out, void* stream) {
+  OF_REQUIRE(a && out && B >= 1 && C >= 1 && N >= 2, "of_row_mean_std: bad args");
+  OF_CHECK_CUDA(launch_pdl(row_mean_std_kernel, dim3((unsigned)(B * C)), dim3(256), 0, STREAM, a, C, N, out));
+  DONE()
+}

@@ -257,8 +257,12 @@ class ParamStore:
 
     # ---- gradient arena
     def ensure_arena(self, unet) -> None:
-        order = backward_param_order(unet)
-        fs, fe = backward_param_order.film_span
+        custom = getattr(unet, "backward_param_order", None)
+        if custom is not None:       # other backbones (osufusion_b200/backbones.py) supply their own completion order; no FiLM block
+            order, fs, fe = custom(), 0, 0
+        else:
+            order = backward_param_order(unet)
+            fs, fe = backward_param_order.film_span
         film_ids = {id(p) for p in order[fs:fe]}
         params = [p for p in order if p.requires_grad]
         key = tuple(id(p) for p in params) + (str(params[0].device) if params else "",)
