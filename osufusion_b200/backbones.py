@@ -628,6 +628,7 @@ class DiT(_Backbone):
         self.final = FinalLayer(dim_h, dim_h)
         self.initialize_weights()
         self._init_engine()
+        self._perm_cache = {}
 
     def initialize_weights(self) -> None:
         """dit.py:223-250."""
@@ -646,7 +647,11 @@ class DiT(_Backbone):
     # wide input buffer: [a (dim_in_a) | x (dim_in_x) | zero pad] so that both slices start 16-byte aligned; the CrossEmbed weights'
     # input channels are permuted accordingly (the reference concatenates [x, a], dit.py:275)
     def _perm(self, device) -> torch.Tensor:
-        return torch.cat([torch.arange(self.dim_in_x, self.dim_in_x + self.dim_in_a), torch.arange(self.dim_in_x)]).to(device)
+        key = str(device)
+        if key not in self._perm_cache:     # built once per device (no host-to-device copy inside a captured step)
+            self._perm_cache[key] = torch.cat([torch.arange(self.dim_in_x, self.dim_in_x + self.dim_in_a),
+                                               torch.arange(self.dim_in_x)]).to(device)
+        return self._perm_cache[key]
 
     def _cross_embed(self, ctx: Ctx, wide: torch.Tensor) -> Act:
         st, dev = ctx.store, ctx.device

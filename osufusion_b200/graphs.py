@@ -57,3 +57,25 @@ class GraphedTrainStep:
             self.orig_len.copy_(orig_len, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+
+class GraphedCallable:
+    """Captures an arbitrary launch-only closure (e.g. `zero_grad -> loss = f(backbone(x, a, t, c)) -> loss.backward()` of the DiT /
+    MMDiT backbones) into one CUDA graph.  The closure must read its inputs from tensors that stay alive and are updated in
+    place between replays, and must not synchronise with the host.  `__call__` replays and returns what the closure returned."""
+
+    def __init__(self, fn, warmup: int = 2) -> None:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.result

@@ -76,13 +76,16 @@ def main():
         step_new()
         torch.cuda.synchronize()
         launches = N.lib().of_launch_count()
-        ms = time_steps(step_new, args.steps, args.warmup)
+        ms_eager = time_steps(step_new, args.steps, args.warmup)
+        from osufusion_b200.graphs import GraphedCallable
+        graphed = GraphedCallable(step_new)
+        ms = time_steps(graphed, args.steps, args.warmup)
         fl = 3.0 * flops_fwd(kind, args.batch, args.frames, args.dim, args.depth)
         line = {"backbone": kind, "metric": "fwd+bwd samples/s", "value": args.batch / ms * 1e3, "ms_per_step": ms,
                 "config": {"dim_h": args.dim, "depth": args.depth, "batch": args.batch, "frames": args.frames, "heads": "8x64",
-                           "cuda_graph": False},
+                           "cuda_graph": True},
                 "algorithmic_tflops": fl / ms / 1e9, "frac_of_measured_bf16_peak": fl / ms / 1e9 / peak, "peak_tflops": peak,
-                "gpu_launches_per_step": launches, "params_m": sum(p.numel() for p in new.parameters()) / 1e6}
+                "gpu_launches_per_step": launches, "ms_per_step_eager_launches": ms_eager, "params_m": sum(p.numel() for p in new.parameters()) / 1e6}
         if not args.no_eager:
             ora = ora.to(dev)
 
