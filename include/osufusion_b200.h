@@ -395,6 +395,23 @@ int of_headnorm_bwd(const float* dq, long long dq_ld, long long dq_bs, const flo
                     const float* gamma_q, const float* gamma_k, float scale, void* dqkv16, long long o_ld, long long o_bs,
                     float* dgamma_q, float* dgamma_k, void* stream);
 int of_row_mean_std(const float* a, int B, int C, int N, float* out, void* stream);
+/* Batched forms (one launch for all samples; strides in elements, `*_ld` of the (B, C) vectors = their row stride):
+ *   of_adaln_fwd : out_bf16[b,l,:] = LayerNorm_noaffine(x[b,l,:]) * scale1p[b,:] + shift[b,:]  (scale1p = 1 + scale, dit.py:13-15);
+ *                  mean_rstd (B*L, 2) saved for backward.  Bytes/element: 4 read, 2 written.
+ *   of_adaln_bwd : dx = LayerNorm backward of dy * scale1p[b,:]  (+ dres, the residual-stream gradient that bypasses the branch);
+ *                  dscale[b,:] += sum_l dy * xhat, dshift[b,:] += sum_l dy (atomic; caller zero-fills).  Bytes/element: 8 (+4) read, 4 written.
+ *   of_gate_bwd  : backward of `gate.unsqueeze(1) * y` in one pass: dy16 = bf16(gate[b,:] * d), dgate[b,:] += sum_l d * y (atomic), with
+ *                  d rounded to bf16 first when round_bf16 (the forward product was a bf16 multiplication).  Bytes/element: 4 + 2 read, 2 written. */
+int of_adaln_fwd(const float* x, long long x_ld, long long x_bs, int B, int L, int C, const float* scale1p, long long sc_ld,
+                 const float* shift, long long sh_ld, float eps, void* out_bf16, long long o_ld, long long o_bs, float* mean_rstd,
+                 void* stream);
+int of_adaln_bwd(const float* dy, long long dy_ld, long long dy_bs, const float* x, long long x_ld, long long x_bs, int B, int L, int C,
+                 const float* scale1p, long long sc_ld, const float* mean_rstd, const float* dres, long long r_ld, long long r_bs,
+                 float* dx, long long dx_ld, long long dx_bs, float* dscale, long long ds_ld, float* dshift, long long dsh_ld,
+                 void* stream);
+int of_gate_bwd(const float* d32, long long d_ld, long long d_bs, const float* gate, long long gate_ld, const void* y16, long long y_ld,
+                long long y_bs, int round_bf16, int B, int L, int C, void* dy16, long long o_ld, long long o_bs, float* dgate,
+                long long dg_ld, void* stream);
 
 #ifdef __cplusplus
 }

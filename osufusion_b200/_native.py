@@ -140,6 +140,9 @@ _SIGS = {
     "of_headnorm_fwd": [P, LL, LL, I, I, I, I, I, I, P, P, F, P, LL, LL, P],
     "of_headnorm_bwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, I, P, P, F, P, LL, LL, P, P, P],
     "of_row_mean_std": [P, I, I, I, P, P],
+    "of_adaln_fwd": [P, LL, LL, I, I, I, P, LL, P, LL, F, P, LL, LL, P, P],
+    "of_adaln_bwd": [P, LL, LL, P, LL, LL, I, I, I, P, LL, P, P, LL, LL, P, LL, LL, P, LL, P, LL, P],
+    "of_gate_bwd": [P, LL, LL, P, LL, P, LL, LL, I, I, I, I, P, LL, LL, P, LL, P],
 }
 _PLAIN = {"of_set_sm_limit": [I], "of_rb_pool_parts": [C.POINTER(RbArgs)], "of_film_chunk_rows": [], "of_pack_seg_ctas": [I, I, I, I], "of_opt_tensor_ctas": [LL]}    # host-side helpers: no stream argument, return a value
 EXPORTS = ["of_last_error", "of_version", "of_launch_count", "of_reset_launch_count", *_SIGS.keys(), *_PLAIN.keys()]

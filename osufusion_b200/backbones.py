@@ -19,6 +19,7 @@ stream silently becomes bf16 after the first `x + gate * ...`), which is closer 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -30,6 +31,11 @@ from . import ops_raw as R
 from .engine import BF16, F32, Act, Ctx, ParamStore, Tape, _bl, _p
 from .modules import (A_PAD_VALUE, X_PAD_VALUE, CrossEmbedLayer, SinusoidalPositionEmbedding, UNetFunction, _Container, _pack,
                       prob_mask_like)
+
+
+# adaLN / gate backward as ONE launch over all samples (of_adaln_fwd/bwd, of_gate_bwd) vs the per-sample composition of the UNet
+# path's LayerNorm kernels + of_gate_mul_bwd + of_coldot_bf16 (kept as the cross-check: OF_BACKBONE_BATCHED=0)
+BATCHED = os.environ.get("OF_BACKBONE_BATCHED", "0") != "0"
 
 
 # ------------------------------------------------------------------------------------------------ parameter containers
@@ -161,6 +167,10 @@ def ada_ln_fwd(x32: torch.Tensor, shift: torch.Tensor, scale1p: torch.Tensor, ep
     bs, ld = _bl(x32)
     h16 = E.empty((B, L, Cc), BF16, x32.device)
     mr = E.empty((B, L, 2), F32, x32.device)
+    if BATCHED:
+        N.call("of_adaln_fwd", _p(x32), ld, bs, B, L, Cc, _p(scale1p), scale1p.stride(0), _p(shift), shift.stride(0), eps, _p(h16), Cc,
+               L * Cc, _p(mr))
+        return h16, mr
     for b in range(B):
         N.call("of_layernorm_fwd", x32.data_ptr() + 4 * b * bs, ld, L, Cc, scale1p[b].data_ptr(), shift[b].data_ptr(), eps, None,
                h16[b].data_ptr(), Cc, mr[b].data_ptr())
@@ -168,15 +178,23 @@ def ada_ln_fwd(x32: torch.Tensor, shift: torch.Tensor, scale1p: torch.Tensor, ep
 
 
 def ada_ln_bwd(dh32: torch.Tensor, x32: torch.Tensor, scale1p: torch.Tensor, mr: torch.Tensor, dshift: torch.Tensor,
-               dscale: torch.Tensor) -> torch.Tensor:
-    """Returns dx (fresh fp32 tensor); accumulates d shift / d scale into the given (B, C) row views of the modulation gradient."""
+               dscale: torch.Tensor, dres: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Returns dx (+ dres, the stream gradient that bypasses the branch) as a fresh fp32 tensor; accumulates d shift / d scale into the
+    given (B, C) row views of the modulation gradient."""
     B, L, Cc = x32.shape
     bs, ld = _bl(x32)
     d_bs, d_ld = _bl(dh32)
     dx = E.empty((B, L, Cc), F32, x32.device)
+    if BATCHED:
+        r_bs, r_ld = _bl(dres) if dres is not None else (0, 0)
+        N.call("of_adaln_bwd", _p(dh32), d_ld, d_bs, _p(x32), ld, bs, B, L, Cc, _p(scale1p), scale1p.stride(0), _p(mr), _p(dres), r_ld, r_bs,
+               _p(dx), Cc, L * Cc, _p(dscale), dscale.stride(0), _p(dshift), dshift.stride(0))
+        return dx
     for b in range(B):
         N.call("of_layernorm_bwd", dh32.data_ptr() + 4 * b * d_bs, d_ld, x32.data_ptr() + 4 * b * bs, ld, L, Cc, scale1p[b].data_ptr(),
                mr[b].data_ptr(), dx[b].data_ptr(), None, Cc, dscale[b].data_ptr(), dshift[b].data_ptr())
+    if dres is not None:
+        E.cast_copy(dres, dx, accumulate=True)
     return dx
 
 
@@ -202,8 +220,12 @@ def gate_backward(d32: torch.Tensor, gate: torch.Tensor, y16: torch.Tensor, dgat
     dev = d32.device
     d_bs, d_ld = _bl(d32)
     y_bs, y_ld = _bl(y16)
-    dx16 = E.empty((B, L, Cc), BF16, dev)
     dy16 = E.empty((B, L, Cc), BF16, dev)
+    if BATCHED:
+        N.call("of_gate_bwd", _p(d32), d_ld, d_bs, _p(gate), gate.stride(0), _p(y16), y_ld, y_bs, 1, B, L, Cc, _p(dy16), Cc, L * Cc,
+               _p(dgate), dgate.stride(0))
+        return dy16
+    dx16 = E.empty((B, L, Cc), BF16, dev)
     N.call("of_gate_mul_bwd", _p(d32), d_ld, d_bs, _p(gate), gate.stride(0), 1, B, L, Cc, _p(dx16), _p(dy16), Cc, L * Cc)
     for b in range(B):
         N.call("of_coldot_bf16", dx16[b].data_ptr(), Cc, y16[b].data_ptr(), y_ld, L, Cc, None, dgate[b].data_ptr())
@@ -331,8 +353,7 @@ def dit_block(ctx: Ctx, m: DiTBlock, x: Act, cact: torch.Tensor) -> Act:
             # feed-forward branch
             df16 = gate_backward(d2, g2, f16, dg2)
             dh2 = ff_bwd(ctx, m.ff, df16, ff_saved)
-            d1 = ada_ln_bwd(dh2, x1, s1p2, mr2, dsh2, dsc2)
-            E.cast_copy(d2, d1, accumulate=True)
+            d1 = ada_ln_bwd(dh2, x1, s1p2, mr2, dsh2, dsc2, dres=d2)
             # attention branch
             dO = gate_backward(d1, g1, o16, dg1)
             delta = E.empty((B, H, L), F32, dev)
@@ -343,8 +364,7 @@ def dit_block(ctx: Ctx, m: DiTBlock, x: Act, cact: torch.Tensor) -> Act:
             hact = Act(None, None)
             E._dgrad_into(hact, dqkv, wqkv, N_out=Cc, K=3 * HD)
             E._wgrad_linear(st, at.to_qkv.weight, dqkv, h1)
-            d0 = ada_ln_bwd(hact.grad, x0, s1p1, mr1, dsh1, dsc1)
-            E.cast_copy(d1, d0, accumulate=True)
+            d0 = ada_ln_bwd(hact.grad, x0, s1p1, mr1, dsh1, dsc1, dres=d1)
             x.add_grad(d0)
             E.linear_small_bwd_param(st, dmod, None, 0, cact, lin.weight, lin.bias, ctx.d_emb_act)
         ctx.tape.push(backward)
@@ -412,8 +432,7 @@ def mmdit_block(ctx: Ctx, m: MMDiTBlock, x: Act, a: Act, cact: torch.Tensor, las
                     continue
                 df = gate_backward(d2, d["g2"], d["f"], dg2)
                 dh2 = ff_bwd(ctx, d["ff"], df, d["ff_saved"])
-                d1 = ada_ln_bwd(dh2, d["x1"], d["s1p2"], d["mr2"], dsh2, dsc2)
-                E.cast_copy(d2, d1, accumulate=True)
+                d1 = ada_ln_bwd(dh2, d["x1"], d["s1p2"], d["mr2"], dsh2, dsc2, dres=d2)
                 dy = gate_backward(d1, d["g1"], d["y"], dg1)
                 R.gemm_fwd(dy, d["wout"], N_out=HD, K=Cc, b_mn_major=True, out_bf16=dO[:, d["r0"]:d["r1"]])
                 E._wgrad_linear(st, d["out_lin"].weight, dy, d["o"])
@@ -434,9 +453,7 @@ def mmdit_block(ctx: Ctx, m: MMDiTBlock, x: Act, a: Act, cact: torch.Tensor, las
                     n_ = p.weight.shape[0]
                     E._wgrad_linear(st, p.weight, dqkv[:, :, c0:c0 + n_], d["h1"])
                     c0 += n_
-                d0 = ada_ln_bwd(hact.grad, d["x0"], d["s1p1"], d["mr1"], dsh1, dsc1)
-                if d["d1"] is not None:
-                    E.cast_copy(d["d1"], d0, accumulate=True)
+                d0 = ada_ln_bwd(hact.grad, d["x0"], d["s1p1"], d["mr1"], dsh1, dsc1, dres=d["d1"])
                 d["src"].add_grad(d0)
                 E.linear_small_bwd_param(st, d["dmod"], None, 0, cact, d["lin"].weight, d["lin"].bias, ctx.d_emb_act)
         ctx.tape.push(backward)

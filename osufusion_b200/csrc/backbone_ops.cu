@@ -208,6 +208,193 @@ __global__ void __launch_bounds__(256) row_mean_std_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Batched adaLN: LayerNorm without affine + per-sample modulation `xhat * (1 + scale_b) + shift_b` -> bf16 GEMM operand.
+// Warp per row over all B*L rows; lane owns 16-byte vectors lane + 32*i (i < NV); the row stays in registers.
+template <int NV>
+__global__ void __launch_bounds__(256) adaln_fwd_kernel(const float* __restrict__ x, long long x_ld, long long x_bs, int B, int L, int C,
+                                                        const float* __restrict__ scale1p, long long sc_ld,
+                                                        const float* __restrict__ shift, long long sh_ld, float eps,
+                                                        __nv_bfloat16* __restrict__ out, long long o_ld, long long o_bs,
+                                                        float* __restrict__ mean_rstd) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= (long long)B * L) return;
+  const int b = (int)(row / L), l = (int)(row % L);
+  const float* xp = x + b * x_bs + (long long)l * x_ld;
+  const int vecs = C >> 3;
+  V8 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+      v[i] = ld_f32x8(xp + vi * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i].v[j];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i].v[j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  if (lane == 0) {
+    mean_rstd[2 * row] = mean;
+    mean_rstd[2 * row + 1] = rstd;
+  }
+  __nv_bfloat16* op = out + b * o_bs + (long long)l * o_ld;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+      const V8 g = ld_f32x8(scale1p + b * sc_ld + vi * 8), bt = ld_f32x8(shift + b * sh_ld + vi * 8);
+      V8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = (v[i].v[j] - mean) * rstd * g.v[j] + bt.v[j];
+      st_bf16x8(op + vi * 8, o);
+    }
+  }
+}
+
+// Backward: grid (row chunks, B).  dx = rstd * (dxh - mean(dxh) - xh * mean(dxh * xh)) [+ dres], dxh = dy * (1 + scale_b);
+// d scale_b[c] += sum_l dy * xh, d shift_b[c] += sum_l dy  (shared-memory reduction per CTA, one global atomic per channel per CTA).
+template <int NV>
+__global__ void __launch_bounds__(256) adaln_bwd_kernel(const float* __restrict__ dy, long long dy_ld, long long dy_bs,
+                                                        const float* __restrict__ x, long long x_ld, long long x_bs, int L, int C,
+                                                        const float* __restrict__ scale1p, long long sc_ld,
+                                                        const float* __restrict__ mean_rstd, const float* __restrict__ dres,
+                                                        long long r_ld, long long r_bs, float* __restrict__ dx, long long dx_ld,
+                                                        long long dx_bs, float* __restrict__ dscale, long long ds_ld,
+                                                        float* __restrict__ dshift, long long dsh_ld, int rows_per_warp) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_red[];  // [2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int vecs = C >> 3;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_red[c] = 0.f;
+  __syncthreads();
+  V8 g[NV], dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) g[i] = ld_f32x8(scale1p + b * sc_ld + vi * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i].v[j] = db[i].v[j] = 0.f;
+  }
+  const int row0 = (blockIdx.x * 8 + warp) * rows_per_warp;
+  for (int r = 0; r < rows_per_warp; ++r) {
+    const int l = row0 + r;
+    if (l >= L) break;
+    const long long grow = (long long)b * L + l;
+    const float mean = mean_rstd[2 * grow], rstd = mean_rstd[2 * grow + 1];
+    V8 xh[NV], dxh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < vecs) {
+        const V8 xv = ld_f32x8(x + b * x_bs + (long long)l * x_ld + vi * 8);
+        const V8 dv = ld_f32x8(dy + b * dy_bs + (long long)l * dy_ld + vi * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i].v[j] = (xv.v[j] - mean) * rstd;
+          dg[i].v[j] += dv.v[j] * xh[i].v[j];
+          db[i].v[j] += dv.v[j];
+          dxh[i].v[j] = dv.v[j] * g[i].v[j];
+          s1 += dxh[i].v[j];
+          s2 += dxh[i].v[j] * xh[i].v[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < vecs) {
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = rstd * (dxh[i].v[j] - s1 - xh[i].v[j] * s2);
+        if (dres) {
+          const V8 rv = ld_f32x8(dres + b * r_bs + (long long)l * r_ld + vi * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[j] += rv.v[j];
+        }
+        st_f32x8(dx + b * dx_bs + (long long)l * dx_ld + vi * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&s_red[vi * 8 + j], dg[i].v[j]);
+        atomicAdd(&s_red[C + vi * 8 + j], db[i].v[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(dscale + b * ds_ld + c, s_red[c]);
+    atomicAdd(dshift + b * dsh_ld + c, s_red[C + c]);
+  }
+}
+
+// Backward of `gate_b * y` in one pass: dy16 = bf16(gate * d~), d gate[b, c] += sum_l d~ * y with d~ = bf16(d) when the forward product
+// was a bf16 multiplication.  Grid (row chunks, B); thread = (16-byte channel vector, row lane); shared reduction, then global atomics.
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ d32, long long d_ld, long long d_bs,
+                                                       const float* __restrict__ gate, long long gate_ld,
+                                                       const __nv_bfloat16* __restrict__ y16, long long y_ld, long long y_bs,
+                                                       int round_bf16, int L, int C, __nv_bfloat16* __restrict__ dy16, long long o_ld,
+                                                       long long o_bs, float* __restrict__ dgate, long long dg_ld, int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_acc[];  // [C]
+  const int b = blockIdx.y;
+  const int vecs = C >> 3;
+  const int rpar = blockDim.x / vecs;
+  const int vi = threadIdx.x % vecs, rsub = threadIdx.x / vecs;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_acc[c] = 0.f;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, L);
+  if (rsub < rpar) {
+    const V8 g = ld_f32x8(gate + b * gate_ld + vi * 8);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int l = r0 + rsub; l < r1; l += rpar) {
+      const V8 d = ld_f32x8(d32 + b * d_bs + (long long)l * d_ld + vi * 8);
+      const V8 y = ld_bf16x8(y16 + b * y_bs + (long long)l * y_ld + vi * 8);
+      V8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dr = round_bf16 ? bf16r(d.v[j]) : d.v[j];
+        acc[j] += dr * y.v[j];
+        o.v[j] = g.v[j] * dr;
+      }
+      st_bf16x8(dy16 + b * o_bs + (long long)l * o_ld + vi * 8, o);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[vi * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dgate + b * dg_ld + c, s_acc[c]);
+}
+
 static unsigned grid_for(long long total, int threads) {
   long long need = (total + threads - 1) / threads;
   long long cap = (long long)device_sm_count() * 8;
@@ -284,5 +471,63 @@ extern "C" int of_headnorm_bwd(const float* dq, long long dq_ld, long long dq_bs
 extern "C" int of_row_mean_std(const float* a, int B, int C, int N, float* out, void* stream) {
   OF_REQUIRE(a && out && B >= 1 && C >= 1 && N >= 2, "of_row_mean_std: bad args");
   OF_CHECK_CUDA(launch_pdl(row_mean_std_kernel, dim3((unsigned)(B * C)), dim3(256), 0, STREAM, a, C, N, out));
+  DONE()
+}
+
+extern "C" int of_adaln_fwd(const float* x, long long x_ld, long long x_bs, int B, int L, int C, const float* scale1p, long long sc_ld,
+                            const float* shift, long long sh_ld, float eps, void* out_bf16, long long o_ld, long long o_bs,
+                            float* mean_rstd, void* stream) {
+  OF_REQUIRE(x && scale1p && shift && out_bf16 && mean_rstd, "of_adaln_fwd: null pointer");
+  OF_REQUIRE(B >= 1 && L >= 1 && C >= 8 && C % 8 == 0 && C <= 2048, "of_adaln_fwd: unsupported C=%d", C);
+  OF_REQUIRE(x_ld % 4 == 0 && x_bs % 4 == 0 && sc_ld % 4 == 0 && sh_ld % 4 == 0 && o_ld % 8 == 0 && o_bs % 8 == 0,
+             "of_adaln_fwd: strides must keep 16-byte alignment");
+  const long long rows = (long long)B * L;
+  const dim3 grid((unsigned)((rows + 7) / 8));
+  const int nv = (C / 8 + 31) / 32;
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (nv <= 1) OF_CHECK_CUDA(launch_pdl(adaln_fwd_kernel<1>, grid, dim3(256), 0, STREAM, x, x_ld, x_bs, B, L, C, scale1p, sc_ld, shift, sh_ld, eps, o16, o_ld, o_bs, mean_rstd));
+  else if (nv <= 2) OF_CHECK_CUDA(launch_pdl(adaln_fwd_kernel<2>, grid, dim3(256), 0, STREAM, x, x_ld, x_bs, B, L, C, scale1p, sc_ld, shift, sh_ld, eps, o16, o_ld, o_bs, mean_rstd));
+  else if (nv <= 4) OF_CHECK_CUDA(launch_pdl(adaln_fwd_kernel<4>, grid, dim3(256), 0, STREAM, x, x_ld, x_bs, B, L, C, scale1p, sc_ld, shift, sh_ld, eps, o16, o_ld, o_bs, mean_rstd));
+  else OF_CHECK_CUDA(launch_pdl(adaln_fwd_kernel<8>, grid, dim3(256), 0, STREAM, x, x_ld, x_bs, B, L, C, scale1p, sc_ld, shift, sh_ld, eps, o16, o_ld, o_bs, mean_rstd));
+  DONE()
+}
+
+extern "C" int of_adaln_bwd(const float* dy, long long dy_ld, long long dy_bs, const float* x, long long x_ld, long long x_bs, int B, int L,
+                            int C, const float* scale1p, long long sc_ld, const float* mean_rstd, const float* dres, long long r_ld,
+                            long long r_bs, float* dx, long long dx_ld, long long dx_bs, float* dscale, long long ds_ld, float* dshift,
+                            long long dsh_ld, void* stream) {
+  OF_REQUIRE(dy && x && scale1p && mean_rstd && dx && dscale && dshift, "of_adaln_bwd: null pointer");
+  OF_REQUIRE(B >= 1 && L >= 1 && C >= 8 && C % 8 == 0 && C <= 2048, "of_adaln_bwd: unsupported C=%d", C);
+  OF_REQUIRE(dy_ld % 4 == 0 && dy_bs % 4 == 0 && x_ld % 4 == 0 && x_bs % 4 == 0 && sc_ld % 4 == 0 && dx_ld % 4 == 0 && dx_bs % 4 == 0 &&
+                 (!dres || (r_ld % 4 == 0 && r_bs % 4 == 0)), "of_adaln_bwd: strides must keep 16-byte alignment");
+  int target = 2 * device_sm_count() / B;            // CTAs per sample: ~2 per SM over the whole grid
+  if (target < 1) target = 1;
+  int rpw = (L + 8 * target - 1) / (8 * target);
+  if (rpw < 1) rpw = 1;
+  const dim3 grid((unsigned)((L + 8 * rpw - 1) / (8 * rpw)), (unsigned)B);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  const int nv = (C / 8 + 31) / 32;
+  if (nv <= 1) OF_CHECK_CUDA(launch_pdl(adaln_bwd_kernel<1>, grid, dim3(256), smem, STREAM, dy, dy_ld, dy_bs, x, x_ld, x_bs, L, C, scale1p, sc_ld, mean_rstd, dres, r_ld, r_bs, dx, dx_ld, dx_bs, dscale, ds_ld, dshift, dsh_ld, rpw));
+  else if (nv <= 2) OF_CHECK_CUDA(launch_pdl(adaln_bwd_kernel<2>, grid, dim3(256), smem, STREAM, dy, dy_ld, dy_bs, x, x_ld, x_bs, L, C, scale1p, sc_ld, mean_rstd, dres, r_ld, r_bs, dx, dx_ld, dx_bs, dscale, ds_ld, dshift, dsh_ld, rpw));
+  else if (nv <= 4) OF_CHECK_CUDA(launch_pdl(adaln_bwd_kernel<4>, grid, dim3(256), smem, STREAM, dy, dy_ld, dy_bs, x, x_ld, x_bs, L, C, scale1p, sc_ld, mean_rstd, dres, r_ld, r_bs, dx, dx_ld, dx_bs, dscale, ds_ld, dshift, dsh_ld, rpw));
+  else OF_CHECK_CUDA(launch_pdl(adaln_bwd_kernel<8>, grid, dim3(256), smem, STREAM, dy, dy_ld, dy_bs, x, x_ld, x_bs, L, C, scale1p, sc_ld, mean_rstd, dres, r_ld, r_bs, dx, dx_ld, dx_bs, dscale, ds_ld, dshift, dsh_ld, rpw));
+  DONE()
+}
+
+extern "C" int of_gate_bwd(const float* d32, long long d_ld, long long d_bs, const float* gate, long long gate_ld, const void* y16,
+                           long long y_ld, long long y_bs, int round_bf16, int B, int L, int C, void* dy16, long long o_ld, long long o_bs,
+                           float* dgate, long long dg_ld, void* stream) {
+  OF_REQUIRE(d32 && gate && y16 && dy16 && dgate, "of_gate_bwd: null pointer");
+  OF_REQUIRE(B >= 1 && L >= 1 && C >= 8 && C % 8 == 0 && C <= 2048, "of_gate_bwd: unsupported C=%d", C);
+  OF_REQUIRE(d_ld % 4 == 0 && d_bs % 4 == 0 && gate_ld % 4 == 0 && y_ld % 8 == 0 && y_bs % 8 == 0 && o_ld % 8 == 0 && o_bs % 8 == 0,
+             "of_gate_bwd: strides must keep 16-byte alignment");
+  int target = 2 * device_sm_count() / B;
+  if (target < 1) target = 1;
+  int rpc = (L + target - 1) / target;
+  if (rpc < 16) rpc = 16;
+  const dim3 grid((unsigned)((L + rpc - 1) / rpc), (unsigned)B);
+  OF_CHECK_CUDA(launch_pdl(gate_bwd_kernel, grid, dim3(256), (size_t)C * sizeof(float), STREAM, d32, d_ld, d_bs, gate, gate_ld,
+                           reinterpret_cast<const __nv_bfloat16*>(y16), y_ld, y_bs, round_bf16, L, C, reinterpret_cast<__nv_bfloat16*>(dy16),
+                           o_ld, o_bs, dgate, dg_ld, rpc));
   DONE()
 }

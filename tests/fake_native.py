@@ -320,6 +320,36 @@ def of_row_mean_std(a, B, Cc, n, out):
     v2(out, F32, B, 2 * Cc).copy_(torch.cat([A.mean(-1), A.std(-1)], 1))
 
 
+def of_adaln_fwd(x, x_ld, x_bs, B, L, Cc, s1p, sc_ld, shift, sh_ld, eps, out16, o_ld, o_bs, mean_rstd):
+    X = v3(x, F32, B, L, Cc, x_bs, x_ld)
+    mean = X.mean(2, keepdim=True)
+    rstd = torch.rsqrt(((X - mean) ** 2).mean(2, keepdim=True) + eps)
+    y = (X - mean) * rstd * v2(s1p, F32, B, Cc, sc_ld)[:, None, :] + v2(shift, F32, B, Cc, sh_ld)[:, None, :]
+    v3(out16, BF16, B, L, Cc, o_bs, o_ld).copy_(y.to(BF16))
+    v2(mean_rstd, F32, B * L, 2).copy_(torch.cat([mean, rstd], 2).view(B * L, 2))
+
+
+def of_adaln_bwd(dy, dy_ld, dy_bs, x, x_ld, x_bs, B, L, Cc, s1p, sc_ld, mean_rstd, dres, r_ld, r_bs, dx, dx_ld, dx_bs, dscale, ds_ld,
+                 dshift, dsh_ld):
+    DY, X = v3(dy, F32, B, L, Cc, dy_bs, dy_ld), v3(x, F32, B, L, Cc, x_bs, x_ld)
+    mr = v2(mean_rstd, F32, B * L, 2).view(B, L, 2)
+    xh = (X - mr[:, :, :1]) * mr[:, :, 1:]
+    dxh = DY * v2(s1p, F32, B, Cc, sc_ld)[:, None, :]
+    out = mr[:, :, 1:] * (dxh - dxh.mean(2, keepdim=True) - xh * (dxh * xh).mean(2, keepdim=True))
+    if dres:
+        out = out + v3(dres, F32, B, L, Cc, r_bs, r_ld)
+    v3(dx, F32, B, L, Cc, dx_bs, dx_ld).copy_(out)
+    v2(dscale, F32, B, Cc, ds_ld).add_((DY * xh).sum(1))
+    v2(dshift, F32, B, Cc, dsh_ld).add_(DY.sum(1))
+
+
+def of_gate_bwd(d32, d_ld, d_bs, gate, gate_ld, y16, y_ld, y_bs, rnd, B, L, Cc, dy16, o_ld, o_bs, dgate, dg_ld):
+    d = v3(d32, F32, B, L, Cc, d_bs, d_ld)
+    dr = rb(d) if rnd else d
+    v3(dy16, BF16, B, L, Cc, o_bs, o_ld).copy_((v2(gate, F32, B, Cc, gate_ld)[:, None, :] * dr).to(BF16))
+    v2(dgate, F32, B, Cc, dg_ld).add_((dr * v3(y16, BF16, B, L, Cc, y_bs, y_ld).float()).sum(1))
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith("of_")}
 CALLS = []
 

@@ -33,10 +33,13 @@ def _pair(kind):
     return ora, new
 
 
+@pytest.mark.parametrize("batched", [False, True])
 @pytest.mark.parametrize("kind,n", [("dit", 64), ("dit", 56), ("mmdit", 64), ("mmdit", 50)])
-def test_engine_tape_matches_oracle_through_emulated_abi(fake_abi, kind, n):
+def test_engine_tape_matches_oracle_through_emulated_abi(fake_abi, monkeypatch, kind, n, batched):
     from oracle.synth import synth_inputs
+    from osufusion_b200 import backbones
     from osufusion_b200.modules import UNetFunction
+    monkeypatch.setattr(backbones, "BATCHED", batched)
     ora, new = _pair(kind)
     x, a, c, t, noise, mask = synth_inputs(2, n, 1234)
     y_o = ora(x, a, t, c, cond_mask=mask)
@@ -53,8 +56,11 @@ def test_engine_tape_matches_oracle_through_emulated_abi(fake_abi, kind, n):
         if p.grad is not None:
             assert nrel(p.grad, go[k].grad) <= 4e-2, (k, nrel(p.grad, go[k].grad))
     used = set(fake_abi.CALLS)
-    assert {"of_gemm", "of_attn_fwd", "of_attn_bwd", "of_headnorm_fwd", "of_headnorm_bwd", "of_gate_residual_fwd", "of_gate_mul_bwd",
-            "of_layernorm_fwd", "of_layernorm_bwd", "of_row_mean_std"} <= used
+    assert {"of_gemm", "of_attn_fwd", "of_attn_bwd", "of_headnorm_fwd", "of_headnorm_bwd", "of_gate_residual_fwd", "of_row_mean_std"} <= used
+    if batched:
+        assert {"of_adaln_fwd", "of_adaln_bwd", "of_gate_bwd"} <= used and not ({"of_layernorm_fwd", "of_coldot_bf16"} & used)
+    else:
+        assert {"of_layernorm_fwd", "of_layernorm_bwd", "of_gate_mul_bwd", "of_coldot_bf16"} <= used
     # inference path (no tape) gives the same output
     with torch.no_grad():
         out16, _ = new.run(None, x, a, t, c, mask)

@@ -91,6 +91,42 @@ def test_headnorm_forward_backward(B, L, Hq, Hk, D, Ltot, r0):
     assert nrel(got[2].cpu(), ref[2]) <= 1e-4 and nrel(got[3].cpu(), ref[3]) <= 1e-4
 
 
+@pytest.mark.parametrize("B,L,C", [(2, 50, 128), (4, 300, 512), (1, 37, 1536)])
+def test_batched_adaln_and_gate_backward(B, L, C):
+    """of_adaln_fwd / of_adaln_bwd / of_gate_bwd (one launch over all samples) against the header contracts."""
+    from osufusion_b200 import _native as N
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, L, C, generator=g) * 2 + 0.5
+    mod = (0.3 * torch.randn(B, 6 * C, generator=g)).to(torch.bfloat16).float()
+    shift, s1p = mod[:, :C], (1 + mod[:, C:2 * C]).to(torch.bfloat16).float().contiguous()
+    gate = mod[:, 2 * C:3 * C]
+    dy, dres = torch.randn(B, L, C, generator=g), torch.randn(B, L, C, generator=g)
+    y16 = torch.randn(B, L, C, generator=g).to(torch.bfloat16)
+
+    def run(call, to):
+        x_, mod_, s1p_, dy_, dres_, y_ = to(x), to(mod), to(s1p), to(dy), to(dres), to(y16)
+        shift_, gate_ = mod_[:, :C], mod_[:, 2 * C:3 * C]
+        h16, mr = to(torch.zeros(B, L, C, dtype=torch.bfloat16)), to(torch.zeros(B * L, 2))
+        call("of_adaln_fwd", _p(x_), C, L * C, B, L, C, _p(s1p_), C, _p(shift_), 6 * C, 1e-6, _p(h16), C, L * C, _p(mr))
+        dmod = to(torch.zeros(B, 6 * C))
+        dx = to(torch.zeros(B, L, C))
+        call("of_adaln_bwd", _p(dy_), C, L * C, _p(x_), C, L * C, B, L, C, _p(s1p_), C, _p(mr), _p(dres_), C, L * C, _p(dx), C, L * C,
+             _p(dmod[:, C:2 * C]), 6 * C, _p(dmod[:, :C]), 6 * C)
+        dy16 = to(torch.zeros(B, L, C, dtype=torch.bfloat16))
+        call("of_gate_bwd", _p(dy_), C, L * C, _p(gate_), 6 * C, _p(y_), C, L * C, 1, B, L, C, _p(dy16), C, L * C, _p(dmod[:, 2 * C:3 * C]),
+             6 * C)
+        return h16, mr, dx, dmod, dy16
+
+    ref = run(lambda name, *a: getattr(FK, name)(*a), lambda t: t.clone())
+    got = run(N.call, lambda t: t.to(dev))
+    torch.cuda.synchronize()
+    assert nrel(got[0].cpu(), ref[0]) <= 1e-2 and (got[0].cpu().float() - ref[0].float()).abs().mean() <= 1e-3
+    assert nrel(got[1].cpu(), ref[1]) <= 1e-4
+    assert nrel(got[2].cpu(), ref[2]) <= 1e-4
+    assert nrel(got[3].cpu(), ref[3]) <= 1e-4
+    assert nrel(got[4].cpu(), ref[4]) <= 4e-3
+
+
 def test_row_mean_std():
     from osufusion_b200 import _native as N
     a = torch.randn(3, 96, 1000) * 3 - 8
@@ -123,8 +159,11 @@ def _fwd_bwd(model, inputs, keep, autocast):
     return y.detach().float(), {k: p.grad.detach().float().clone() for k, p in model.named_parameters() if p.grad is not None}
 
 
-def _check(kind, cfg, B, n):
+def _check(kind, cfg, B, n, batched=None, monkeypatch=None):
     from oracle.synth import synth_inputs
+    if batched is not None:
+        from osufusion_b200 import backbones
+        monkeypatch.setattr(backbones, "BATCHED", batched)
     ora, new = _build(kind, cfg)
     x, a, c, t, noise, mask = (v.to(dev) for v in synth_inputs(B, n, 1234))
     inputs = (x, a, c, t, noise)
@@ -145,17 +184,19 @@ def _check(kind, cfg, B, n):
     assert len(outliers) <= max(1, int(OUTLIER_FRAC * len(g_tru))), outliers[:8]
 
 
+@pytest.mark.parametrize("batched", [False, True])
 @pytest.mark.parametrize("kind,n", [("dit", 64), ("dit", 200), ("mmdit", 64), ("mmdit", 198)])
-def test_tiny_forward_backward(kind, n):
+def test_tiny_forward_backward(monkeypatch, kind, n, batched):
     from oracle.make_golden_backbones import DIT_TINY, MMDIT_TINY
-    _check(kind, DIT_TINY if kind == "dit" else MMDIT_TINY, 2, n)
+    _check(kind, DIT_TINY if kind == "dit" else MMDIT_TINY, 2, n, batched, monkeypatch)
 
 
+@pytest.mark.parametrize("batched", [False, True])
 @pytest.mark.parametrize("kind", ["dit", "mmdit"])
-def test_reference_default_width(kind):
+def test_reference_default_width(monkeypatch, kind, batched):
     """dim_h = 512, 8 heads of 64 (the reference's default head configuration; MMDiT: 2 kv heads, patch 4), depth 2, 1024 frames."""
     cfg = dict(dim_h=512, depth=2)
-    _check(kind, cfg, 2, 1024)
+    _check(kind, cfg, 2, 1024, batched, monkeypatch)
     torch.cuda.empty_cache()
 
 

@@ -6,6 +6,7 @@ oracle under torch-eager bf16 autocast on the same GPU (cuBLAS / SDPA: what the 
 """
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -80,12 +81,20 @@ def main():
         from osufusion_b200.graphs import GraphedCallable
         graphed = GraphedCallable(step_new)
         ms = time_steps(graphed, args.steps, args.warmup)
+        N.PROFILE = []                       # one instrumented eager step: CUDA events around every entry point
+        step_new()
+        torch.cuda.synchronize()
+        fam = {}
+        for name, _, e0, e1, _ in N.PROFILE:
+            fam[name] = fam.get(name, 0.0) + e0.elapsed_time(e1)
+        N.PROFILE = None
         fl = 3.0 * flops_fwd(kind, args.batch, args.frames, args.dim, args.depth)
         line = {"backbone": kind, "metric": "fwd+bwd samples/s", "value": args.batch / ms * 1e3, "ms_per_step": ms,
                 "config": {"dim_h": args.dim, "depth": args.depth, "batch": args.batch, "frames": args.frames, "heads": "8x64",
                            "cuda_graph": True},
                 "algorithmic_tflops": fl / ms / 1e9, "frac_of_measured_bf16_peak": fl / ms / 1e9 / peak, "peak_tflops": peak,
-                "gpu_launches_per_step": launches, "ms_per_step_eager_launches": ms_eager, "params_m": sum(p.numel() for p in new.parameters()) / 1e6}
+                "gpu_launches_per_step": launches, "batched_adaln_gate": os.environ.get("OF_BACKBONE_BATCHED", "0"),
+                "families_ms_one_eager_step": {k: round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}, "ms_per_step_eager_launches": ms_eager, "params_m": sum(p.numel() for p in new.parameters()) / 1e6}
         if not args.no_eager:
             ora = ora.to(dev)
 
