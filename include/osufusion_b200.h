@@ -380,6 +380,9 @@ int of_adamw_step(const of_opt_tensor* table_dev, int num_tensors, int total_cta
  *                          so the two modality streams of JointAttention (mmdit.py:98-129) are written straight into the joint
  *                          [audio ; beatmap] sequence.  bwd takes the fp32 dq/dk/dv of of_attn_bwd and the PRE-norm projection, emits
  *                          the bf16 [dq | dk | dv] operand and accumulates dgamma_q (Hq*D) / dgamma_k (Hk*D).
+ *                          variant: 1 = one thread per head vector; 2 = one thread per 16-byte vector, the D/8 lanes of a head
+ *                          reduce with shuffles (D in {8,16,32,64}; coalesced 128-byte lines, register gamma gradients);
+ *                          0 = auto (2 where supported).  Bytes/element: fwd 2 + 2, bwd 4 + 2 read, 2 written.
  *   of_row_mean_std      : statistic audio pooling `cat([a.mean(-1), a.std(-1)])` (dit.py:279-282, mmdit.py:352-355) of the fp32
  *                          (B, C, N) spectrogram -> (B, 2C) fp32 (unbiased std).
  * ------------------------------------------------------------------------------------------------ */
@@ -389,11 +392,12 @@ int of_gate_residual_fwd(const float* x32, const void* x16, long long x_ld, long
 int of_gate_mul_bwd(const float* dx32, long long d_ld, long long d_bs, const float* gate, long long gate_ld, int round_bf16, int B,
                     int L, int C, void* dx16, void* dy16, long long o_ld, long long o_bs, void* stream);
 int of_headnorm_fwd(const void* in16, long long in_ld, long long in_bs, int B, int L, int Hq, int Hk, int Hv, int D,
-                    const float* gamma_q, const float* gamma_k, float scale, void* out16, long long o_ld, long long o_bs, void* stream);
+                    const float* gamma_q, const float* gamma_k, float scale, void* out16, long long o_ld, long long o_bs, int variant,
+                    void* stream);
 int of_headnorm_bwd(const float* dq, long long dq_ld, long long dq_bs, const float* dk, const float* dv, long long dkv_ld,
                     long long dkv_bs, const void* in16, long long in_ld, long long in_bs, int B, int L, int Hq, int Hk, int Hv, int D,
                     const float* gamma_q, const float* gamma_k, float scale, void* dqkv16, long long o_ld, long long o_bs,
-                    float* dgamma_q, float* dgamma_k, void* stream);
+                    float* dgamma_q, float* dgamma_k, int variant, void* stream);
 int of_row_mean_std(const float* a, int B, int C, int N, float* out, void* stream);
 /* Batched forms (one launch for all samples; strides in elements, `*_ld` of the (B, C) vectors = their row stride):
  *   of_adaln_fwd : out_bf16[b,l,:] = LayerNorm_noaffine(x[b,l,:]) * scale1p[b,:] + shift[b,:]  (scale1p = 1 + scale, dit.py:13-15);

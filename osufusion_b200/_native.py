@@ -137,8 +137,8 @@ _SIGS = {
     "of_dora_grad": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P, P, P],
     "of_gate_residual_fwd": [P, P, LL, LL, P, LL, LL, P, LL, I, I, I, I, P, LL, LL, P],
     "of_gate_mul_bwd": [P, LL, LL, P, LL, I, I, I, I, P, P, LL, LL, P],
-    "of_headnorm_fwd": [P, LL, LL, I, I, I, I, I, I, P, P, F, P, LL, LL, P],
-    "of_headnorm_bwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, I, P, P, F, P, LL, LL, P, P, P],
+    "of_headnorm_fwd": [P, LL, LL, I, I, I, I, I, I, P, P, F, P, LL, LL, I, P],
+    "of_headnorm_bwd": [P, LL, LL, P, P, LL, LL, P, LL, LL, I, I, I, I, I, I, P, P, F, P, LL, LL, P, P, I, P],
     "of_row_mean_std": [P, I, I, I, P, P],
     "of_adaln_fwd": [P, LL, LL, I, I, I, P, LL, P, LL, F, P, LL, LL, P, P],
     "of_adaln_bwd": [P, LL, LL, P, LL, LL, I, I, I, P, LL, P, P, LL, LL, P, LL, LL, P, LL, P, LL, P],

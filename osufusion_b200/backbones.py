@@ -35,7 +35,9 @@ from .modules import (A_PAD_VALUE, X_PAD_VALUE, CrossEmbedLayer, SinusoidalPosit
 
 # adaLN / gate backward as ONE launch over all samples (of_adaln_fwd/bwd, of_gate_bwd) vs the per-sample composition of the UNet
 # path's LayerNorm kernels + of_gate_mul_bwd + of_coldot_bf16 (kept as the cross-check: OF_BACKBONE_BATCHED=0)
-BATCHED = os.environ.get("OF_BACKBONE_BATCHED", "0") != "0"
+BATCHED = os.environ.get("OF_BACKBONE_BATCHED", "1") != "0"
+# of_headnorm_fwd/bwd kernel variant (see include/osufusion_b200.h): 1 = thread per head vector, 2 = thread per 16-byte vector, 0 = auto
+HEADNORM_VARIANT = int(os.environ.get("OF_HEADNORM_VARIANT", "1"))
 
 
 # ------------------------------------------------------------------------------------------------ parameter containers
@@ -244,7 +246,8 @@ def headnorm_fwd(raw: torch.Tensor, out: torch.Tensor, Hq: int, Hk: int, D: int,
         return
     i_bs, i_ld = _bl(raw)
     o_bs, o_ld = _bl(out)
-    N.call("of_headnorm_fwd", _p(raw), i_ld, i_bs, B, L, Hq, Hk, Hk, D, _p(qn.gamma), _p(kn.gamma), float(qn.scale), _p(out), o_ld, o_bs)
+    N.call("of_headnorm_fwd", _p(raw), i_ld, i_bs, B, L, Hq, Hk, Hk, D, _p(qn.gamma), _p(kn.gamma), float(qn.scale), _p(out), o_ld, o_bs,
+           HEADNORM_VARIANT)
 
 
 def headnorm_bwd(st: ParamStore, dq, dk, dv, raw: torch.Tensor, Hq: int, Hk: int, D: int, qn, kn) -> torch.Tensor:
@@ -260,7 +263,7 @@ def headnorm_bwd(st: ParamStore, dq, dk, dv, raw: torch.Tensor, Hq: int, Hk: int
     assert _bl(dv) == (dk_bs, dk_ld)
     i_bs, i_ld = _bl(raw)
     N.call("of_headnorm_bwd", _p(dq), dq_ld, dq_bs, _p(dk), _p(dv), dk_ld, dk_bs, _p(raw), i_ld, i_bs, B, L, Hq, Hk, Hk, D, _p(qn.gamma),
-           _p(kn.gamma), float(qn.scale), _p(dqkv), W, L * W, st.grad(qn.gamma).data_ptr(), st.grad(kn.gamma).data_ptr())
+           _p(kn.gamma), float(qn.scale), _p(dqkv), W, L * W, st.grad(qn.gamma).data_ptr(), st.grad(kn.gamma).data_ptr(), HEADNORM_VARIANT)
     return dqkv
 
 

@@ -186,6 +186,140 @@ __global__ void __launch_bounds__(256) headnorm_bwd_kernel(const float* __restri
   }
 }
 
+// ---- variant 2 of the per-head RMS norm (head dims 8 / 16 / 32 / 64): thread = ONE 16-byte vector of one head, so a warp reads and
+// writes whole 128-byte lines; the D/8 lanes of a head reduce |x|^2 and <dxh, xh> with shuffles; a thread keeps its channel column
+// for every row it visits, so the gamma gradient accumulates in registers (variant 1 above: one thread per head, 128-byte strides
+// between lanes and a 32-way bank conflict on its shared-memory gamma atomics).  Grid: (row chunks, column chunks of <= 256 vectors).
+__global__ void __launch_bounds__(256) headnorm2_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long in_ld, long long in_bs,
+                                                            long long rows, int L, int Hq, int Hk, int Hv, int D,
+                                                            const float* __restrict__ gq, const float* __restrict__ gk, float scale,
+                                                            __nv_bfloat16* __restrict__ out, long long o_ld, long long o_bs, int cols,
+                                                            int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int gs = D >> 3;
+  const int total_cols = (Hq + Hk + Hv) * gs;
+  const int c0 = blockIdx.y * cols;
+  const int ncols = min(cols, total_cols - c0);
+  const int rpar = blockDim.x / ncols;
+  const int c = threadIdx.x % ncols, rsub = threadIdx.x / ncols;
+  const bool active = rsub < rpar;
+  const int col = c0 + c;
+  const int h = col / gs;
+  const bool is_v = h >= Hq + Hk;
+  V8 gv;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gv.v[j] = 1.f;
+  if (!is_v) gv = ld_f32x8((h < Hq ? gq : gk - (long long)Hq * D) + (long long)col * 8);
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(r0 + (long long)rows_per_cta, rows);
+  for (long long base = r0; base < r1; base += rpar) {
+    const long long row = base + rsub;
+    const bool valid = active && row < r1;
+    const int b = (int)(row / L), l = (int)(row % L);
+    V8 x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x.v[j] = 0.f;
+    if (valid) x = ld_bf16x8(in + b * in_bs + (long long)l * in_ld + (long long)col * 8);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += x.v[j] * x.v[j];
+    for (int o = gs >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (valid) {
+      if (!is_v) {
+        const float n = fmaxf(bf16r(sqrtf(ss)), 1e-12f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x.v[j] = (bf16r(x.v[j] / n) * gv.v[j]) * scale;
+      }
+      st_bf16x8(out + b * o_bs + (long long)l * o_ld + (long long)col * 8, x);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) headnorm2_bwd_kernel(const float* __restrict__ dq, long long dq_ld, long long dq_bs,
+                                                            const float* __restrict__ dk, const float* __restrict__ dvp, long long dkv_ld,
+                                                            long long dkv_bs, const __nv_bfloat16* __restrict__ in, long long in_ld,
+                                                            long long in_bs, long long rows, int L, int Hq, int Hk, int Hv, int D,
+                                                            const float* __restrict__ gq, const float* __restrict__ gk, float scale,
+                                                            __nv_bfloat16* __restrict__ out, long long o_ld, long long o_bs,
+                                                            float* __restrict__ dgq, float* __restrict__ dgk, int cols, int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_dg[];   // [ncols * 8]
+  const int gs = D >> 3;
+  const int total_cols = (Hq + Hk + Hv) * gs;
+  const int c0 = blockIdx.y * cols;
+  const int ncols = min(cols, total_cols - c0);
+  const int rpar = blockDim.x / ncols;
+  const int c = threadIdx.x % ncols, rsub = threadIdx.x / ncols;
+  const bool active = rsub < rpar;
+  const int col = c0 + c;
+  const int h = col / gs;
+  const bool is_v = h >= Hq + Hk;
+  for (int i = threadIdx.x; i < ncols * 8; i += blockDim.x) s_dg[i] = 0.f;
+  __syncthreads();
+  V8 gv;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gv.v[j] = 1.f;
+  if (!is_v) gv = ld_f32x8((h < Hq ? gq : gk - (long long)Hq * D) + (long long)col * 8);
+  // gradient source of this column: dq | dk | dv hold Hq*D | Hk*D | Hv*D channels
+  const float* dsrc;
+  long long s_ld, s_bs;
+  if (h < Hq) { dsrc = dq + (long long)col * 8; s_ld = dq_ld; s_bs = dq_bs; }
+  else if (!is_v) { dsrc = dk + ((long long)col * 8 - (long long)Hq * D); s_ld = dkv_ld; s_bs = dkv_bs; }
+  else { dsrc = dvp + ((long long)col * 8 - (long long)(Hq + Hk) * D); s_ld = dkv_ld; s_bs = dkv_bs; }
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(r0 + (long long)rows_per_cta, rows);
+  for (long long base = r0; base < r1; base += rpar) {
+    const long long row = base + rsub;
+    const bool valid = active && row < r1;
+    const int b = (int)(row / L), l = (int)(row % L);
+    V8 x, d;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x.v[j] = d.v[j] = 0.f;
+    if (valid) {
+      d = ld_f32x8(dsrc + b * s_bs + (long long)l * s_ld);
+      if (!is_v) x = ld_bf16x8(in + b * in_bs + (long long)l * in_ld + (long long)col * 8);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += x.v[j] * x.v[j];
+    for (int o = gs >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    float dot = 0.f;
+    V8 xh, dxh;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xh.v[j] = x.v[j] * rn;
+      dxh.v[j] = d.v[j] * gv.v[j] * scale;
+      dot += dxh.v[j] * xh.v[j];
+    }
+    for (int o = gs >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (valid) {
+      if (!is_v) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] += d.v[j] * xh.v[j] * scale;
+          d.v[j] = (dxh.v[j] - xh.v[j] * dot) * rn;
+        }
+      }
+      st_bf16x8(out + b * o_bs + (long long)l * o_ld + (long long)col * 8, d);
+    }
+  }
+  if (active && !is_v) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_dg[c * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  const long long nq = (long long)Hq * D, nqk = (long long)(Hq + Hk) * D;
+  for (int i = threadIdx.x; i < ncols * 8; i += blockDim.x) {
+    const long long ch = (long long)c0 * 8 + i;      // channel index within [q | k | v]
+    const float v = s_dg[i];
+    if (ch < nqk && v != 0.f) atomicAdd(ch < nq ? dgq + ch : dgk + (ch - nq), v);
+  }
+}
+
 // out[b, c] = mean_n a[b, c, n], out[b, C + c] = unbiased std_n a[b, c, n]; one CTA per (b, c) row, two passes (mean, then centred squares).
 __global__ void __launch_bounds__(256) row_mean_std_kernel(const float* __restrict__ a, int C, int N, float* __restrict__ out) {
   pdl_launch_dependents();
@@ -435,13 +569,37 @@ extern "C" int of_gate_mul_bwd(const float* dx32, long long d_ld, long long d_bs
   DONE()
 }
 
+static bool headnorm2_ok(int D) { return D == 8 || D == 16 || D == 32 || D == 64; }
+// column chunk (<= 256 vectors, a multiple of the D/8 lanes of a head) and rows per CTA of the variant-2 kernels
+static void headnorm2_shape(int Ht, int D, long long rows, int ctas_per_sm, int* cols, dim3* grid, int* rpc) {
+  const int total_cols = Ht * (D / 8);
+  *cols = total_cols < 256 ? total_cols : 256;
+  const int ychunks = (total_cols + *cols - 1) / *cols;
+  long long target = (long long)device_sm_count() * ctas_per_sm / ychunks;
+  if (target < 1) target = 1;
+  long long r = (rows + target - 1) / target;
+  if (r < 16) r = 16;
+  *rpc = (int)r;
+  *grid = dim3((unsigned)((rows + r - 1) / r), (unsigned)ychunks);
+}
+
 extern "C" int of_headnorm_fwd(const void* in16, long long in_ld, long long in_bs, int B, int L, int Hq, int Hk, int Hv, int D,
                                const float* gamma_q, const float* gamma_k, float scale, void* out16, long long o_ld, long long o_bs,
-                               void* stream) {
+                               int variant, void* stream) {
   OF_REQUIRE(in16 && out16 && gamma_q && gamma_k, "of_headnorm_fwd: null pointer");
   OF_REQUIRE(D >= 8 && D <= 8 * kHeadVecs && D % 8 == 0, "of_headnorm_fwd: head dim %d unsupported (8..64, multiple of 8)", D);
   OF_REQUIRE(B >= 1 && L >= 1 && Hq >= 1 && Hk >= 1 && Hv >= 0, "of_headnorm_fwd: bad sizes");
   OF_REQUIRE(in_ld % 8 == 0 && in_bs % 8 == 0 && o_ld % 8 == 0 && o_bs % 8 == 0, "of_headnorm_fwd: strides must be multiples of 8");
+  OF_REQUIRE(variant >= 0 && variant <= 2 && (variant != 2 || headnorm2_ok(D)), "of_headnorm_fwd: variant %d unsupported for D=%d", variant, D);
+  if (variant == 2 || (variant == 0 && headnorm2_ok(D))) {
+    int cols, rpc;
+    dim3 grid;
+    headnorm2_shape(Hq + Hk + Hv, D, (long long)B * L, 4, &cols, &grid, &rpc);
+    OF_CHECK_CUDA(launch_pdl(headnorm2_fwd_kernel, grid, dim3(256), 0, STREAM, reinterpret_cast<const __nv_bfloat16*>(in16), in_ld, in_bs,
+                             (long long)B * L, L, Hq, Hk, Hv, D, gamma_q, gamma_k, scale, reinterpret_cast<__nv_bfloat16*>(out16), o_ld,
+                             o_bs, cols, rpc));
+    DONE()
+  }
   OF_CHECK_CUDA(launch_pdl(headnorm_fwd_kernel, dim3(grid_for((long long)B * L * (Hq + Hk + Hv), 256)), dim3(256), 0, STREAM,
                            reinterpret_cast<const __nv_bfloat16*>(in16), in_ld, in_bs, B, L, Hq, Hk, Hv, D, gamma_q, gamma_k, scale,
                            reinterpret_cast<__nv_bfloat16*>(out16), o_ld, o_bs));
@@ -451,12 +609,22 @@ extern "C" int of_headnorm_fwd(const void* in16, long long in_ld, long long in_b
 extern "C" int of_headnorm_bwd(const float* dq, long long dq_ld, long long dq_bs, const float* dk, const float* dv, long long dkv_ld,
                                long long dkv_bs, const void* in16, long long in_ld, long long in_bs, int B, int L, int Hq, int Hk, int Hv,
                                int D, const float* gamma_q, const float* gamma_k, float scale, void* dqkv16, long long o_ld,
-                               long long o_bs, float* dgamma_q, float* dgamma_k, void* stream) {
+                               long long o_bs, float* dgamma_q, float* dgamma_k, int variant, void* stream) {
   OF_REQUIRE(dq && dk && (dv || Hv == 0) && in16 && dqkv16 && gamma_q && gamma_k && dgamma_q && dgamma_k, "of_headnorm_bwd: null pointer");
   OF_REQUIRE(D >= 8 && D <= 8 * kHeadVecs && D % 8 == 0, "of_headnorm_bwd: head dim %d unsupported (8..64, multiple of 8)", D);
   OF_REQUIRE(B >= 1 && L >= 1 && Hq >= 1 && Hk >= 1 && Hv >= 0, "of_headnorm_bwd: bad sizes");
   OF_REQUIRE(dq_ld % 4 == 0 && dq_bs % 4 == 0 && dkv_ld % 4 == 0 && dkv_bs % 4 == 0 && in_ld % 8 == 0 && in_bs % 8 == 0 && o_ld % 8 == 0 &&
                  o_bs % 8 == 0, "of_headnorm_bwd: strides must keep 16-byte alignment");
+  OF_REQUIRE(variant >= 0 && variant <= 2 && (variant != 2 || headnorm2_ok(D)), "of_headnorm_bwd: variant %d unsupported for D=%d", variant, D);
+  if (variant == 2 || (variant == 0 && headnorm2_ok(D))) {
+    int cols, rpc;
+    dim3 grid;
+    headnorm2_shape(Hq + Hk + Hv, D, (long long)B * L, 2, &cols, &grid, &rpc);
+    OF_CHECK_CUDA(launch_pdl(headnorm2_bwd_kernel, grid, dim3(256), (size_t)cols * 8 * sizeof(float), STREAM, dq, dq_ld, dq_bs, dk, dv, dkv_ld,
+                             dkv_bs, reinterpret_cast<const __nv_bfloat16*>(in16), in_ld, in_bs, (long long)B * L, L, Hq, Hk, Hv, D, gamma_q,
+                             gamma_k, scale, reinterpret_cast<__nv_bfloat16*>(dqkv16), o_ld, o_bs, dgamma_q, dgamma_k, cols, rpc));
+    DONE()
+  }
   const size_t smem = (size_t)(Hq + Hk) * D * sizeof(float);
   OF_REQUIRE(smem <= 48 * 1024, "of_headnorm_bwd: (Hq + Hk) * D = %d too large", (Hq + Hk) * D);
   long long need = ((long long)B * L * (Hq + Hk + Hv) + 255) / 256;

@@ -281,7 +281,7 @@ def of_gate_mul_bwd(d32, d_ld, d_bs, gate, gate_ld, rnd, B, L, Cc, dx16, dy16, o
     v3(dy16, BF16, B, L, Cc, o_bs, o_ld).copy_((v2(gate, F32, B, Cc, gate_ld)[:, None, :] * (rb(d) if rnd else d)).to(BF16))
 
 
-def of_headnorm_fwd(in16, in_ld, in_bs, B, L, Hq, Hk, Hv, D, gq, gk, scale, out16, o_ld, o_bs):
+def of_headnorm_fwd(in16, in_ld, in_bs, B, L, Hq, Hk, Hv, D, gq, gk, scale, out16, o_ld, o_bs, variant=0):
     W = (Hq + Hk + Hv) * D
     X = v3(in16, BF16, B, L, W, in_bs, in_ld).float()
     out = v3(out16, BF16, B, L, W, o_bs, o_ld)
@@ -294,7 +294,7 @@ def of_headnorm_fwd(in16, in_ld, in_bs, B, L, Hq, Hk, Hv, D, gq, gk, scale, out1
 
 
 def of_headnorm_bwd(dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs, in16, in_ld, in_bs, B, L, Hq, Hk, Hv, D, gq, gk, scale, dqkv16, o_ld, o_bs,
-                    dgq, dgk):
+                    dgq, dgk, variant=0):
     W = (Hq + Hk + Hv) * D
     X = v3(in16, BF16, B, L, W, in_bs, in_ld).float()
     out = v3(dqkv16, BF16, B, L, W, o_bs, o_ld)

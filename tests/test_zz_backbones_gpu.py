@@ -58,8 +58,10 @@ def test_gate_residual_and_backward(B, L, C, x_bf16):
     assert nrel(dy_g.cpu(), dy_c) <= 4e-3      # a product on a bf16 rounding boundary may round the other way (fma vs mul)
 
 
-@pytest.mark.parametrize("B,L,Hq,Hk,D,Ltot,r0", [(2, 64, 2, 2, 64, 64, 0), (2, 13, 4, 2, 32, 26, 13), (1, 300, 8, 2, 64, 600, 300)])
-def test_headnorm_forward_backward(B, L, Hq, Hk, D, Ltot, r0):
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,L,Hq,Hk,D,Ltot,r0", [(2, 64, 2, 2, 64, 64, 0), (2, 13, 4, 2, 32, 26, 13), (1, 300, 8, 2, 64, 600, 300),
+                                                 (3, 130, 16, 16, 64, 130, 0), (2, 40, 3, 1, 16, 40, 0)])
+def test_headnorm_forward_backward(B, L, Hq, Hk, D, Ltot, r0, variant):
     """Per-head q/k RMS norm; the output / gradient inputs are row slices [r0, r0 + L) of a longer joint sequence."""
     from osufusion_b200 import _native as N
     g = torch.Generator().manual_seed(2)
@@ -75,12 +77,12 @@ def test_headnorm_forward_backward(B, L, Hq, Hk, D, Ltot, r0):
         raw_, gq_, gk_, dq_, dkv_ = to(raw), to(gq), to(gk), to(dq), to(dkv)
         joint = to(torch.zeros(B, Ltot, W, dtype=torch.bfloat16))
         out = joint[:, r0:r0 + L]
-        call("of_headnorm_fwd", _p(raw_), W, L * W, B, L, Hq, Hk, Hk, D, _p(gq_), _p(gk_), scale, _p(out), W, Ltot * W)
+        call("of_headnorm_fwd", _p(raw_), W, L * W, B, L, Hq, Hk, Hk, D, _p(gq_), _p(gk_), scale, _p(out), W, Ltot * W, variant)
         dqkv = to(torch.zeros(B, L, W, dtype=torch.bfloat16))
         dgq, dgk = to(torch.zeros(Hq * D)), to(torch.zeros(Hk * D))
         dq_s, dk_s, dv_s = dq_[:, r0:r0 + L], dkv_[:, r0:r0 + L, :Hk * D], dkv_[:, r0:r0 + L, Hk * D:]
         call("of_headnorm_bwd", _p(dq_s), Hq * D, Ltot * Hq * D, _p(dk_s), _p(dv_s), 2 * Hk * D, Ltot * 2 * Hk * D, _p(raw_), W, L * W,
-             B, L, Hq, Hk, Hk, D, _p(gq_), _p(gk_), scale, _p(dqkv), W, L * W, _p(dgq), _p(dgk))
+             B, L, Hq, Hk, Hk, D, _p(gq_), _p(gk_), scale, _p(dqkv), W, L * W, _p(dgq), _p(dgk), variant)
         return joint, dqkv, dgq, dgk
 
     ref = run(lambda name, *a: getattr(FK, name)(*a), lambda t: t.clone(), 0)
@@ -164,6 +166,7 @@ def _check(kind, cfg, B, n, batched=None, monkeypatch=None):
     if batched is not None:
         from osufusion_b200 import backbones
         monkeypatch.setattr(backbones, "BATCHED", batched)
+        monkeypatch.setattr(backbones, "HEADNORM_VARIANT", 2 if batched else 1)     # both kernel variants go through the whole model
     ora, new = _build(kind, cfg)
     x, a, c, t, noise, mask = (v.to(dev) for v in synth_inputs(B, n, 1234))
     inputs = (x, a, c, t, noise)

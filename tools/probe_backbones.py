@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--only", choices=["dit", "mmdit"], default=None)
     args = ap.parse_args()
     from oracle.backbones import DiT as ODiT, MMDiT as OMMDiT
     from oracle.synth import synth_inputs, synth_state_dict
@@ -62,6 +63,8 @@ def main():
     dev = "cuda"
     x, a, c, t, noise, mask = (v.to(dev) for v in synth_inputs(args.batch, args.frames, 1234))
     for kind, new_cls, ora_cls in (("dit", DiT, ODiT), ("mmdit", MMDiT, OMMDiT)):
+        if args.only is not None and kind != args.only:
+            continue
         cfg = dict(dim_h=args.dim, depth=args.depth)
         ora = ora_cls(6, 96, 5, **cfg)
         ora.load_state_dict(synth_state_dict(ora))
@@ -93,7 +96,8 @@ def main():
                 "config": {"dim_h": args.dim, "depth": args.depth, "batch": args.batch, "frames": args.frames, "heads": "8x64",
                            "cuda_graph": True},
                 "algorithmic_tflops": fl / ms / 1e9, "frac_of_measured_bf16_peak": fl / ms / 1e9 / peak, "peak_tflops": peak,
-                "gpu_launches_per_step": launches, "batched_adaln_gate": os.environ.get("OF_BACKBONE_BATCHED", "0"),
+                "gpu_launches_per_step": launches, "batched_adaln_gate": os.environ.get("OF_BACKBONE_BATCHED", "1"),
+                "headnorm_variant": os.environ.get("OF_HEADNORM_VARIANT", "1"),
                 "families_ms_one_eager_step": {k: round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}, "ms_per_step_eager_launches": ms_eager, "params_m": sum(p.numel() for p in new.parameters()) / 1e6}
         if not args.no_eager:
             ora = ora.to(dev)
