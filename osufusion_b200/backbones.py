@@ -37,7 +37,7 @@ from .modules import (A_PAD_VALUE, X_PAD_VALUE, CrossEmbedLayer, SinusoidalPosit
 # path's LayerNorm kernels + of_gate_mul_bwd + of_coldot_bf16 (kept as the cross-check: OF_BACKBONE_BATCHED=0)
 BATCHED = os.environ.get("OF_BACKBONE_BATCHED", "1") != "0"
 # of_headnorm_fwd/bwd kernel variant (see include/osufusion_b200.h): 1 = thread per head vector, 2 = thread per 16-byte vector, 0 = auto
-HEADNORM_VARIANT = int(os.environ.get("OF_HEADNORM_VARIANT", "1"))
+HEADNORM_VARIANT = int(os.environ.get("OF_HEADNORM_VARIANT", "0"))
 
 
 # ------------------------------------------------------------------------------------------------ parameter containers
@@ -546,7 +546,7 @@ class _Backbone(nn.Module):
     def _begin(self, tape: Optional[Tape], device) -> Ctx:
         ctx = Ctx(device, self._store, tape)
         ctx.attn_variant = self.attn_variant
-        self._store.begin_forward(tape is not None)
+        self._store.begin_forward(tape is not None, self)     # all projection weights -> bf16 operands in ONE grouped launch
         if tape is not None:
             self._store.ensure_arena(self)
         return ctx

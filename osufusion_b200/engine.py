@@ -363,6 +363,20 @@ class ParamStore:
             elif kind == "Parallel":
                 conv_entry(m.fns[0].weight)
                 lin_entry(m.fns[1].weight)
+            elif kind == "DiTBlock":          # osufusion_b200/backbones.py
+                lin_entry(m.attn.to_qkv.weight)
+                lin_entry(m.ff[0].weight)
+                lin_entry(m.ff[2].weight)
+            elif kind == "MMDiTBlock":
+                for s_ in ("x", "a"):
+                    at = m.attn
+                    lin_entry(getattr(at, f"to_q_{s_}").weight, getattr(at, f"to_k_{s_}").weight, getattr(at, f"to_v_{s_}").weight)
+                    lin_entry(getattr(m, f"attn_out_{s_}").weight)
+                    ff = getattr(m, f"mlp_{s_}")
+                    lin_entry(ff[0].weight)
+                    lin_entry(ff[2].weight)
+            elif kind == "FinalLayer":
+                lin_entry(m.linear.weight)
         if not entries:
             return None
         dev = entries[0][1][0].device

@@ -320,6 +320,25 @@ def of_row_mean_std(a, B, Cc, n, out):
     v2(out, F32, B, 2 * Cc).copy_(torch.cat([A.mean(-1), A.std(-1)], 1))
 
 
+def of_pack_weights(table, num_segs, total_ctas):
+    from osufusion_b200._native import PackSeg
+    segs = (PackSeg * num_segs).from_address(int(table))
+    ctas = 0
+    for sg in segs:
+        assert sg.cta_begin == ctas
+        if sg.k == 1 and sg.cin_pad == sg.Cin:
+            n = sg.Cout * sg.Cin
+            _mem(sg.dst, n, BF16).copy_(_mem(sg.src, n, F32).to(BF16))
+            ctas += (n + 4095) // 4096
+        else:
+            w = _mem(sg.src, sg.Cout * sg.Cin * sg.k, F32).view(sg.Cout, sg.Cin, sg.k)
+            out = torch.zeros(sg.k, sg.Cout, sg.cin_pad)
+            out[:, :, :sg.Cin] = w.permute(2, 0, 1)
+            _mem(sg.dst, sg.k * sg.Cout * sg.cin_pad, BF16).copy_(out.reshape(-1).to(BF16))
+            ctas += sg.Cout * ((sg.cin_pad + 1023) // 1024)
+    assert ctas == total_ctas, (ctas, total_ctas)
+
+
 def of_adaln_fwd(x, x_ld, x_bs, B, L, Cc, s1p, sc_ld, shift, sh_ld, eps, out16, o_ld, o_bs, mean_rstd):
     X = v3(x, F32, B, L, Cc, x_bs, x_ld)
     mean = X.mean(2, keepdim=True)

@@ -97,7 +97,7 @@ def main():
                            "cuda_graph": True},
                 "algorithmic_tflops": fl / ms / 1e9, "frac_of_measured_bf16_peak": fl / ms / 1e9 / peak, "peak_tflops": peak,
                 "gpu_launches_per_step": launches, "batched_adaln_gate": os.environ.get("OF_BACKBONE_BATCHED", "1"),
-                "headnorm_variant": os.environ.get("OF_HEADNORM_VARIANT", "1"),
+                "headnorm_variant": os.environ.get("OF_HEADNORM_VARIANT", "0 (auto: 2)"),
                 "families_ms_one_eager_step": {k: round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}, "ms_per_step_eager_launches": ms_eager, "params_m": sum(p.numel() for p in new.parameters()) / 1e6}
         if not args.no_eager:
             ora = ora.to(dev)
