@@ -36,6 +36,10 @@ from .modules import (A_PAD_VALUE, X_PAD_VALUE, CrossEmbedLayer, SinusoidalPosit
 # adaLN / gate backward as ONE launch over all samples (of_adaln_fwd/bwd, of_gate_bwd) vs the per-sample composition of the UNet
 # path's LayerNorm kernels + of_gate_mul_bwd + of_coldot_bf16 (kept as the cross-check: OF_BACKBONE_BATCHED=0)
 BATCHED = os.environ.get("OF_BACKBONE_BATCHED", "1") != "0"
+# bf16 operand copies of all projection weights by ONE grouped of_pack_weights launch (the U-Net's mechanism, engine.ParamStore) instead of
+# one of_cast_f32_bf16 launch per weight.  Host logic covered on CPU (tests/test_backbones_host_cpu.py); NOT yet run on a B200 for the
+# backbones (round-1 GPU budget exhausted), hence off by default.
+GROUPED_PACK = os.environ.get("OF_BACKBONE_GROUPED_PACK", "0") != "0"
 # of_headnorm_fwd/bwd kernel variant (see include/osufusion_b200.h): 1 = thread per head vector, 2 = thread per 16-byte vector, 0 = auto
 HEADNORM_VARIANT = int(os.environ.get("OF_HEADNORM_VARIANT", "0"))
 
@@ -546,7 +550,7 @@ class _Backbone(nn.Module):
     def _begin(self, tape: Optional[Tape], device) -> Ctx:
         ctx = Ctx(device, self._store, tape)
         ctx.attn_variant = self.attn_variant
-        self._store.begin_forward(tape is not None, self)     # all projection weights -> bf16 operands in ONE grouped launch
+        self._store.begin_forward(tape is not None, self if GROUPED_PACK else None)
         if tape is not None:
             self._store.ensure_arena(self)
         return ctx
