@@ -13,7 +13,7 @@ import math
 import torch
 
 BF16, F32 = torch.bfloat16, torch.float32
-_SIZE = {BF16: 2, F32: 4, torch.float64: 8}
+_SIZE = {BF16: 2, F32: 4, torch.float64: 8, torch.int32: 4, torch.int64: 8}
 
 
 def _mem(ptr, n, dtype):
@@ -87,7 +87,11 @@ def of_gemm(g):
             v3(g.out_bf16, BF16, Bn, rows, Nn, g.out_bf16_batch_stride, g.out_bf16_ld).copy_(v.to(BF16))
         if g.out_f32:
             v3(g.out_f32, F32, Bn, rows, Nn, g.out_f32_batch_stride, g.out_f32_ld).copy_(v)
-        assert not g.stats, "stats epilogue not emulated"
+        if g.stats:
+            vr = rb(v).double()
+            st = _mem(g.stats, 2 * Bn, torch.float64).view(Bn, 2)
+            st[:, 0] += vr.sum((1, 2))
+            st[:, 1] += (vr * vr).sum((1, 2))
     else:
         M = K
         dY = v3(g.a, BF16, Bn, rows, M, g.a_batch_stride, g.a_ld).float()
@@ -367,6 +371,283 @@ def of_gate_bwd(d32, d_ld, d_bs, gate, gate_ld, y16, y_ld, y_bs, rnd, B, L, Cc, 
     dr = rb(d) if rnd else d
     v3(dy16, BF16, B, L, Cc, o_bs, o_ld).copy_((v2(gate, F32, B, Cc, gate_ld)[:, None, :] * dr).to(BF16))
     v2(dgate, F32, B, Cc, dg_ld).add_((dr * v3(y16, BF16, B, L, Cc, y_bs, y_ld).float()).sum(1))
+
+
+# ------------------------------------------------------------------------------------------------ U-Net path (of_rb_*, RoPE, FiLM, ...)
+def _gn(a):
+    """GroupNorm(1, C) + FiLM + SiLU recompute shared by the of_rb_* kernels: returns y, xhat, z, f, h, rstd, sp1."""
+    B, L, Cc = a.B, a.L, a.C
+    y = v3(a.y, BF16, B, L, Cc, a.y_bs, a.y_ld).float()
+    st = _mem(a.stats, 2 * B, torch.float64).view(B, 2)
+    n = float(L * Cc)
+    mean = (st[:, 0] / n)
+    var = (st[:, 1] / n - mean * mean).clamp_min(0)
+    rstd = (1.0 / torch.sqrt(var + a.eps)).float().view(B, 1, 1)
+    mean = mean.float().view(B, 1, 1)
+    gamma, beta = _mem(a.gamma, Cc, F32), _mem(a.beta, Cc, F32)
+    xhat = (y - mean) * rstd
+    z = xhat * gamma + beta
+    sp1 = None
+    f = z
+    if a.ss:
+        ss = _mem(a.ss, B * 2 * Cc, F32).view(B, 2 * Cc)
+        sp1 = rb(ss[:, :Cc] + 1.0)[:, None, :]
+        f = z * sp1 + ss[:, None, Cc:]
+    return y, xhat, z, f, silu(f), rstd, sp1
+
+
+def of_rb_apply_fwd(a):
+    a = _struct(a)
+    h = _gn(a)[4]
+    v3(a.out_bf16, BF16, a.B, a.L, a.C, a.out_bf16_bs, a.out_bf16_ld).copy_(h.to(BF16))
+
+
+def of_rb_rowdot(a):
+    a = _struct(a)
+    B, L, Cc = a.B, a.L, a.C
+    h = rb(_gn(a)[4])
+    out = _mem(a.out_rows, B * L, F32).view(B, L)
+    if a.mode == 0:
+        w = rb(_mem(a.vec, Cc, F32))
+        bias = _mem(a.vec_bias, 1, F32)[0] if a.vec_bias else 0.0
+        out.copy_(rb((h * w).sum(-1) + bias))
+    else:
+        w = v2(a.vec, F32, B, Cc, a.vec_bs)
+        out.copy_((h * w[:, None, :]).sum(-1))
+
+
+def of_softmax_rows(rows, B, L):
+    r = _mem(rows, B * L, F32).view(B, L)
+    r.copy_(torch.softmax(r, dim=-1))
+
+
+def of_softmax_bwd_rows(p, rd, B, L):
+    P, R = _mem(p, B * L, F32).view(B, L), _mem(rd, B * L, F32).view(B, L)
+    R.copy_(P * (R - (P * R).sum(-1, keepdim=True)))
+
+
+def of_rb_pool(a):
+    a = _struct(a)
+    B, L, Cc = a.B, a.L, a.C
+    h = rb(_gn(a)[4])
+    P = rb(_mem(a.p, B * L, F32).view(B, L))
+    _mem(a.acc_bc, B * Cc, F32).view(B, Cc).add_((h * P[:, :, None]).sum(1))
+
+
+def of_rb_logit_pool(a, part, pooled):
+    a = _struct(a)
+    B, L, Cc = a.B, a.L, a.C
+    h = rb(_gn(a)[4])
+    w = rb(_mem(a.vec, Cc, F32))
+    bias = _mem(a.vec_bias, 1, F32)[0] if a.vec_bias else 0.0
+    P = torch.softmax(rb((h * w).sum(-1) + bias), dim=-1)
+    _mem(a.out_rows, B * L, F32).view(B, L).copy_(P)
+    _mem(pooled, B * Cc, F32).view(B, Cc).copy_((h * P[:, :, None]).sum(1))
+
+
+def of_rb_gate_fwd(a):
+    a = _struct(a)
+    B, L, Cc = a.B, a.L, a.C
+    h = _gn(a)[4]
+    res = v3(a.res_f32, F32, B, L, Cc, a.res_f32_bs, a.res_f32_ld) if a.res_f32 else \
+        v3(a.res_bf16, BF16, B, L, Cc, a.res_bf16_bs, a.res_bf16_ld).float()
+    o = h * _mem(a.gate, B * Cc, F32).view(B, 1, Cc) + res
+    if a.out_f32:
+        v3(a.out_f32, F32, B, L, Cc, a.out_f32_bs, a.out_f32_ld).copy_(o)
+    if a.out_bf16:
+        v3(a.out_bf16, BF16, B, L, Cc, a.out_bf16_bs, a.out_bf16_ld).copy_(o.to(BF16))
+
+
+def of_rb_gate_bwd_reduce(a):
+    a = _struct(a)
+    B, L, Cc = a.B, a.L, a.C
+    h = _gn(a)[4]
+    d = v3(a.dout_f32, F32, B, L, Cc, a.dout_f32_bs, a.dout_f32_ld)
+    _mem(a.acc_bc, B * Cc, F32).view(B, Cc).add_((d * h).sum(1))
+
+
+def of_rb_bwd_pass1(a):
+    a = _struct(a)
+    B, L, Cc = a.B, a.L, a.C
+    y, xhat, z, f, h, rstd, sp1 = _gn(a)
+    gamma = _mem(a.gamma, Cc, F32)
+    if a.mode == 0:
+        d = v3(a.dout_f32, F32, B, L, Cc, a.dout_f32_bs, a.dout_f32_ld)
+        gate = _mem(a.gate, B * Cc, F32).view(B, 1, Cc)
+        dpool = _mem(a.dpooled, B * Cc, F32).view(B, 1, Cc)
+        P = rb(_mem(a.p, B * L, F32).view(B, L))[:, :, None]
+        da = _mem(a.da, B * L, F32).view(B, L)[:, :, None]
+        wk = rb(_mem(a.wk, Cc, F32))
+        dh = d * gate + dpool * P + da * wk
+        _mem(a.dwk, Cc, F32).add_((da * rb(h)).sum((0, 1)))
+        if a.dbk:
+            _mem(a.dbk, 1, F32).add_(da.sum())
+        if a.dout_bf16:
+            v3(a.dout_bf16, BF16, B, L, Cc, a.dout_bf16_bs, a.dout_bf16_ld).copy_(d.to(BF16))
+    else:
+        dh = v3(a.dh_bf16, BF16, B, L, Cc, a.dh_bs, a.dh_ld).float()
+    df = dh * dsilu(f)
+    dz = df
+    if a.ss:
+        dss = _mem(a.dss, B * 2 * Cc, F32).view(B, 2 * Cc)
+        dss[:, :Cc] += (df * z).sum(1)
+        dss[:, Cc:] += df.sum(1)
+        dz = df * sp1
+    _mem(a.dgamma, Cc, F32).add_((dz * xhat).sum((0, 1)))
+    _mem(a.dbeta, Cc, F32).add_(dz.sum((0, 1)))
+    dx = dz * gamma
+    v3(a.dxhat_bf16, BF16, B, L, Cc, a.dxhat_bs, a.dxhat_ld).copy_(dx.to(BF16))
+    dxr = rb(dx)
+    ds = _mem(a.dstats, 2 * B, torch.float64).view(B, 2)
+    ds[:, 0] += dxr.sum((1, 2)).double()
+    ds[:, 1] += (dxr * xhat).sum((1, 2)).double()
+
+
+def of_rb_bwd_apply(a):
+    a = _struct(a)
+    B, L, Cc = a.B, a.L, a.C
+    y, xhat, z, f, h, rstd, sp1 = _gn(a)
+    n = float(L * Cc)
+    ds = _mem(a.dstats, 2 * B, torch.float64).view(B, 2)
+    m1, m2 = (ds[:, 0] / n).float().view(B, 1, 1), (ds[:, 1] / n).float().view(B, 1, 1)
+    dx = v3(a.dxhat_bf16, BF16, B, L, Cc, a.dxhat_bs, a.dxhat_ld).float()
+    o = rstd * (dx - m1 - xhat * m2)
+    v3(a.dy_bf16, BF16, B, L, Cc, a.dy_bs, a.dy_ld).copy_(o.to(BF16))
+    if a.dbias:
+        _mem(a.dbias, Cc, F32).add_(rb(o).sum((0, 1)))
+
+
+def _rope_tabs(cos_tab, sin_tab, L, D, table_f32):
+    dt = F32 if table_f32 else BF16
+    return _mem(cos_tab, L * D, dt).view(L, D).float(), _mem(sin_tab, L * D, dt).view(L, D).float()
+
+
+def of_rope_fwd(qkv, ld, bs, B, L, H, KVH, D, cos_tab, sin_tab, table_f32):
+    W = (H + KVH) * D
+    t = v3(qkv, BF16, B, L, W, bs, ld)
+    x = t.float().view(B, L, H + KVH, D)
+    cos, sin = _rope_tabs(cos_tab, sin_tab, L, D, table_f32)
+    cos, sin = cos[None, :, None, :], sin[None, :, None, :]
+    half = D // 2
+    rot = torch.cat([-x[..., half:], x[..., :half]], dim=-1)
+    o = (x * cos + rot * sin) if table_f32 else (rb(x * cos) + rb(rot * sin))
+    t.copy_(o.reshape(B, L, W).to(BF16))
+
+
+def of_rope_bwd(dq, dq_ld, dq_bs, dk, dv, dkv_ld, dkv_bs, out16, o_ld, o_bs, B, L, H, KVH, D, cos_tab, sin_tab, table_f32):
+    g = torch.cat([v3(dq, F32, B, L, H * D, dq_bs, dq_ld), v3(dk, F32, B, L, KVH * D, dkv_bs, dkv_ld)], dim=2).view(B, L, H + KVH, D)
+    cos, sin = _rope_tabs(cos_tab, sin_tab, L, D, table_f32)
+    cos, sin = cos[None, :, None, :], sin[None, :, None, :]
+    half = D // 2
+    gs = g * sin
+    dx = g * cos + torch.cat([gs[..., half:], -gs[..., :half]], dim=-1)      # transpose of the rotation
+    out = v3(out16, BF16, B, L, (H + 2 * KVH) * D, o_bs, o_ld)
+    out[:, :, :(H + KVH) * D] = dx.reshape(B, L, -1).to(BF16)
+    out[:, :, (H + KVH) * D:] = v3(dv, F32, B, L, KVH * D, dkv_bs, dkv_ld).to(BF16)
+
+
+def of_upsample2x_fwd(x, x_ld, x_bs, B, L, Cc, out, o_ld, o_bs):
+    X = v3(x, BF16, B, L, Cc, x_bs, x_ld)
+    v3(out, BF16, B, 2 * L, Cc, o_bs, o_ld).copy_(X.repeat_interleave(2, dim=1))
+
+
+def of_upsample2x_bwd(d, d_ld, d_bs, B, L, Cc, out32, out16, o_ld, o_bs):
+    D2 = v3(d, F32, B, 2 * L, Cc, d_bs, d_ld)
+    o = D2[:, 0::2] + D2[:, 1::2]
+    if out32:
+        v3(out32, F32, B, L, Cc, o_bs, o_ld).copy_(o)
+    if out16:
+        v3(out16, BF16, B, L, Cc, o_bs, o_ld).copy_(o.to(BF16))
+
+
+def of_pack_conv_weight(w, Cout, Cin, k, out, cin_pad, tap_offset, taps_total):
+    Wt = _mem(w, Cout * Cin * k, F32).view(Cout, Cin, k)
+    o = _mem(out, taps_total * Cout * cin_pad, BF16).view(taps_total, Cout, cin_pad)
+    o[tap_offset:tap_offset + k, :, :Cin] = Wt.permute(2, 0, 1).to(BF16)
+    o[tap_offset:tap_offset + k, :, Cin:] = 0
+
+
+def of_unpack_conv_wgrad(packed, Cout, Cin, k, cin_pad, tap_offset, dw, accumulate, rezero):
+    Pk = _mem(packed, (tap_offset + k) * Cout * cin_pad, F32).view(tap_offset + k, Cout, cin_pad)
+    g = Pk[tap_offset:tap_offset + k, :, :Cin].permute(1, 2, 0)
+    D = _mem(dw, Cout * Cin * k, F32).view(Cout, Cin, k)
+    D.copy_(D + g if accumulate else g)
+    if rezero:
+        Pk[tap_offset:tap_offset + k, :, :Cin] = 0
+
+
+def _film_groups(groups, num_groups):
+    from osufusion_b200._native import FilmGroup
+    return (FilmGroup * num_groups).from_address(int(groups))
+
+
+def of_film_fwd(groups, num_groups, total_rows, x, M, K, out):
+    X = v2(x, F32, M, K)
+    for g in _film_groups(groups, num_groups):
+        W = rb(v2(g.W, F32, g.N, K))
+        y = X @ W.t()
+        if g.bias:
+            y = y + _mem(g.bias, g.N, F32)
+        _mem(out + 4 * g.out_off, M * g.N, F32).view(M, g.N).copy_(rb(y))
+
+
+def of_film_bwd(groups, chunks, num_chunks, dss, x, M, K, d_emb):
+    X = v2(x, F32, M, K)
+    for g in _film_groups(groups, num_groups=len(set(_mem(chunks, 2 * num_chunks, torch.int32)[0::2].tolist()))):
+        d = _mem(dss + 4 * g.out_off, M * g.N, F32).view(M, g.N)
+        if g.dW:
+            v2(g.dW, F32, g.N, K).copy_(d.t() @ X)
+        if g.dbias:
+            _mem(g.dbias, g.N, F32).copy_(d.sum(0))
+        v2(d_emb, F32, M, K).add_(d @ rb(v2(g.W, F32, g.N, K)))
+
+
+def of_mse_fwd(pred, ld, bs, x, noise, ta, tb, orig_len, B, Cc, n, accum2, loss):
+    P = v3(pred, BF16, B, n, Cc, bs, ld).float().transpose(1, 2)
+    tgt = tb * _mem(noise, B * Cc * n, F32).view(B, Cc, n)
+    if ta != 0.0:
+        tgt = tgt + ta * _mem(x, B * Cc * n, F32).view(B, Cc, n)
+    mask = torch.ones(B, 1, n)
+    if orig_len:
+        ol = _mem(orig_len, B, torch.int64)
+        mask = (torch.arange(n)[None, :] < ol[:, None]).float()[:, None, :]
+    se, cnt = (mask * (P - tgt) ** 2).sum(), (mask.expand(B, Cc, n)).sum()
+    _mem(accum2, 2, F32).copy_(torch.stack([se, cnt]))
+    _mem(loss, 1, F32).copy_((se / cnt).view(1))
+
+
+def of_mse_bwd(pred, ld, bs, x, noise, ta, tb, orig_len, B, Cc, n, Lp, Cp, accum2, gscale, dpred):
+    P = v3(pred, BF16, B, n, Cc, bs, ld).float().transpose(1, 2)
+    tgt = tb * _mem(noise, B * Cc * n, F32).view(B, Cc, n)
+    if ta != 0.0:
+        tgt = tgt + ta * _mem(x, B * Cc * n, F32).view(B, Cc, n)
+    mask = torch.ones(B, 1, n)
+    if orig_len:
+        ol = _mem(orig_len, B, torch.int64)
+        mask = (torch.arange(n)[None, :] < ol[:, None]).float()[:, None, :]
+    g = 2.0 * mask * (P - tgt) / _mem(accum2, 2, F32)[1] * (_mem(gscale, 1, F32)[0] if gscale else 1.0)
+    o = torch.zeros(B, Lp, Cp)
+    o[:, :n, :Cc] = g.transpose(1, 2)
+    _mem(dpred, B * Lp * Cp, BF16).view(B, Lp, Cp).copy_(o.to(BF16))
+
+
+def of_sampler_update(xin, cond, null_, ld, bs, s, mode, c_eps, c_div, c_x0, c_dir, B, Cc, n, xout, packed, Lp, Cp, pad):
+    e = v3(cond, BF16, B, n, Cc, bs, ld).float().transpose(1, 2)
+    if null_:
+        nl = v3(null_, BF16, B, n, Cc, bs, ld).float().transpose(1, 2)
+        e = rb(nl + rb(rb(e - nl) * s))
+    X = _mem(xin, B * Cc * n, F32).view(B, Cc, n)
+    if mode == 0:
+        x0 = ((X - rb(c_eps * e)) / c_div).clamp(-1.0, 1.0)
+        o = c_x0 * x0 + rb(c_dir * e)
+    else:
+        o = X + rb(c_eps * e)
+    _mem(xout, B * Cc * n, F32).view(B, Cc, n).copy_(o)
+    if packed:
+        pk = torch.zeros(B, Lp, Cp)
+        pk[:, :n, :Cc] = o.transpose(1, 2)
+        pk[:, n:, :Cc] = pad
+        _mem(packed, B * Lp * Cp, BF16).view(B, Lp, Cp).copy_(pk.to(BF16))
 
 
 _TABLE = {k: v for k, v in globals().items() if k.startswith("of_")}
