@@ -650,6 +650,86 @@ def of_sampler_update(xin, cond, null_, ld, bs, s, mode, c_eps, c_div, c_x0, c_d
         _mem(packed, B * Lp * Cp, BF16).view(B, Lp, Cp).copy_(pk.to(BF16))
 
 
+# ------------------------------------------------------------------------------------------------ LoRA / DoRA, optimizer
+def _packed_view(ptr, dtype, k, Cout, cin_pad, tap_stride):
+    return _mem(ptr, (k - 1) * tap_stride + Cout * cin_pad, dtype).as_strided((k, Cout, cin_pad), (tap_stride, cin_pad, 1))
+
+
+def of_scale_cast_f32_bf16(src, scale, dst, n):
+    _mem(dst, n, BF16).copy_((_mem(src, n, F32) * scale).to(BF16))
+
+
+def of_dora_scale_pack(V, mag, Cout, Cin, k, n2_out, packed, cin_pad, tap_stride):
+    Vm = _mem(V, Cout * Cin * k, F32).view(Cout, Cin * k)
+    n2 = (Vm * Vm).sum(1)
+    _mem(n2_out, Cout, F32).copy_(n2)
+    sc = _mem(mag, Cout, F32) / n2.sqrt() if mag else torch.ones(Cout)
+    out = _packed_view(packed, BF16, k, Cout, cin_pad, tap_stride)
+    out[:, :, :Cin] = (sc[:, None] * Vm).view(Cout, Cin, k).permute(2, 0, 1).to(BF16)
+
+
+def of_dora_merge(W, A, Bm, mag, scaling, Cout, Cin, k, r, n2_ws, packed, cin_pad, tap_stride, s_out):
+    E = Cin * k
+    Vm = _mem(W, Cout * E, F32).view(Cout, E) + scaling * (_mem(Bm, Cout * r, F32).view(Cout, r) @ _mem(A, r * E, F32).view(r, E))
+    n2 = (Vm * Vm).sum(1)
+    _mem(n2_ws, Cout, F32).copy_(n2)
+    sc = _mem(mag, Cout, F32) / n2.sqrt() if mag else torch.ones(Cout)
+    if s_out:
+        _mem(s_out, Cout, F32).copy_(sc)
+    out = _packed_view(packed, BF16, k, Cout, cin_pad, tap_stride)
+    out[:, :, :Cin] = (sc[:, None] * Vm).view(Cout, Cin, k).permute(2, 0, 1).to(BF16)
+
+
+def of_dora_rankr_prep(Bm, mag, n2, scaling, Cout, r, Bst, rowscale):
+    sc = _mem(mag, Cout, F32) / _mem(n2, Cout, F32).sqrt() if mag else torch.ones(Cout)
+    rs = scaling * sc
+    _mem(rowscale, Cout, F32).copy_(rs)
+    _mem(Bst, r * Cout, BF16).view(r, Cout).copy_((rs[:, None] * _mem(Bm, Cout * r, F32).view(Cout, r)).t().to(BF16))
+
+
+def of_dora_rankr_finish(dBraw, rowscale, gB, dm, mag, gmag, Cout, r):
+    _mem(gB, Cout * r, F32).view(Cout, r).add_(_mem(rowscale, Cout, F32)[:, None] * _mem(dBraw, Cout * r, F32).view(Cout, r))
+    if gmag:
+        _mem(gmag, Cout, F32).add_(_mem(dm, Cout, F32) / _mem(mag, Cout, F32))
+
+
+def of_dora_grad(W, A, Bm, mag, scaling, Cout, Cin, k, r, n2, dWp, cin_pad, tap_stride, dA, dB, dmag):
+    E = Cin * k
+    Am, Bmat = _mem(A, r * E, F32).view(r, E), _mem(Bm, Cout * r, F32).view(Cout, r)
+    Vm = _mem(W, Cout * E, F32).view(Cout, E) + scaling * (Bmat @ Am)
+    dWeff = _packed_view(dWp, F32, k, Cout, cin_pad, tap_stride)[:, :, :Cin].permute(1, 2, 0).reshape(Cout, E)
+    if mag:
+        nrm = _mem(n2, Cout, F32).sqrt()
+        sc = _mem(mag, Cout, F32) / nrm
+        _mem(dmag, Cout, F32).add_((dWeff * Vm).sum(1) / nrm)
+    else:
+        sc = torch.ones(Cout)
+    dV = sc[:, None] * dWeff
+    _mem(dA, r * E, F32).view(r, E).add_(scaling * (Bmat.t() @ dV))
+    _mem(dB, Cout * r, F32).view(Cout, r).add_(scaling * (dV @ Am.t()))
+
+
+def of_grad_sumsq(grads, n, out):
+    g = _mem(grads, n, F32).double()
+    _mem(out, 1, torch.float64).copy_((g * g).sum().view(1))
+
+
+def of_adamw_step(table, num, total_ctas, grads, exp_avg, exp_avg_sq, sumsq, max_norm, lr, b1, b2, eps, wd, step):
+    from osufusion_b200._native import OptTensor
+    clip = 1.0
+    if sumsq and max_norm > 0:
+        clip = min(1.0, max_norm / (float(_mem(sumsq, 1, torch.float64)[0]) ** 0.5 + 1e-6))
+    bc1, bc2s = 1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5
+    for t in (OptTensor * num).from_address(int(table)):
+        p = _mem(t.param, t.numel, F32)
+        g = _mem(grads + 4 * t.arena_off, t.numel, F32) * clip
+        m, v = _mem(exp_avg + 4 * t.arena_off, t.numel, F32), _mem(exp_avg_sq + 4 * t.arena_off, t.numel, F32)
+        p.mul_(1.0 - lr * wd)
+        m.mul_(b1).add_((1.0 - b1) * g)
+        v.mul_(b2).add_((1.0 - b2) * g * g)
+        p.sub_((lr / bc1) * m / (v.sqrt() / bc2s + eps))
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith("of_")}
 CALLS = []
 

@@ -136,3 +136,135 @@ def test_sampler_wrapper_matches_oracle(fake_abi, kind, steps):
         assert nrel(y_new, y_ref) < (3e-2 if steps <= 2 else 0.3), (kind, steps, scale, nrel(y_new, y_ref))
         assert (y_new - y_ref).abs().mean() < 3e-2 * y_ref.abs().mean().clamp_min(0.1)
     assert "of_sampler_update" in set(fake_abi.CALLS)
+
+
+# ------------------------------------------------------------------------------------------------ LoRA / DoRA and the optimizer tail
+def _lora_build(use_dora):
+    """Engine UNet with injected adapters + the oracle UNet whose adapted layers evaluate the reference's three-term forward
+    (lora_layers.py:59-92) under autograd on cloned leaves — the construction of tests/test_lora_gpu.py, on the CPU."""
+    from oracle.denoiser import UNet as OracleUNet
+    from oracle.dora import dora_conv1d, dora_linear
+    from oracle.synth import TINY
+    from osufusion_b200 import lora
+    from osufusion_b200.modules import UNet
+    F = torch.nn.functional
+    torch.manual_seed(0)
+    ora = OracleUNet(6, 96, 5, **TINY)
+    torch.nn.init.normal_(ora.final_conv.weight, std=0.02)
+    new = UNet(6, 96, 5, **TINY)
+    new.load_state_dict(ora.state_dict())
+    names = lora.inject_adapters(new, r=8, lora_alpha=16, use_dora=use_dora)
+    for p in ora.parameters():
+        p.requires_grad_(False)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    leaves = {}
+    for name in names:
+        ad = new.get_submodule(name)
+        with torch.no_grad():
+            ad.lora_B["default"].weight.copy_(0.05 * torch.randn(ad.lora_B["default"].weight.shape, generator=g))
+            if use_dora:
+                ad.magnitude().mul_(1 + 0.1 * torch.randn(ad.magnitude().shape, generator=g))
+        A = ad.lora_A["default"].weight.detach().clone().requires_grad_(True)
+        Bm = ad.lora_B["default"].weight.detach().clone().requires_grad_(True)
+        mag = ad.magnitude().detach().clone().requires_grad_(True) if use_dora else None
+        leaves[name] = (A, Bm, mag)
+        om = ora.get_submodule(name)
+        sc = ad.scaling
+        if isinstance(om, torch.nn.Conv1d):
+            def fwd(x, om=om, A=A, Bm=Bm, mag=mag, sc=sc):
+                if mag is None:
+                    return F.conv1d(x, om.weight, om.bias, padding=1) + F.conv1d(F.conv1d(x, A, None, padding=1), Bm) * sc
+                return dora_conv1d(x, om.weight, om.bias, A, Bm, mag, sc, padding=om.padding[0])
+        else:
+            def fwd(x, om=om, A=A, Bm=Bm, mag=mag, sc=sc):
+                if mag is None:
+                    return F.linear(x, om.weight, om.bias) + F.linear(F.linear(x, A), Bm) * sc
+                return dora_linear(x, om.weight, om.bias, A, Bm, mag, sc)
+        om.forward = fwd
+    return ora, new, names, leaves
+
+
+@pytest.mark.parametrize("rank_r,merge_tc", [(True, True), (False, False)])
+@pytest.mark.parametrize("use_dora", [True, False])
+def test_lora_dora_tape_matches_oracle(fake_abi, monkeypatch, use_dora, rank_r, merge_tc):
+    from oracle.synth import synth_inputs
+    from osufusion_b200 import engine
+    from osufusion_b200.modules import UNetFunction
+    monkeypatch.setattr(engine, "LORA_RANK_R", rank_r)
+    monkeypatch.setattr(engine, "LORA_MERGE_TC", merge_tc)
+    ora, new, names, leaves = _lora_build(use_dora)
+    x, a, c, t, noise, keep = synth_inputs(2, 56, 5)
+
+    def run_oracle(autocast):
+        for vs in leaves.values():
+            for v in vs:
+                if v is not None:
+                    v.grad = None
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            y = ora(x, a, t, c, cond_mask=keep)
+        torch.nn.functional.mse_loss(y.float(), noise).backward()
+        return y.detach().float(), {n: tuple(None if v is None else v.grad.detach().clone() for v in leaves[n]) for n in names}
+
+    y_ref, g_ref = run_oracle(True)
+    y_tru, g_tru = run_oracle(False)
+    y_new = UNetFunction.apply(new, x, a, t, c, keep, *list(new.parameters()))
+    torch.nn.functional.mse_loss(y_new, noise).backward()
+    assert nrel(y_new, y_tru) <= max(1e-2, 2 * nrel(y_ref, y_tru))
+    assert all(p.grad is None for n, p in new.named_parameters() if "lora_" not in n)      # base weights stay frozen
+    bad = []
+    for n in names:
+        ad = new.get_submodule(n)
+        mine = (ad.lora_A["default"].weight.grad, ad.lora_B["default"].weight.grad, ad.magnitude().grad if use_dora else None)
+        for which, gm, gr, gt in zip("ABm", mine, g_ref[n], g_tru[n]):
+            if gt is None:
+                continue
+            e_new, e_ref = nrel(gm.view(gt.shape), gt), nrel(gr, gt)
+            if e_new > max(2e-2, 3 * e_ref, 6e-2 if use_dora else 0.0):
+                bad.append((n, which, e_new, e_ref))
+    assert not bad, bad[:6]
+    used = set(fake_abi.CALLS)
+    if rank_r:
+        assert {"of_dora_rankr_prep", "of_dora_rankr_finish"} <= used and "of_dora_grad" not in used
+    else:
+        assert "of_dora_grad" in used
+    assert ("of_dora_scale_pack" in used) == merge_tc and ("of_dora_merge" in used) == (not merge_tc)
+
+
+@pytest.mark.parametrize("max_norm", [1.0, None])
+def test_fused_adamw_host_logic_matches_torch(fake_abi, max_norm):
+    import copy
+
+    from oracle.synth import TINY, synth_inputs
+    from osufusion_b200.modules import UNet, UNetFunction
+    from osufusion_b200.optim import FusedAdamW, cosine_schedule_with_warmup
+    torch.manual_seed(0)
+    net = UNet(6, 96, 5, **TINY)
+    torch.nn.init.normal_(net.final_conv.weight, std=0.02)
+    ref = copy.deepcopy(net)
+    opt = FusedAdamW(net, lr=1e-3, weight_decay=1e-2, max_grad_norm=max_norm)
+    sched = cosine_schedule_with_warmup(opt, 2, 10)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=1e-2)
+    rsched = cosine_schedule_with_warmup(ropt, 2, 10)
+    x, a, c, t, noise, keep = synth_inputs(2, 48, 7)
+    y0 = None
+    for it in range(3):
+        net.zero_grad(set_to_none=True)
+        y = UNetFunction.apply(net, x, a, t, c, keep, *list(net.parameters()))
+        y0 = y.detach().clone() if y0 is None else y0
+        torch.nn.functional.mse_loss(y, noise).backward()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            q.grad = p.grad.detach().clone()
+        if max_norm is not None:
+            tn = torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm)
+        ropt.step()
+        rsched.step()
+        opt.step()
+        sched.step()
+        if max_norm is not None:
+            assert abs(float(opt.grad_norm) - float(tn)) <= 1e-4 * float(tn)
+        worst = max(((p - q).abs().max() / q.abs().max().clamp_min(1e-12)).item() for p, q in zip(net.parameters(), ref.parameters()))
+        assert worst < 1e-5, (it, worst)
+    # parameters were updated through raw pointers: the operand caches must have been invalidated (param_epoch)
+    with torch.no_grad():
+        out16, _ = net.run(None, x, a, t, c, keep)
+        assert nrel(net.unpack(out16, 48), y0) > 1e-4
