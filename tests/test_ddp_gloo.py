@@ -1,4 +1,5 @@
-"""N>1 host logic on CPU: world_size-2 gloo run of the gradient arena / bucket scheduler (osufusion_b200/ddp.py)."""
+"""N>1 host logic on CPU: world_size-2 gloo runs of the gradient arena / bucket scheduler (osufusion_b200/ddp.py) — once with a
+hand-driven stand-in for the backward tape, once with the REAL engine tape executed through the emulated C-ABI (tests/fake_native.py)."""
 import os
 import socket
 
@@ -58,6 +59,64 @@ def test_bucketed_allreduce_world2_gloo():
     for p in procs:
         p.start()
     res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == "ok" for r in res)
+
+
+def _worker_real_tape(rank, world, port, out):
+    """Every rank runs the real engine forward/backward (through the emulated C-ABI) on its own batch with the bucketed all-reduce
+    hooked into the tape; the result must equal the mean of the per-rank gradients computed without any reducer — in the learning
+    step (all buckets reduced at the end) and in the overlapped step (buckets launched from inside backward)."""
+    import copy
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import fake_native
+    from oracle.synth import TINY, synth_inputs
+    from osufusion_b200 import _native
+    from osufusion_b200.ddp import GradAllReducer
+    from osufusion_b200.modules import UNet, UNetFunction
+    _native.call = fake_native.call
+
+    torch.manual_seed(0)
+    base = UNet(6, 96, 5, **TINY)
+    torch.nn.init.normal_(base.final_conv.weight, std=0.02)
+
+    def grads_of(net, seed):
+        x, a, c, t, noise, keep = synth_inputs(2, 48, seed)
+        net.zero_grad(set_to_none=True)
+        y = UNetFunction.apply(net, x, a, t, c, keep, *list(net.parameters()))
+        torch.nn.functional.mse_loss(y, noise).backward()
+        return [p.grad.detach().clone() for p in net.parameters()]
+
+    per_rank = [grads_of(copy.deepcopy(base), 100 + r) for r in range(world)]
+    expect = [sum(gs) / world for gs in zip(*per_rank)]
+    net = copy.deepcopy(base)
+    red = GradAllReducer(net, bucket_bytes=1 << 18)
+    assert len(red.buckets) > 8
+    for step in range(2):
+        got = grads_of(net, 100 + rank)
+        worst = max(((g - e).abs().max() / e.abs().max().clamp_min(1e-12)).item() for g, e in zip(got, expect))
+        assert worst < 1e-5, (rank, step, worst)
+        if step == 0:
+            assert red.ready_at is not None
+        else:
+            assert len(red._launched) == len(red.buckets)
+    out.put((rank, "ok", len(red.buckets)))
+    dist.destroy_process_group()
+
+
+def test_real_backward_tape_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_real_tape, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
