@@ -516,10 +516,25 @@ class _Backbone(nn.Module):
                 m.gradient_checkpointing = value
 
     def forward_with_cond_scale(self, *args, cond_scale: float = 1.0, **kwargs) -> torch.Tensor:
+        """dit.py:258-265 / mmdit.py:335-342.  At inference the conditional and the null pass run as ONE forward over the batch
+        [cond ; null] (keep mask 1..1 0..0): every op of the backbones is per-sample, so the result equals two separate passes."""
+        if cond_scale != 1.0 and not kwargs and len(args) == 4 and not torch.is_grad_enabled() and 2 * args[0].shape[0] <= 16:
+            x, a, t, c = args
+            if not x.is_cuda:
+                raise RuntimeError(f"osufusion_b200.{type(self).__name__} runs only on CUDA (sm_100a); there is no CPU path")
+            return self._cfg_batched(x, a, t, c, cond_scale)
         cond = self(*args, **kwargs)
         if cond_scale == 1.0:
             return cond
         null = self(*args, **kwargs, cond_drop_prob=1.0)
+        return null + (cond - null) * cond_scale
+
+    def _cfg_batched(self, x, a, t, c, cond_scale: float) -> torch.Tensor:
+        B = x.shape[0]
+        keep = torch.cat([torch.ones(B, dtype=torch.bool, device=x.device), torch.zeros(B, dtype=torch.bool, device=x.device)])
+        out16, _ = self.run(None, torch.cat([x, x]), torch.cat([a, a]), torch.cat([t, t]), torch.cat([c, c]), keep)
+        y = self.unpack(out16, x.shape[-1])
+        cond, null = y[:B], y[B:]
         return null + (cond - null) * cond_scale
 
     def forward(self, x, a, t, c, cond_drop_prob: float = 0.0, cond_mask: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -86,3 +86,20 @@ def test_reference_api_surface(kind):
         all(b.modulation_x[1].weight.abs().max() == 0 and b.modulation_a[1].weight.abs().max() == 0 for b in net.blocks)
     with pytest.raises(ValueError):
         (DiT if kind == "dit" else MMDiT)(6, 96, 5, dim_h=128, depth=1, attn_heads=3, attn_dim_head=32)
+
+
+@pytest.mark.parametrize("kind", ["dit", "mmdit"])
+def test_cfg_batched_pass_equals_two_passes(fake_abi, kind):
+    """forward_with_cond_scale at inference = one forward over [cond ; null]; must equal the reference's two separate passes."""
+    from oracle.synth import synth_inputs
+    ora, new = _pair(kind)
+    x, a, c, t, _, _ = synth_inputs(2, 44, 3)
+    with torch.no_grad():
+        ones, zeros = torch.ones(2, dtype=torch.bool), torch.zeros(2, dtype=torch.bool)
+        cond = new.unpack(new.run(None, x, a, t, c, ones)[0], 44)
+        null = new.unpack(new.run(None, x, a, t, c, zeros)[0], 44)
+        two = null + (cond - null) * 2.0
+        one = new._cfg_batched(x, a, t, c, 2.0)
+        assert nrel(one, two) <= 1e-5
+        ref = ora.forward_with_cond_scale(x, a, t, c, cond_scale=2.0)
+        assert nrel(one, ref) <= 3e-2
