@@ -40,6 +40,10 @@ BATCHED = os.environ.get("OF_BACKBONE_BATCHED", "1") != "0"
 # one of_cast_f32_bf16 launch per weight.  Host logic covered on CPU (tests/test_backbones_host_cpu.py); NOT yet run on a B200 for the
 # backbones (round-1 GPU budget exhausted), hence off by default.
 GROUPED_PACK = os.environ.get("OF_BACKBONE_GROUPED_PACK", "0") != "0"
+# every adaLN head (`modulation[1]` of all blocks + the final layer; their common input is SiLU(c)) by ONE grouped launch forward and ONE
+# backward (of_film_fwd / of_film_bwd, the U-Net's FiLM-head kernels) instead of one small-M linear per head.  Same status as
+# GROUPED_PACK: host logic covered on CPU, not yet run on a B200 for the backbones.
+GROUPED_MOD = os.environ.get("OF_BACKBONE_GROUPED_MOD", "0") != "0"
 # of_headnorm_fwd/bwd kernel variant (see include/osufusion_b200.h): 1 = thread per head vector, 2 = thread per 16-byte vector, 0 = auto
 HEADNORM_VARIANT = int(os.environ.get("OF_HEADNORM_VARIANT", "0"))
 
@@ -322,6 +326,26 @@ def _mod_views(mod: torch.Tensor, Cc: int, n: int):
     return [mod[:, i * Cc:(i + 1) * Cc] for i in range(n)]
 
 
+def modulation_fwd(ctx: Ctx, lin: nn.Linear, cact: torch.Tensor) -> torch.Tensor:
+    """adaLN head `Linear(SiLU(c))` -> (B, n) fp32 with bf16-rounded values (precomputed for all heads when GROUPED_MOD)."""
+    if ctx.film is not None:
+        return ctx.film[id(lin)]
+    return E.linear_small_fwd(cact, lin.weight, lin.bias)[0]
+
+
+def modulation_grad_buffer(ctx: Ctx, lin: nn.Linear, B: int) -> torch.Tensor:
+    """Zero-initialised (B, n) accumulator for d modulation (a slice of the grouped gradient buffer when GROUPED_MOD)."""
+    if ctx.film_dss is not None:
+        return ctx.film_dss[id(lin)]
+    return E.zeros((B, lin.weight.shape[0]), F32, ctx.device)
+
+
+def modulation_bwd(ctx: Ctx, lin: nn.Linear, dmod: torch.Tensor, cact: torch.Tensor) -> None:
+    if ctx.film_dss is not None:
+        return      # consumed by the grouped of_film_bwd launch in the conditioning backward
+    E.linear_small_bwd_param(ctx.store, dmod, None, 0, cact, lin.weight, lin.bias, ctx.d_emb_act)
+
+
 # ------------------------------------------------------------------------------------------------ blocks
 def dit_block(ctx: Ctx, m: DiTBlock, x: Act, cact: torch.Tensor) -> Act:
     """DiTBlock.forward_body (dit.py:147-153)."""
@@ -331,7 +355,7 @@ def dit_block(ctx: Ctx, m: DiTBlock, x: Act, cact: torch.Tensor) -> Act:
     H, D = at.heads, at.dim_head
     HD = H * D
     lin = m.modulation[1]
-    mod, _ = E.linear_small_fwd(cact, lin.weight, lin.bias)
+    mod = modulation_fwd(ctx, lin, cact)
     sh1, sc1, g1, sh2, sc2, g2 = _mod_views(mod, Cc, 6)
     s1p1, s1p2 = one_plus(sc1), one_plus(sc2)
     x0 = x.f32
@@ -355,7 +379,7 @@ def dit_block(ctx: Ctx, m: DiTBlock, x: Act, cact: torch.Tensor) -> Act:
         def backward():
             d2 = out.grad
             out.grad = None
-            dmod = E.zeros((B, 6 * Cc), F32, dev)
+            dmod = modulation_grad_buffer(ctx, lin, B)
             dsh1, dsc1, dg1, dsh2, dsc2, dg2 = _mod_views(dmod, Cc, 6)
             # feed-forward branch
             df16 = gate_backward(d2, g2, f16, dg2)
@@ -373,7 +397,7 @@ def dit_block(ctx: Ctx, m: DiTBlock, x: Act, cact: torch.Tensor) -> Act:
             E._wgrad_linear(st, at.to_qkv.weight, dqkv, h1)
             d0 = ada_ln_bwd(hact.grad, x0, s1p1, mr1, dsh1, dsc1, dres=d1)
             x.add_grad(d0)
-            E.linear_small_bwd_param(st, dmod, None, 0, cact, lin.weight, lin.bias, ctx.d_emb_act)
+            modulation_bwd(ctx, lin, dmod, cact)
         ctx.tape.push(backward)
     return out
 
@@ -393,7 +417,7 @@ def mmdit_block(ctx: Ctx, m: MMDiTBlock, x: Act, a: Act, cact: torch.Tensor, las
     S = {}
     for s, src, r0, r1 in (("a", a, 0, La), ("x", x, La, Lt)):
         lin = getattr(m, f"modulation_{s}")[1]
-        mod, _ = E.linear_small_fwd(cact, lin.weight, lin.bias)
+        mod = modulation_fwd(ctx, lin, cact)
         sh1, sc1, g1, sh2, sc2, g2 = _mod_views(mod, Cc, 6)
         d = dict(lin=lin, mod=mod, sh1=sh1, g1=g1, sh2=sh2, g2=g2, s1p1=one_plus(sc1), s1p2=one_plus(sc2), r0=r0, r1=r1, src=src,
                  x0=src.f32, qn=getattr(at, f"q_{s}_norm"), kn=getattr(at, f"k_{s}_norm"),
@@ -431,7 +455,7 @@ def mmdit_block(ctx: Ctx, m: MMDiTBlock, x: Act, a: Act, cact: torch.Tensor, las
                 d = S[s]
                 d2 = outs[s].grad
                 outs[s].grad = None
-                d["dmod"] = E.zeros((B, 6 * Cc), F32, dev)
+                d["dmod"] = modulation_grad_buffer(ctx, d["lin"], B)
                 dsh1, dsc1, dg1, dsh2, dsc2, dg2 = _mod_views(d["dmod"], Cc, 6)
                 d["d1"] = None
                 if d2 is None:
@@ -462,7 +486,7 @@ def mmdit_block(ctx: Ctx, m: MMDiTBlock, x: Act, a: Act, cact: torch.Tensor, las
                     c0 += n_
                 d0 = ada_ln_bwd(hact.grad, d["x0"], d["s1p1"], d["mr1"], dsh1, dsc1, dres=d["d1"])
                 d["src"].add_grad(d0)
-                E.linear_small_bwd_param(st, d["dmod"], None, 0, cact, d["lin"].weight, d["lin"].bias, ctx.d_emb_act)
+                modulation_bwd(ctx, d["lin"], d["dmod"], cact)
         ctx.tape.push(backward)
     return outs["x"], outs["a"]
 
@@ -472,7 +496,7 @@ def final_layer(ctx: Ctx, m: FinalLayer, x: Act, cact: torch.Tensor) -> Act:
     st, dev = ctx.store, ctx.device
     B, L, Cc = x.f32.shape
     lin = m.modulation[1]
-    mod, _ = E.linear_small_fwd(cact, lin.weight, lin.bias)
+    mod = modulation_fwd(ctx, lin, cact)
     sh, sc = _mod_views(mod, Cc, 2)
     s1p = one_plus(sc)
     h16, mr = ada_ln_fwd(x.f32, sh, s1p, m.norm.eps)
@@ -486,14 +510,14 @@ def final_layer(ctx: Ctx, m: FinalLayer, x: Act, cact: torch.Tensor) -> Act:
         def backward():
             dy16 = out.grad          # bf16 (B, L, dim_out), produced by the output conv's dgrad
             out.grad = None
-            dmod = E.zeros((B, 2 * Cc), F32, dev)
+            dmod = modulation_grad_buffer(ctx, lin, B)
             dsh, dsc = _mod_views(dmod, Cc, 2)
             E._wgrad_linear(st, m.linear.weight, dy16, h16)
             E._bias_grad(st, m.linear.bias, dy16)
             hact = Act(None, None)
             E._dgrad_into(hact, dy16, w, N_out=Cc, K=No)
             x.add_grad(ada_ln_bwd(hact.grad, x.f32, s1p, mr, dsh, dsc))
-            E.linear_small_bwd_param(st, dmod, None, 0, cact, lin.weight, lin.bias, ctx.d_emb_act)
+            modulation_bwd(ctx, lin, dmod, cact)
         ctx.tape.push(backward)
     return out
 
@@ -590,10 +614,28 @@ class _Backbone(nn.Module):
         cfull = (csel + tv.val + av.val).contiguous()
         cact = E.empty((B, dim), F32, dev)
         N.call("of_silu_small", cfull.data_ptr(), None, cact.data_ptr(), cfull.numel())
+        plan = self._modulation_plan(st, B, ctx.tape is not None) if GROUPED_MOD else None
+        emb_r = None
+        if plan is not None:
+            emb_r = cact.to(BF16).to(F32)          # the heads' Linear sees its input in bf16 under autocast
+            mod_all = E.empty((B * plan["rows"],), F32, dev)
+            N.call("of_film_fwd", plan["groups"].data_ptr(), plan["num_groups"], plan["rows"], emb_r.data_ptr(), B, dim, mod_all.data_ptr())
+            ctx.film = {k: mod_all[o:o + B * n].view(B, n) for k, (o, n) in plan["slices"].items()}
         if ctx.tape is not None:
             ctx.d_emb_act = E.zeros((B, dim), F32, dev)
+            dmod_all = None
+            if plan is not None:
+                dmod_all = torch.zeros((B * plan["rows"],), dtype=F32, device=dev)
+                ctx.film_dss = {k: dmod_all[o:o + B * n].view(B, n) for k, (o, n) in plan["slices"].items()}
 
             def backward():
+                if plan is not None:
+                    N.call("of_film_bwd", plan["groups"].data_ptr(), plan["chunks"].data_ptr(), plan["num_chunks"], dmod_all.data_ptr(),
+                           emb_r.data_ptr(), B, dim, ctx.d_emb_act.data_ptr())
+                    for lin in plan["heads"]:
+                        for p_ in lin.parameters():
+                            if p_.requires_grad:
+                                st.touch(p_)
                 dc = E.empty((B, dim), F32, dev)
                 N.call("of_silu_small", cfull.data_ptr(), ctx.d_emb_act.data_ptr(), dc.data_ptr(), cfull.numel())
                 if self.null_cond.requires_grad:
@@ -603,6 +645,36 @@ class _Backbone(nn.Module):
                 av.grad = dc
             ctx.tape.push(backward)
         return cact
+
+    def _modulation_plan(self, st: ParamStore, B: int, with_grads: bool):
+        """Device-resident descriptor tables (of_film_group) of every adaLN head for batch size B; rebuilt when a pointer moves."""
+        heads = [m.modulation[1] for m in self.modules() if isinstance(getattr(m, "modulation", None), nn.Sequential)]
+        for blk in self.blocks:
+            heads += [getattr(blk, f"modulation_{s_}")[1] for s_ in ("a", "x") if hasattr(blk, f"modulation_{s_}")]
+        ptrs = tuple(h.weight.data_ptr() for h in heads) + (st.arena.data_ptr() if (with_grads and st.arena is not None) else 0, B)
+        cache = self.__dict__.setdefault("_mod_plans", {})
+        plan = cache.get(with_grads)
+        if plan is not None and plan["ptrs"] == ptrs:
+            return plan
+        dev = heads[0].weight.device
+        groups, chunks, slices, row = [], [], {}, 0
+        ch = N.lib().of_film_chunk_rows()
+        for gi, lin in enumerate(heads):
+            Nn = lin.weight.shape[0]
+            assert Nn % 4 == 0 and lin.weight.shape[1] == heads[0].weight.shape[1]
+            dW = st.arena_views[id(lin.weight)].data_ptr() if (with_grads and lin.weight.requires_grad) else 0
+            db = st.arena_views[id(lin.bias)].data_ptr() if (with_grads and lin.bias is not None and lin.bias.requires_grad) else 0
+            groups.append(N.FilmGroup(lin.weight.data_ptr(), lin.bias.data_ptr() if lin.bias is not None else 0, dW, db, B * row, Nn, row))
+            for n0 in range(0, Nn, ch):
+                chunks += [gi, n0]
+            slices[id(lin)] = (B * row, Nn)
+            row += Nn
+        arr = (N.FilmGroup * len(groups))(*groups)
+        plan = {"ptrs": ptrs, "heads": heads, "rows": row, "num_groups": len(groups), "slices": slices,
+                "groups": torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev),
+                "chunks": torch.tensor(chunks, dtype=torch.int32).to(dev), "num_chunks": len(chunks) // 2}
+        cache[with_grads] = plan
+        return plan
 
     def _output_conv(self, ctx: Ctx, conv: nn.Conv1d, y16: torch.Tensor) -> torch.Tensor:
         """1x1 conv dim_h -> dim_in_x on a (B, L, dim_h) bf16 view, padded to 8 output channels."""

@@ -41,6 +41,7 @@ def test_engine_tape_matches_oracle_through_emulated_abi(fake_abi, monkeypatch, 
     from osufusion_b200.modules import UNetFunction
     monkeypatch.setattr(backbones, "BATCHED", batched)
     monkeypatch.setattr(backbones, "GROUPED_PACK", batched)
+    monkeypatch.setattr(backbones, "GROUPED_MOD", batched)
     ora, new = _pair(kind)
     x, a, c, t, noise, mask = synth_inputs(2, n, 1234)
     y_o = ora(x, a, t, c, cond_mask=mask)
@@ -60,6 +61,7 @@ def test_engine_tape_matches_oracle_through_emulated_abi(fake_abi, monkeypatch, 
     assert {"of_gemm", "of_attn_fwd", "of_attn_bwd", "of_headnorm_fwd", "of_headnorm_bwd", "of_gate_residual_fwd", "of_row_mean_std"} <= used
     if batched:
         assert "of_pack_weights" in used and "of_cast_f32_bf16" not in used  # every projection weight goes through the grouped pack
+        assert {"of_film_fwd", "of_film_bwd"} <= used                          # every adaLN head in one launch each way
         assert {"of_adaln_fwd", "of_adaln_bwd", "of_gate_bwd"} <= used and not ({"of_layernorm_fwd", "of_coldot_bf16"} & used)
     else:
         assert {"of_layernorm_fwd", "of_layernorm_bwd", "of_gate_mul_bwd", "of_coldot_bf16"} <= used
