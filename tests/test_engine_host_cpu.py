@@ -268,3 +268,34 @@ def test_fused_adamw_host_logic_matches_torch(fake_abi, max_norm):
     with torch.no_grad():
         out16, _ = net.run(None, x, a, t, c, keep)
         assert nrel(net.unpack(out16, 48), y0) > 1e-4
+
+
+@pytest.mark.parametrize("use_dora", [True, False])
+def test_adapted_forward_equals_merged_model(fake_abi, use_dora):
+    """The engine's on-the-fly effective weight s * (W + scaling * B A) must give the same output as the plain model after
+    `merge_and_unload` (peft's merge, lora_layers.py:197-256): the adapter directory and the merged checkpoint describe one model."""
+    from oracle.synth import TINY, synth_inputs
+    from osufusion_b200 import lora
+    from osufusion_b200.modules import UNet
+    torch.manual_seed(0)
+    net = UNet(6, 96, 5, **TINY)
+    torch.nn.init.normal_(net.final_conv.weight, std=0.02)
+    names = lora.inject_adapters(net, r=8, lora_alpha=16, use_dora=use_dora)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for name in names:
+            ad = net.get_submodule(name)
+            ad.lora_B["default"].weight.copy_(0.05 * torch.randn(ad.lora_B["default"].weight.shape, generator=g))
+            if use_dora:
+                ad.magnitude().mul_(1 + 0.1 * torch.randn(ad.magnitude().shape, generator=g))
+    x, a, c, t, _, keep = synth_inputs(2, 40, 9)
+    with torch.no_grad():
+        y_adapted = net.unpack(net.run(None, x, a, t, c, keep)[0], 40)
+        lora.merge_and_unload(net)
+        assert not any(hasattr(m, "base_layer") for m in net.modules())
+        y_merged = net.unpack(net.run(None, x, a, t, c, keep)[0], 40)
+    assert y_adapted.abs().max() > 1e-3
+    # both are bf16 evaluations of the same effective weights; under DoRA the adapted to_q keeps q in fp32 through RoPE (the reference's
+    # type promotion, lora_layers / peft) while the merged model rotates in bf16, hence bf16-level rather than bit-level agreement
+    assert nrel(y_adapted, y_merged) <= 5e-2
+    assert (y_adapted - y_merged).abs().mean() <= 3e-2 * y_merged.abs().mean()
