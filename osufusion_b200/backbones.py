@@ -37,13 +37,12 @@ from .modules import (A_PAD_VALUE, X_PAD_VALUE, CrossEmbedLayer, SinusoidalPosit
 # path's LayerNorm kernels + of_gate_mul_bwd + of_coldot_bf16 (kept as the cross-check: OF_BACKBONE_BATCHED=0)
 BATCHED = os.environ.get("OF_BACKBONE_BATCHED", "1") != "0"
 # bf16 operand copies of all projection weights by ONE grouped of_pack_weights launch (the U-Net's mechanism, engine.ParamStore) instead of
-# one of_cast_f32_bf16 launch per weight.  Host logic covered on CPU (tests/test_backbones_host_cpu.py); NOT yet run on a B200 for the
-# backbones (round-1 GPU budget exhausted), hence off by default.
-GROUPED_PACK = os.environ.get("OF_BACKBONE_GROUPED_PACK", "0") != "0"
-# every adaLN head (`modulation[1]` of all blocks + the final layer; their common input is SiLU(c)) by ONE grouped launch forward and ONE
-# backward (of_film_fwd / of_film_bwd, the U-Net's FiLM-head kernels) instead of one small-M linear per head.  Same status as
-# GROUPED_PACK: host logic covered on CPU, not yet run on a B200 for the backbones.
-GROUPED_MOD = os.environ.get("OF_BACKBONE_GROUPED_MOD", "0") != "0"
+# one of_cast_f32_bf16 launch per weight; every adaLN head (`modulation[1]` of all blocks + the final layer; their common input is SiLU(c))
+# by ONE grouped launch forward and ONE backward (of_film_fwd / of_film_bwd, the U-Net's FiLM-head kernels) instead of one small-M linear
+# per head.  Both parity-checked on the B200 (tests/test_zz_backbones_gpu.py with the switches on; profiles/r01_backbones_gpu_tests.log);
+# their effect on the step time has not been measured yet (round-1 GPU budget).  =0 restores the per-tensor launches.
+GROUPED_PACK = os.environ.get("OF_BACKBONE_GROUPED_PACK", "1") != "0"
+GROUPED_MOD = os.environ.get("OF_BACKBONE_GROUPED_MOD", "1") != "0"
 # of_headnorm_fwd/bwd kernel variant (see include/osufusion_b200.h): 1 = thread per head vector, 2 = thread per 16-byte vector, 0 = auto
 HEADNORM_VARIANT = int(os.environ.get("OF_HEADNORM_VARIANT", "0"))
 

@@ -65,7 +65,7 @@ def test_bucketed_allreduce_world2_gloo():
     assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == "ok" for r in res)
 
 
-def _worker_real_tape(rank, world, port, out):
+def _worker_real_tape(rank, world, port, out, kind="unet"):
     """Every rank runs the real engine forward/backward (through the emulated C-ABI) on its own batch with the bucketed all-reduce
     hooked into the tape; the result must equal the mean of the per-rank gradients computed without any reducer — in the learning
     step (all buckets reduced at the end) and in the overlapped step (buckets launched from inside backward)."""
@@ -82,23 +82,31 @@ def _worker_real_tape(rank, world, port, out):
     _native.call = fake_native.call
 
     torch.manual_seed(0)
-    base = UNet(6, 96, 5, **TINY)
-    torch.nn.init.normal_(base.final_conv.weight, std=0.02)
+    if kind == "unet":
+        base = UNet(6, 96, 5, **TINY)
+        torch.nn.init.normal_(base.final_conv.weight, std=0.02)
+    else:                                   # the DiT / MMDiT backbones share the arena / hook protocol (osufusion_b200/backbones.py)
+        from oracle.make_golden_backbones import MMDIT_TINY
+        from oracle.synth import synth_state_dict
+        from osufusion_b200.backbones import MMDiT
+        base = MMDiT(6, 96, 5, **MMDIT_TINY)
+        base.load_state_dict(synth_state_dict(base))
 
     def grads_of(net, seed):
         x, a, c, t, noise, keep = synth_inputs(2, 48, seed)
         net.zero_grad(set_to_none=True)
         y = UNetFunction.apply(net, x, a, t, c, keep, *list(net.parameters()))
         torch.nn.functional.mse_loss(y, noise).backward()
-        return [p.grad.detach().clone() for p in net.parameters()]
+        return [p.grad.detach().clone() for p in net.parameters() if p.grad is not None]
 
     per_rank = [grads_of(copy.deepcopy(base), 100 + r) for r in range(world)]
     expect = [sum(gs) / world for gs in zip(*per_rank)]
     net = copy.deepcopy(base)
     red = GradAllReducer(net, bucket_bytes=1 << 18)
-    assert len(red.buckets) > 8
+    assert len(red.buckets) > 4
     for step in range(2):
         got = grads_of(net, 100 + rank)
+        assert len(got) == len(expect)
         worst = max(((g - e).abs().max() / e.abs().max().clamp_min(1e-12)).item() for g, e in zip(got, expect))
         assert worst < 1e-5, (rank, step, worst)
         if step == 0:
@@ -109,11 +117,15 @@ def _worker_real_tape(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_real_backward_tape_allreduce_world2_gloo():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("kind", ["unet", "mmdit"])
+def test_real_backward_tape_allreduce_world2_gloo(kind):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_real_tape, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker_real_tape, args=(r, 2, port, out, kind)) for r in range(2)]
     for p in procs:
         p.start()
     res = [out.get(timeout=300) for _ in procs]
