@@ -167,6 +167,8 @@ def _check(kind, cfg, B, n, batched=None, monkeypatch=None):
         from osufusion_b200 import backbones
         monkeypatch.setattr(backbones, "BATCHED", batched)
         monkeypatch.setattr(backbones, "HEADNORM_VARIANT", 2 if batched else 1)     # both kernel variants go through the whole model
+        monkeypatch.setattr(backbones, "GROUPED_PACK", batched)                    # all-off = the first (per-tensor / per-sample) composition
+        monkeypatch.setattr(backbones, "GROUPED_MOD", batched)
     ora, new = _build(kind, cfg)
     x, a, c, t, noise, mask = (v.to(dev) for v in synth_inputs(B, n, 1234))
     inputs = (x, a, c, t, noise)
