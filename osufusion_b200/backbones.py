@@ -530,6 +530,7 @@ class _Backbone(nn.Module):
         self.attn_variant = 0
         self.grad_sync = None
         self.grad_finish = None
+        self._mod_plans = {}     # adaLN-head descriptor tables per (with gradients?) — device tensors, not part of the state_dict
 
     # ---- reference API
     def set_gradient_checkpointing(self, value: bool) -> None:
@@ -651,7 +652,7 @@ class _Backbone(nn.Module):
         for blk in self.blocks:
             heads += [getattr(blk, f"modulation_{s_}")[1] for s_ in ("a", "x") if hasattr(blk, f"modulation_{s_}")]
         ptrs = tuple(h.weight.data_ptr() for h in heads) + (st.arena.data_ptr() if (with_grads and st.arena is not None) else 0, B)
-        cache = self.__dict__.setdefault("_mod_plans", {})
+        cache = self._mod_plans
         plan = cache.get(with_grads)
         if plan is not None and plan["ptrs"] == ptrs:
             return plan

@@ -173,9 +173,14 @@ def _adapter(m):
 
 # ------------------------------------------------------------------------------------------------ parameter staging
 def backward_param_order(unet) -> List[torch.nn.Parameter]:
-    """Parameters in the order their gradients become final during the engine's backward pass.  The FiLM heads
-    (`ResidualBlock.mlp`) are the exception: their gradients are produced by ONE grouped kernel when the conditioning
-    MLPs are reached, so they sit together right after `init_x`."""
+    """Parameters in the order their gradients become final during the engine's backward pass (see backward_param_plan)."""
+    return backward_param_plan(unet)[0]
+
+
+def backward_param_plan(unet):
+    """(order, (film_start, film_end)): parameters in the order their gradients become final during the engine's backward pass.
+    The FiLM heads (`ResidualBlock.mlp`) are the exception: their gradients are produced by ONE grouped kernel when the
+    conditioning MLPs are reached, so they sit together right after `init_x` (positions film_start..film_end of the order)."""
     order: List[torch.nn.Parameter] = []
     seen = set()
     film = []
@@ -219,8 +224,7 @@ def backward_param_order(unet) -> List[torch.nn.Parameter]:
         if id(p) not in seen:
             seen.add(id(p))
             order.append(p)
-    backward_param_order.film_span = (film_start, film_end)
-    return order
+    return order, (film_start, film_end)
 
 
 class ParamStore:
@@ -261,8 +265,7 @@ class ParamStore:
         if custom is not None:       # other backbones (osufusion_b200/backbones.py) supply their own completion order; no FiLM block
             order, fs, fe = custom(), 0, 0
         else:
-            order = backward_param_order(unet)
-            fs, fe = backward_param_order.film_span
+            order, (fs, fe) = backward_param_plan(unet)
         film_ids = {id(p) for p in order[fs:fe]}
         params = [p for p in order if p.requires_grad]
         key = tuple(id(p) for p in params) + (str(params[0].device) if params else "",)
