@@ -739,5 +739,7 @@ def call(name, *args, flops=0.0, family=None, tag=""):
     fn = _TABLE.get(name)
     if fn is None:
         raise NotImplementedError(f"fake_native: {name} is not emulated")
+    from osufusion_b200._native import _SIGS
+    assert len(args) == len(_SIGS[name]) - 1, f"{name}: {len(args)} arguments passed, the binding declares {len(_SIGS[name]) - 1} (+ stream)"
     CALLS.append(name)
     fn(*[0 if a is None else a for a in args])

@@ -299,3 +299,33 @@ def test_adapted_forward_equals_merged_model(fake_abi, use_dora):
     # type promotion, lora_layers / peft) while the merged model rotates in bf16, hence bf16-level rather than bit-level agreement
     assert nrel(y_adapted, y_merged) <= 5e-2
     assert (y_adapted - y_merged).abs().mean() <= 3e-2 * y_merged.abs().mean()
+
+
+@pytest.mark.parametrize("kind", ["diffusion", "rectified_flow"])
+def test_training_rng_draw_order_matches_reference(fake_abi, kind):
+    """Without injected draws the wrappers must consume the generator like the reference (diffusion.py:88-98: randn_like -> randint ->
+    CFG uniform_; rectified_flow.py:89-98: randn_like -> rand -> uniform_): same seed => same noise / timesteps / mask => same loss."""
+    from oracle.models import DiffusionOsuFusion as OD, RectifiedFlowOsuFusion as OR
+    from oracle.synth import TINY, synth_inputs
+    from osufusion_b200.models import DiffusionOsuFusion, RectifiedFlowOsuFusion
+    OC, NC = (OD, DiffusionOsuFusion) if kind == "diffusion" else (OR, RectifiedFlowOsuFusion)
+    torch.manual_seed(0)
+    ora = OC(**TINY)
+    torch.nn.init.normal_(ora.unet.final_conv.weight, std=0.02)
+    new = NC(**TINY)
+    new.load_state_dict(ora.state_dict())
+    x, a, c, _, _, _ = synth_inputs(4, 48, 21)
+    losses = []
+    for seed in (5, 6):
+        torch.manual_seed(seed)
+        with torch.autocast("cpu", dtype=torch.bfloat16), torch.no_grad():
+            l_ref = ora(x, a, c).item()
+        after_ref = torch.rand(1).item()
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            l_new = new(x, a, c).item()
+        after_new = torch.rand(1).item()
+        assert abs(l_new - l_ref) <= 1e-2 * abs(l_ref), (seed, l_new, l_ref)
+        assert after_new == after_ref          # the generator was advanced by exactly the same draws
+        losses.append(l_ref)
+    assert abs(losses[0] - losses[1]) > 1e-3   # the draws do matter: a different seed gives a different loss
