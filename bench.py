@@ -137,7 +137,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     frames = args.ref_frames
-    sec, cores, loss = cpu_reference_step_time(args.size, frames, args.steps, min(args.warmup, 1))
+    sec, cores, loss = cpu_reference_step_time(args.size, frames, args.steps, args.warmup)
     # one bounded step = batch 1 x `frames` frames; expressed in the workload's unit (samples of args.frames frames) by algorithmic FLOPs
     equiv = fwd_tflop(args.size, frames) / fwd_tflop(args.size, args.frames)
     value = equiv / sec
@@ -145,10 +145,12 @@ def run_reference(args) -> None:
               f"{args.frames} frames per GPU), fp32, oracle port of the reference, {sec:.2f} s per step")
     line = {
         "impl": "reference", "metric": "denoiser fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CFG-{args.size} dim_h={SIZES[args.size]} denoiser train micro-step (fwd+bwd), cond_drop_prob=0.5",
-                   "sample": sample},
+        # same workload / config keys as our arm (run_ours); `sample` says which bounded part of it one timed step covers
+        "config": {"workload": f"CFG-{args.size} dim_h={SIZES[args.size]} denoiser train micro-step (fwd+bwd, all grads), cond_drop_prob=0.5",
+                   "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "frames": args.frames,
+                   "parallelism": f"dp{args.gpus}", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
