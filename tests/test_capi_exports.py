@@ -71,3 +71,37 @@ def test_host_side_helpers_run_without_a_gpu():
     assert lib.of_pack_seg_ctas(512, 512, 3, 512) == 512 and lib.of_pack_seg_ctas(1024, 512, 1, 512) == 128
     assert lib.of_pack_seg_ctas(8, 8, 15, 8) == -1            # wide kernels use the per-tensor path
     assert lib.of_opt_tensor_ctas(4097) == 2
+
+
+def test_argument_validation_returns_error_codes_without_a_gpu():
+    """Every entry point validates its arguments before touching CUDA: a bad call returns OF_ERR_INVALID (-1) and of_last_error()
+    names the entry point — the error behaviour of the C-ABI (include/osufusion_b200.h), checkable on the GPU-less box."""
+    import ctypes as C
+
+    from osufusion_b200 import _native as N
+    lib = N.lib()
+
+    def last():
+        return lib.of_last_error().decode()
+
+    g = N.GemmArgs()
+    assert lib.of_gemm(None, None) == -1 and "of_gemm" in last()
+    g.mode, g.batch, g.rows, g.N, g.K, g.taps = 0, 1, 16, 12, 8, 1            # N not a multiple of 8
+    assert lib.of_gemm(C.byref(g), None) == -1 and "multiple of 8" in last()
+    a = N.AttnArgs()
+    a.B, a.H, a.KVH, a.L, a.D = 1, 4, 3, 16, 64                              # null pointers
+    assert lib.of_attn_fwd(C.byref(a), None) == -1 and "of_attn_fwd" in last()
+    buf = C.create_string_buffer(4096)
+    p = C.addressof(buf)
+    a.q = a.k = a.v = a.out = p
+    a.D = 72                                                                 # head dim out of range
+    assert lib.of_attn_fwd(C.byref(a), None) == -1 and "head dim" in last()
+    a.D = 64                                                                 # 4 query heads on 3 kv heads
+    assert lib.of_attn_fwd(C.byref(a), None) == -1 and "head counts" in last()
+    assert lib.of_layernorm_fwd(p, 100, 4, 100, p, p, 1e-5, p, None, 100, None, None) == -1 and "of_layernorm_fwd" in last()
+    assert lib.of_headnorm_fwd(p, 64, 64, 1, 1, 1, 1, 1, 72, p, p, 8.0, p, 64, 64, 0, None) == -1 and "head dim" in last()
+    assert lib.of_headnorm_fwd(p, 64, 64, 1, 1, 1, 1, 1, 24, p, p, 4.9, p, 64, 64, 2, None) == -1 and "variant" in last()
+    assert lib.of_adaln_fwd(p, 12, 12, 1, 1, 12, p, 12, p, 12, 1e-6, p, 12, 12, p, None) == -1 and "of_adaln_fwd" in last()
+    assert lib.of_gate_bwd(p, 8, 8, p, 8, None, 8, 8, 1, 1, 1, 8, p, 8, 8, p, 8, None) == -1 and "null" in last()
+    assert lib.of_linear_small_fwd(p, 8, 17, 8, 8, p, 8, None, 0, 1, p, 8, None, None) == -1 and "out of range" in last()
+    assert lib.of_row_mean_std(p, 1, 1, 1, p, None) == -1 and "of_row_mean_std" in last()
