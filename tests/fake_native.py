@@ -1,9 +1,12 @@
-"""TEST INFRASTRUCTURE: a CPU stand-in for the subset of the C-ABI (include/osufusion_b200.h) that osufusion_b200/backbones.py
-drives, written from the header's contracts in plain torch over raw host pointers.
+"""TEST INFRASTRUCTURE: a CPU stand-in for the C-ABI (include/osufusion_b200.h), written from the header's contracts in plain torch
+over raw host pointers: of_gemm (forward / dgrad / wgrad incl. the epilogue options), attention, the ResidualBlock / LayerNorm / RoPE /
+FiLM / loss / sampler kernels of the U-Net path, LoRA / DoRA, the fused optimizer, grouped packing, and the DiT / MMDiT kernels.
 
-Purpose: exercise the HOST side of the engine (argument order, strides and views, tape order, gradient routing, arena plumbing)
-on the GPU-less build box.  It is installed by monkeypatching `osufusion_b200._native.call` inside a test; the product never
-imports it, and it says nothing about the CUDA kernels themselves (those are checked on the B200 by the `-m gpu` tests).
+Purpose: exercise the HOST side of the engine (argument order and counts, strides and views, tape order, gradient routing, arena
+plumbing, DDP bucket scheduling) on the GPU-less build box.  It is installed by monkeypatching `osufusion_b200._native.call` inside a
+test; the product never imports it, and it says nothing about the CUDA kernels themselves (those are checked on the B200 by the
+`-m gpu` tests — the new backbone kernels also against these very restatements).  Rounding points follow the kernels where that is
+cheap (bf16 operands / outputs); results agree with the kernels to bf16 tolerance, not bit for bit.
 """
 from __future__ import annotations
 
