@@ -105,3 +105,35 @@ def test_cfg_batched_pass_equals_two_passes(fake_abi, kind):
         assert nrel(one, two) <= 1e-5
         ref = ora.forward_with_cond_scale(x, a, t, c, cond_scale=2.0)
         assert nrel(one, ref) <= 3e-2
+
+
+def test_fused_adamw_drives_a_backbone(fake_abi):
+    """FusedAdamW / the gradient arena are backbone-agnostic: two optimizer steps on the MMDiT equal torch.optim.AdamW on the same gradients,
+    and the engine sees the updated weights (operand caches are invalidated through `param_epoch`)."""
+    import copy
+
+    from oracle.synth import synth_inputs
+    from osufusion_b200.modules import UNetFunction
+    from osufusion_b200.optim import FusedAdamW
+    _, net = _pair("mmdit")
+    ref = copy.deepcopy(net)
+    opt = FusedAdamW(net, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=1e-2)
+    x, a, c, t, noise, mask = synth_inputs(2, 48, 5)
+    outs = []
+    for _ in range(2):
+        net.zero_grad(set_to_none=True)
+        y = UNetFunction.apply(net, x, a, t, c, mask, *list(net.parameters()))
+        outs.append(y.detach().clone())
+        torch.nn.functional.mse_loss(y, noise).backward()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            q.grad = None if p.grad is None else p.grad.detach().clone()
+        torch.nn.utils.clip_grad_norm_([q for q in ref.parameters() if q.grad is not None], 1.0)
+        for q in ref.parameters():          # FusedAdamW treats a missing gradient as zero (decay + moment update still apply)
+            if q.grad is None:
+                q.grad = torch.zeros_like(q)
+        ropt.step()
+        opt.step()
+        worst = max(((p - q).abs().max() / q.abs().max().clamp_min(1e-12)).item() for p, q in zip(net.parameters(), ref.parameters()))
+        assert worst < 1e-5, worst
+    assert nrel(outs[1], outs[0]) > 1e-4        # the second forward ran with the updated weights
