@@ -2,7 +2,9 @@
 """Minimal training loop of the DiT / MMDiT backbones (osu_fusion/modules/dit.py, mmdit.py) on synthetic data with this repo's
 drop-in pieces: backbone, noise-prediction loss on DDIM-noised inputs, one CUDA graph per micro-step, (optional) data-parallel
 gradient all-reduce overlapped with backward, fused clip + AdamW.  The reference does not wire these backbones into its trainers;
-this mirrors what trainer.py does with the U-Net (trainer.py:290-309).
+this mirrors what trainer.py does with the U-Net (trainer.py:290-309).  Status: the captured micro-step is what tools/probe_backbones.py
+times on the B200 and the optimizer pairing is covered by tests/test_backbones_host_cpu.py, but this script as a whole has not been run
+on a B200 yet (round-1 GPU budget).
 
     python examples/train_backbone_synthetic.py --backbone mmdit --steps 20
     torchrun --nproc-per-node 8 examples/train_backbone_synthetic.py --backbone dit --steps 20
