@@ -1,6 +1,11 @@
 """ORACLE (test infrastructure): restatement of the reference's LoRA/DoRA forward for Conv1d (osu_fusion/modules/lora_layers.py:
-59-92,292-328) and of peft 0.12.0's DoRA nn.Linear path (source absent from the image: PARITY UNPINNED; formula from SURVEY.md
-Appendix B).  Plain torch, autograd-differentiable, used only by tests."""
+59-92,292-328) and of peft 0.12.0's DoRA nn.Linear path.  Plain torch, autograd-differentiable, used only by tests.
+
+Pinning: `dora_conv1d` is PINNED against the reference's own `LoraConv1d` / `DoraConv1dLayer` code, executed through the peft
+bookkeeping stub of tests/peft_stub.py (tests/test_lora_reference_pin.py: live reference in the build container, golden vectors
+tests/golden/lora_conv1d_ref.pt everywhere: outputs <= 1e-6, gradients <= 1e-5).  `dora_linear` restates peft's own
+`DoraLinearLayer.forward`, whose source is absent from the image: PARITY UNPINNED (formula from SURVEY.md Appendix B; it is the
+same expression as the pinned Conv1d variant with `linear` in place of `conv1d`)."""
 from __future__ import annotations
 
 import torch
