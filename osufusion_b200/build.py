@@ -42,7 +42,19 @@ def _digest() -> str:
 
 
 def build_native(force: bool = False, verbose: bool = False) -> Path:
+    """Build (if stale) under an exclusive file lock: under torchrun every rank may get here at once; the first one builds into a
+    temporary file and renames it into place atomically, the others wait for the lock and find the library up to date."""
+    import fcntl
     LIB_DIR.mkdir(exist_ok=True)
+    with open(LIB_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     stamp = LIB_DIR / "build.stamp"
     digest = _digest()
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == digest:
@@ -67,11 +79,13 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [NVCC, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "static",
+    tmp = LIB_PATH.with_suffix(f".tmp{os.getpid()}.so")
+    cmd = [NVCC, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static",
            "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     stamp.write_text(digest)
     return LIB_PATH
 

@@ -59,7 +59,7 @@ def load_checkpoint(model, optimizer, scheduler, checkpoint_path: Path, reset_st
     try:
         model.load_state_dict(checkpoint["model_state_dict"])
         optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
-    except RuntimeError:
+    except (RuntimeError, ValueError):     # RuntimeError: model keys changed (trainer.py:191); ValueError: optimizer group sizes differ
         model.load_state_dict(checkpoint["model_state_dict"], strict=False)
     if not reset_steps:
         scheduler.load_state_dict(checkpoint["scheduler_state_dict"])

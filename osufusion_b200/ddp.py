@@ -7,9 +7,12 @@ trainer.py:211-220,264-269,301).  Differences that matter on an NVSwitch box:
   * buckets are large (default 256 MB: NVLink-5/NVSwitch collectives are latency- not link-bound) and are launched on a
     side stream from inside the backward tape as soon as the last layer writing into them has run;
   * the whole step (backward + collectives) is CUDA-graph capturable;
-  * `reserve_sms` SMs are left to the NCCL kernels: the engine's persistent GEMM sizes its grid for the remaining SMs
-    (of_set_sm_limit), otherwise every GEMM launched while a bucket is in flight runs as two waves (measured at 2 GPUs:
-    67.9 -> 65.7 ms per step with 16 reserved SMs and NCCL_MAX_CTAS=16).
+  * `reserve_sms` SMs are left to the NCCL kernels while buckets are in flight (from the first bucket launch of a backward pass
+    to its end): the engine's persistent GEMM sizes its grid for the remaining SMs (of_set_sm_limit), otherwise every GEMM
+    launched while a bucket is in flight runs as two waves (measured at 2 GPUs: 67.9 -> 65.7 ms per step with 16 reserved SMs
+    and NCCL_MAX_CTAS=16); the forward pass keeps every SM;
+  * buckets taper: 256 MB while plenty of backward is left to hide them, 32 MB over the last 192 MB of the arena, and the arena
+    order puts the audio encoder BEFORE the down path (engine.backward_param_plan), so the exposed tail is one small bucket.
 The path has exactly one exchange step: sum of gradients; everything else is batch-sharded.
 """
 from __future__ import annotations
@@ -24,31 +27,25 @@ from .engine import backward_param_order  # noqa: E402,F401  (re-exported: the a
 
 
 class GradAllReducer:
-    """Owns the gradient arena of `model.unet` and all-reduces (averages) it bucket by bucket during backward."""
+    """Owns the gradient arena of `model.unet` and all-reduces (averages) it bucket by bucket during backward.
+
+    Construction mirrors what DDP construction gives the reference (`accelerator.prepare`, trainer.py:264-269): parameters and
+    buffers are broadcast from rank 0, so replicas start identical whatever each rank's seed / checkpoint state was."""
 
     def __init__(self, model: torch.nn.Module, bucket_bytes: int = 256 << 20, group=None, overlap: bool = True,
-                 reserve_sms: int = 0) -> None:
+                 reserve_sms: int = 0, tail_bucket_bytes: int = 32 << 20, tail_bytes: int = 192 << 20,
+                 broadcast_params: bool = True) -> None:
         unet = model.unet if hasattr(model, "unet") else model
         self.unet, self.group, self.overlap = unet, group, overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bucket_bytes, self.tail_bucket_bytes, self.tail_bytes = bucket_bytes, tail_bucket_bytes, tail_bytes
         store = unet._store
-        store.ensure_arena(unet)                 # the engine owns the gradient arena; buckets are contiguous slices of it
         self.store = store
-        params = store.arena_params
-        dev = params[0].device
-        self.buckets = []      # (start, end, [param ids])
-        b_start, b_ids = 0, []
-        end = 0
-        for p, (s0, e0) in zip(params, store.arena_offsets):
-            b_ids.append(id(p))
-            end = e0
-            if (end - b_start) * 4 >= bucket_bytes:
-                self.buckets.append((b_start, end, b_ids))
-                b_start, b_ids = end, []
-        if b_ids:
-            self.buckets.append((b_start, end, b_ids))
-        self.bucket_of = {pid: bi for bi, (_, _, ids) in enumerate(self.buckets) for pid in ids}
-        self.ready_at = None           # bucket index -> tape op index after which it is complete (learned in step 1)
+        if broadcast_params and self.world > 1:
+            self.broadcast_parameters(model)
+        store.ensure_arena(unet)                 # the engine owns the gradient arena; buckets are contiguous slices of it
+        dev = store.arena_params[0].device
+        self._build_buckets()
         self.comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._pending: List[int] = []
         store.on_backward_begin = self._begin
@@ -56,15 +53,47 @@ class GradAllReducer:
         unet.grad_sync = self._after_op
         unet.grad_finish = self.finish
         self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
-        # leave `reserve_sms` SMs to the NCCL kernels: the persistent GEMM grid shrinks accordingly (see of_set_sm_limit)
-        self.reserve_sms = reserve_sms
-        if reserve_sms > 0 and dev.type == "cuda" and self.world > 1:
-            from . import _native as N
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            N.lib().of_set_sm_limit(max(2, (sms - reserve_sms) // 2 * 2))
+        # leave `reserve_sms` SMs to the NCCL kernels WHILE buckets are in flight: the persistent GEMM grid shrinks from the first
+        # bucket launch of a backward pass to its end (of_set_sm_limit is read at launch time, i.e. baked into a captured graph);
+        # forward and the part of backward before the first bucket keep every SM.
+        self.reserve_sms = reserve_sms if (dev.type == "cuda" and self.world > 1) else 0
+        self._sms = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 0
+        self._reserved = False
         self._touch_log = {}
         self._op = None
         self._launched = set()
+
+    # ---- replica consistency
+    def broadcast_parameters(self, model: torch.nn.Module, src: int = 0) -> None:
+        """Every parameter and buffer takes rank `src`'s value (what DDP's constructor does); operand caches are invalidated."""
+        with torch.no_grad():
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=src, group=self.group)
+        self.store.param_epoch += 1
+
+    # ---- bucket table
+    def _build_buckets(self) -> None:
+        """Contiguous slices of the arena in backward-completion order; large buckets first (NVSwitch collectives are latency-
+        bound), small ones over the last `tail_bytes` so that what cannot hide under the remaining backward is short."""
+        store = self.store
+        params, offs = store.arena_params, store.arena_offsets
+        total = offs[-1][1] if offs else 0
+        tail_start = max(0, total - self.tail_bytes // 4)
+        self.buckets = []      # (start, end, [param ids])
+        b_start, b_ids, end = 0, [], 0
+        for p, (s0, e0) in zip(params, offs):
+            b_ids.append(id(p))
+            end = e0
+            limit = min(self.bucket_bytes, self.tail_bucket_bytes) if s0 >= tail_start else self.bucket_bytes
+            if (end - b_start) * 4 >= limit:
+                self.buckets.append((b_start, end, b_ids))
+                b_start, b_ids = end, []
+        if b_ids:
+            self.buckets.append((b_start, end, b_ids))
+        self.bucket_of = {pid: bi for bi, (_, _, ids) in enumerate(self.buckets) for pid in ids}
+        self.ready_at = None           # bucket index -> tape op index after which it is complete (learned in one backward pass)
+        self._plan_key = (store.arena_key, store.arena.data_ptr() if store.arena is not None else 0)
+        self._tape_len = None
 
     # ---- hooks called by the engine
     @property
@@ -75,7 +104,19 @@ class GradAllReducer:
     def views(self):
         return self.store.arena_views
 
+    def _set_reserved(self, on: bool) -> None:
+        if self.reserve_sms <= 0 or on == self._reserved:
+            return
+        from . import _native as N
+        N.lib().of_set_sm_limit(max(2, (self._sms - self.reserve_sms) // 2 * 2) if on else 0)
+        self._reserved = on
+
     def _begin(self) -> None:
+        store = self.store
+        # the arena is rebuilt whenever the trainable set changes (adapter injection, merge_and_unload, requires_grad_ toggles):
+        # old offsets / learned readiness would then address the wrong slices
+        if self._plan_key != (store.arena_key, store.arena.data_ptr() if store.arena is not None else 0):
+            self._build_buckets()
         self._launched = set()
         self._touch_log = {}
 
@@ -83,7 +124,12 @@ class GradAllReducer:
         self._touch_log[pid] = self._op
 
     def _after_op(self, i: int) -> None:
-        """Called by Tape.run_backward after tape op i (ops run from last to first)."""
+        """Called by the engine before the first tape op (i = len(tape) + 1) and by Tape.run_backward after tape op i (ops run from
+        last to first)."""
+        if self._op is None or i > self._op + 1:           # first call of this backward pass: i = tape length + 1
+            if self._tape_len is not None and self._tape_len != i:
+                self.ready_at = None                       # the tape changed shape: learned readiness is stale
+            self._tape_len = i
         self._op = i - 1
         if self.ready_at is None or not self.overlap or self.world == 1:
             return
@@ -104,6 +150,7 @@ class GradAllReducer:
         if self.comm is None:
             self._reduce(self.arena[s:e])
             return
+        self._set_reserved(True)
         cur = torch.cuda.current_stream()
         self.comm.wait_stream(cur)
         with torch.cuda.stream(self.comm):
@@ -117,12 +164,14 @@ class GradAllReducer:
                     self._launch(bi)
             if self.comm is not None:
                 torch.cuda.current_stream().wait_stream(self.comm)
+        self._set_reserved(False)
         if self.ready_at is None and self._touch_log:
             ready = []
             for _, _, ids in self.buckets:
                 idx = [self._touch_log[p] for p in ids if p in self._touch_log and self._touch_log[p] is not None]
                 ready.append(min(idx) if idx else 0)
             self.ready_at = ready
+        self._op = None
 
     # kept for API symmetry with bench.py's post_backward hook: all work already happened inside backward
     def all_reduce(self) -> None:

@@ -177,54 +177,78 @@ def backward_param_order(unet) -> List[torch.nn.Parameter]:
     return backward_param_plan(unet)[0]
 
 
+def film_units(unet):
+    """Top-level units of the denoiser in FORWARD order, each a list of modules whose FiLM heads (`ResidualBlock.mlp`) get their
+    weight gradients from ONE grouped `of_film_bwd` launch as soon as the unit's backward has run (modules.UNet.denoise)."""
+    units = [[layer] for layer in unet.down_layers]
+    units.append([unet.middle_resnet1, *unet.middle_transformer, unet.middle_resnet2])
+    units += [[layer] for layer in unet.up_layers]
+    units.append([unet.final_resnet])
+    return units
+
+
 def backward_param_plan(unet):
-    """(order, (film_start, film_end)): parameters in the order their gradients become final during the engine's backward pass.
-    The FiLM heads (`ResidualBlock.mlp`) are the exception: their gradients are produced by ONE grouped kernel when the
-    conditioning MLPs are reached, so they sit together right after `init_x` (positions film_start..film_end of the order)."""
+    """(order, film_ranges): parameters in the order their gradients become final during the engine's backward pass.
+    The FiLM heads (`ResidualBlock.mlp`) of one unit (a UNetBlock, the middle, the final resnet) get their gradients from one
+    grouped kernel right after that unit's backward, so they sit together at the END of the unit's parameters; `film_ranges`
+    lists their (start, end) positions in `order`.  The audio encoder's backward runs right after `middle_resnet1` (its forward
+    is recorded after the down path, modules.UNet.run), so the tail of backward is the cheap first down block."""
     order: List[torch.nn.Parameter] = []
     seen = set()
-    film = []
+    film_ranges = []
 
-    def add(module):
+    def add(module, film):
         for name, p in module.named_parameters():
             if id(p) in seen:
                 continue
             seen.add(id(p))
             (film if name.startswith("mlp.") or ".mlp." in name else order).append(p)
 
-    def add_block(blk):
-        add(blk.sampler)
+    def add_block(blk, film):
+        add(blk.sampler, film)
         for res, tr in reversed(list(zip(blk.resnets, blk.transformers))):
-            add(tr)
-            add(res)
-        add(blk.init_resnet)
+            add(tr, film)
+            add(res, film)
+        add(blk.init_resnet, film)
 
-    add(unet.final_conv)
-    add(unet.final_resnet)
+    def close(film):
+        if film:
+            film_ranges.append((len(order), len(order) + len(film)))
+            order.extend(film)
+
+    add(unet.final_conv, [])
+    film = []
+    add(unet.final_resnet, film)
+    close(film)
     for blk in reversed(unet.up_layers):
-        add_block(blk)
-    add(unet.middle_resnet2)
+        film = []
+        add_block(blk, film)
+        close(film)
+    film = []
+    add(unet.middle_resnet2, film)
     for tr in reversed(unet.middle_transformer):
-        add(tr)
-    add(unet.middle_resnet1)
+        add(tr, film)
+    add(unet.middle_resnet1, film)
+    close(film)
+    for blk in reversed(unet.audio_encoder.layers):
+        film = []
+        add_block(blk, film)
+        close(film)
+    add(unet.audio_encoder.init_conv, [])
     for blk in reversed(unet.down_layers):
-        add_block(blk)
-    add(unet.init_x)
-    film_start = len(order)
-    order.extend(film)
-    film_end = len(order)
+        film = []
+        add_block(blk, film)
+        close(film)
+    add(unet.init_x, [])
     for p in list(unet.time_mlp.parameters()) + list(unet.cond_mlp.parameters()) + [unet.null_cond]:
         if id(p) not in seen:
             seen.add(id(p))
             order.append(p)
-    for blk in reversed(unet.audio_encoder.layers):
-        add_block(blk)
-    add(unet.audio_encoder.init_conv)
     for p in unet.parameters():          # anything not covered above
         if id(p) not in seen:
             seen.add(id(p))
             order.append(p)
-    return order, (film_start, film_end)
+    return order, film_ranges
 
 
 class ParamStore:
@@ -248,7 +272,7 @@ class ParamStore:
         self.arena_params = []       # trainable parameters in arena order
         self.arena_offsets = []      # (start, end) in floats, aligned
         self.arena_key = None
-        self.film_floats = None      # (start, end) floats of the FiLM-head block (written, never accumulated -> not zeroed)
+        self.film_floats = None      # [(start, end)] float ranges of the FiLM-head blocks (written, never accumulated -> not zeroed)
         self.touched = set()
         self.param_epoch = 0         # bumped by optimizers that update parameters through raw pointers (osufusion_b200/optim.py)
         self.pack_plan = None
@@ -263,10 +287,10 @@ class ParamStore:
     def ensure_arena(self, unet) -> None:
         custom = getattr(unet, "backward_param_order", None)
         if custom is not None:       # other backbones (osufusion_b200/backbones.py) supply their own completion order; no FiLM block
-            order, fs, fe = custom(), 0, 0
+            order, franges = custom(), []
         else:
-            order, (fs, fe) = backward_param_plan(unet)
-        film_ids = {id(p) for p in order[fs:fe]}
+            order, franges = backward_param_plan(unet)
+        film_ids = {id(p) for fs, fe in franges for p in order[fs:fe]}
         params = [p for p in order if p.requires_grad]
         key = tuple(id(p) for p in params) + (str(params[0].device) if params else "",)
         if key == self.arena_key:
@@ -281,16 +305,18 @@ class ParamStore:
         self.arena = torch.zeros(max(total, 1), dtype=F32, device=dev)
         self.arena_views, self.arena_params, self.arena_offsets = {}, params, []
         off = 0
-        f0 = f1 = None
+        ranges = []
         for p in params:
             n = (p.numel() + A - 1) // A * A
             self.arena_views[id(p)] = self.arena[off:off + p.numel()].view(p.shape)
             self.arena_offsets.append((off, off + n))
             if id(p) in film_ids:
-                f0 = off if f0 is None else f0
-                f1 = off + n
+                if ranges and ranges[-1][1] == off:
+                    ranges[-1][1] = off + n
+                else:
+                    ranges.append([off, off + n])
             off += n
-        self.film_floats = (f0, f1) if f0 is not None else None
+        self.film_floats = [tuple(r) for r in ranges] or None
         self.arena_key = key
         self.film_plans = {}
 
@@ -305,11 +331,13 @@ class ParamStore:
         if self.arena is None:
             pass
         elif film_overwritten and self.film_floats is not None:
-            f0, f1 = self.film_floats
-            if f0 > 0:
-                self.arena[:f0].zero_()
-            if f1 < self.arena.numel():
-                self.arena[f1:].zero_()
+            pos = 0
+            for f0, f1 in self.film_floats:      # the FiLM-head gradients are plain stores: zero only what lies between them
+                if f0 > pos:
+                    self.arena[pos:f0].zero_()
+                pos = f1
+            if pos < self.arena.numel():
+                self.arena[pos:].zero_()
         else:
             self.arena.zero_()
         self.touched = set()
@@ -442,10 +470,11 @@ class ParamStore:
             return plan
         dev = heads[0].mlp[1].weight.device
         K = heads[0].mlp[1].weight.shape[1]
-        groups, chunks, slices = [], [], {}
+        groups, chunks, slices, chunk_range = [], [], {}, {}
         row = 0
         ch = N.lib().of_film_chunk_rows()
         for gi, h in enumerate(heads):
+            c0 = len(chunks) // 2
             lin = h.mlp[1]
             Nn = lin.weight.shape[0]
             assert lin.weight.shape[1] == K and Nn % 4 == 0
@@ -460,10 +489,11 @@ class ParamStore:
             for n0 in range(0, Nn, ch):
                 chunks += [gi, n0]
             slices[id(h)] = (B * row, Nn)
+            chunk_range[id(h)] = (c0, len(chunks) // 2)
             row += Nn
         arr = (N.FilmGroup * len(groups))(*groups)
         plan = {
-            "ptrs": ptrs, "heads": heads, "K": K, "rows": row, "num_groups": len(groups), "slices": slices,
+            "ptrs": ptrs, "heads": heads, "K": K, "rows": row, "num_groups": len(groups), "slices": slices, "chunk_range": chunk_range,
             "groups": torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev),
             "chunks": torch.tensor(chunks, dtype=torch.int32).to(dev), "num_chunks": len(chunks) // 2,
         }
@@ -809,6 +839,7 @@ class Ctx:
         use_pool(self.zpool)
         self.film = None         # id(ResidualBlock) -> (B, 2C) fp32 view of the grouped FiLM output
         self.film_dss = None     # ... and of its gradient accumulator
+        self.film_bwd = None     # callable(heads): grouped FiLM weight-gradient launch for a unit's heads (modules.UNet.conditioning)
 
 
 def conv3(ctx: Ctx, x16, conv, *, stats=None, out=None):

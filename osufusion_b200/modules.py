@@ -305,14 +305,22 @@ class UNet(nn.Module):
                 dss_all = torch.zeros((B * plan["rows"],), dtype=F32, device=dev)
                 ctx.film_dss = {k: dss_all[o:o + B * n].view(B, n) for k, (o, n) in plan["slices"].items()}
 
-            def backward():
-                if plan is not None:
-                    N.call("of_film_bwd", plan["groups"].data_ptr(), plan["chunks"].data_ptr(), plan["num_chunks"],
+            ctx.film_bwd = None
+            if plan is not None:
+                def film_bwd(heads):
+                    """Weight / bias gradients of the given FiLM heads (one grouped launch over their chunk range; consecutive in the
+                    plan) and their contribution to d emb_act; called right after the backward of the unit that owns them."""
+                    c0 = min(plan["chunk_range"][id(h)][0] for h in heads)
+                    c1 = max(plan["chunk_range"][id(h)][1] for h in heads)
+                    N.call("of_film_bwd", plan["groups"].data_ptr(), plan["chunks"].data_ptr() + 8 * c0, c1 - c0,
                            dss_all.data_ptr(), emb_r.data_ptr(), B, plan["K"], ctx.d_emb_act.data_ptr())
-                    for h in plan["heads"]:
+                    for h in heads:
                         for p_ in h.mlp[1].parameters():
                             if p_.requires_grad:
                                 st.touch(p_)
+                ctx.film_bwd = film_bwd
+
+            def backward():
                 dcat = E.empty((B, 2 * Em), F32, dev)
                 N.call("of_silu_small", cat.data_ptr(), ctx.d_emb_act.data_ptr(), dcat.data_ptr(), cat.numel())
                 dt = dcat[:, :Em]
@@ -328,24 +336,42 @@ class UNet(nn.Module):
                 E.linear_small_bwd_param(st, dt1, t1pre, 1, temb, l1.weight, l1.bias, None)
             ctx.tape.push(backward)
 
-    def denoise(self, ctx: Ctx, x16: torch.Tensor, a_feat: Act, t, c, keep) -> tuple:
-        """Everything of UNet.forward after the input packing and the audio encoder.  Returns (out16 (B, Lp, 8), final Act)."""
+    def _film_unit(self, ctx: Ctx, modules) -> None:
+        """Tape marker placed BEFORE a unit's forward ops: in backward it runs right after the unit and produces the weight
+        gradients of the unit's FiLM heads, so they (and their all-reduce bucket) complete progressively instead of at the end."""
+        if ctx.tape is None or ctx.film_bwd is None:
+            return
+        heads = [m for u in modules for m in u.modules() if type(m).__name__ == "ResidualBlock" and m.mlp is not None]
+        if heads:
+            ctx.tape.push(lambda: ctx.film_bwd(heads))
+
+    def denoise(self, ctx: Ctx, x16: torch.Tensor, a_feat, t, c, keep) -> tuple:
+        """Everything of UNet.forward after the input packing and the audio encoder.  Returns (out16 (B, Lp, 8), final Act).
+        `a_feat` is the encoded audio (Act) or a callable producing it: the training step evaluates the audio encoder AFTER the
+        down path (it depends on neither x nor t), so that its backward runs right after `middle_resnet1` and the cheap first
+        down block — not the 26 % audio encoder — is the un-overlappable tail of the gradient all-reduce."""
         st, dev = ctx.store, ctx.device
         self.conditioning(ctx, t, c, keep)
         x = E.cross_embed(ctx, self.init_x, x16)
         r = x
         skips = []
         for layer in self.down_layers:
+            self._film_unit(ctx, [layer])
             x, s = E.unet_block(ctx, layer, x)
             skips.append(s)
+        if callable(a_feat):
+            a_feat = a_feat()
+        self._film_unit(ctx, [self.middle_resnet1, self.middle_resnet2])
         x = E.concat(ctx, x, a_feat)
         x = E.residual_block(ctx, self.middle_resnet1, x)
         for tr in self.middle_transformer:
             x = E.transformer_block(ctx, tr, x)
         x = E.residual_block(ctx, self.middle_resnet2, x)
         for layer in self.up_layers:
+            self._film_unit(ctx, [layer])
             x = E.concat(ctx, x, skips.pop())
             x, _ = E.unet_block(ctx, layer, x)
+        self._film_unit(ctx, [self.final_resnet])
         x = E.concat(ctx, x, r)
         x = E.residual_block(ctx, self.final_resnet, x)
         B, Lp, Cc = x.bf16.shape
@@ -379,8 +405,7 @@ class UNet(nn.Module):
         self._store.begin_forward(refresh if refresh is not None else tape is not None, self)
         x16 = _pack(x, 8, Lp, X_PAD_VALUE, noise, ca, cb)
         a16 = _pack(a, self.dim_in_a, Lp, A_PAD_VALUE)
-        a_feat = self.encode_audio(ctx, a16)
-        out16, xf = self.denoise(ctx, x16, a_feat, t, c, keep)
+        out16, xf = self.denoise(ctx, x16, lambda: self.encode_audio(ctx, a16), t, c, keep)
         return out16, (ctx, xf)
 
     def backward_from(self, ctx: Ctx, xf: Act, dY16: torch.Tensor, params):

@@ -32,7 +32,12 @@ def cosine_schedule_with_warmup(optimizer, num_warmup_steps: int, num_training_s
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    """AdamW over `model.unet`'s trainable parameters with the gradient-norm clip fused in (torch.optim.AdamW defaults)."""
+    """AdamW over `model.unet`'s trainable parameters with the gradient-norm clip fused in (torch.optim.AdamW defaults).
+
+    `param_groups[0]["params"]` lists the trainable parameters in `model.parameters()` order — the order
+    `torch.optim.AdamW(model.parameters())` of the reference (trainer.py:230) uses — and `state_dict()` emits torch's own
+    per-parameter format (`state[i] = {step, exp_avg, exp_avg_sq}`), so optimizer checkpoints move between the reference and
+    this repo in both directions.  Internally the moments live in two flat arenas with the gradient arena's layout."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
                  max_grad_norm: Optional[float] = 1.0) -> None:
@@ -41,25 +46,44 @@ class FusedAdamW(torch.optim.Optimizer):
         store = unet._store
         store.ensure_arena(unet)
         self.store = store
-        params = list(store.arena_params)
+        in_arena = {id(p) for p in store.arena_params}
+        params = [p for p in model.parameters() if id(p) in in_arena]
+        assert len(params) == len(in_arena), "every trainable parameter of the model must belong to model.unet"
+        self._n_model_params = sum(1 for _ in model.parameters())
+        self._model_index = [i for i, p in enumerate(model.parameters()) if id(p) in in_arena]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.max_grad_norm = max_grad_norm
         self._step = 0
         self._plan_key = None
+        self._tables = {}
         self._build()
+
+    def _table(self, skip: frozenset):
+        """Device table of the tensors to update (parameters whose gradient is None are skipped, as torch.optim.AdamW does)."""
+        hit = self._tables.get(skip)
+        if hit is not None:
+            return hit
+        st = self.store
+        lib = N.lib()
+        rows, cta = [], 0
+        for p, (s0, _) in zip(st.arena_params, st.arena_offsets):
+            if id(p) in skip:
+                continue
+            assert p.is_contiguous() and p.dtype == torch.float32
+            rows.append(N.OptTensor(p.data_ptr(), s0, p.numel(), cta, 0))
+            cta += lib.of_opt_tensor_ctas(p.numel())
+        if not rows:
+            hit = (None, 0, 0)
+        else:
+            arr = (N.OptTensor * len(rows))(*rows)
+            hit = (torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(st.arena.device), len(rows), cta)
+        self._tables[skip] = hit
+        return hit
 
     def _build(self) -> None:
         st = self.store
         dev = st.arena.device
-        lib = N.lib()
-        rows, cta = [], 0
-        for p, (s0, _) in zip(st.arena_params, st.arena_offsets):
-            assert p.is_contiguous() and p.dtype == torch.float32
-            rows.append(N.OptTensor(p.data_ptr(), s0, p.numel(), cta, 0))
-            cta += lib.of_opt_tensor_ctas(p.numel())
-        arr = (N.OptTensor * len(rows))(*rows)
-        self._table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-        self._num, self._ctas = len(rows), cta
+        self._tables = {}
         if getattr(self, "exp_avg", None) is None or self.exp_avg.numel() != st.arena.numel():
             self.exp_avg = torch.zeros_like(st.arena)
             self.exp_avg_sq = torch.zeros_like(st.arena)
@@ -78,32 +102,71 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._plan_key != (st.arena.data_ptr(), tuple(p.data_ptr() for p in st.arena_params)):
             self._build()
         # gradients must be the engine's arena views (they are after a backward pass of the engine); anything else is copied in
+        skip = []
         for p in st.arena_params:
             v = st.arena_views[id(p)]
             if p.grad is None:
-                v.zero_()
+                v.zero_()                # keeps the global norm right; the tensor itself is left untouched (torch skips grad None)
+                skip.append(id(p))
             elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
+        table, num, ctas = self._table(frozenset(skip))
         g = self.param_groups[0]
         self._step += 1
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
         if clip:
             N.call("of_grad_sumsq", st.arena.data_ptr(), st.arena.numel(), self._sumsq.data_ptr())
-        N.call("of_adamw_step", self._table.data_ptr(), self._num, self._ctas, st.arena.data_ptr(), self.exp_avg.data_ptr(),
-               self.exp_avg_sq.data_ptr(), self._sumsq.data_ptr() if clip else None, float(self.max_grad_norm or 0.0), float(g["lr"]),
-               float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self._step)
+        if table is not None:
+            N.call("of_adamw_step", table.data_ptr(), num, ctas, st.arena.data_ptr(), self.exp_avg.data_ptr(),
+                   self.exp_avg_sq.data_ptr(), self._sumsq.data_ptr() if clip else None, float(self.max_grad_norm or 0.0), float(g["lr"]),
+                   float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self._step)
         st.param_epoch += 1     # parameters changed through raw pointers (torch's _version did not move): invalidate operand caches
         return loss
 
+    # ---- checkpoints: torch.optim.AdamW's own state layout
+    def _moment_views(self, p):
+        (s0, _) = self.store.arena_offsets[self._arena_index[id(p)]]
+        return self.exp_avg[s0:s0 + p.numel()].view(p.shape), self.exp_avg_sq[s0:s0 + p.numel()].view(p.shape)
+
+    @property
+    def _arena_index(self):
+        return {id(p): i for i, p in enumerate(self.store.arena_params)}
+
     def state_dict(self):
+        """torch format: `state[i] = {"step", "exp_avg", "exp_avg_sq"}` with i indexing the trainable parameters in
+        `model.parameters()` order (empty before the first step, like torch)."""
+        self.state.clear()
+        if self._step > 0:
+            for p in self.param_groups[0]["params"]:
+                m, v = self._moment_views(p)
+                self.state[p] = {"step": torch.tensor(float(self._step)), "exp_avg": m, "exp_avg_sq": v}
         d = super().state_dict()
-        d["fused"] = {"step": self._step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+        self.state.clear()
         return d
 
     def load_state_dict(self, sd):
-        fused = sd.get("fused")
-        super().load_state_dict({k: v for k, v in sd.items() if k != "fused"})
-        if fused is not None:
-            self._step = int(fused["step"])
-            self.exp_avg.copy_(fused["exp_avg"])
-            self.exp_avg_sq.copy_(fused["exp_avg_sq"])
+        """Accepts this class's own dict and a reference `torch.optim.AdamW(model.parameters())` dict — including one saved over ALL
+        model parameters with some of them frozen (trainer_peft.py: state only for the adapter tensors)."""
+        sd = {k: v for k, v in sd.items() if k != "fused"}          # round-1 private key: ignored
+        groups = sd["param_groups"]
+        n_here = len(self.param_groups[0]["params"])
+        ids = [i for g in groups for i in g["params"]]
+        if len(groups) == 1 and len(ids) == self._n_model_params and n_here != self._n_model_params:
+            keep = [ids[i] for i in self._model_index]                # indices of our trainable tensors in the reference's numbering
+            remap = {old: new for new, old in enumerate(keep)}
+            sd = {"state": {remap[k]: v for k, v in sd["state"].items() if k in remap},
+                  "param_groups": [dict(groups[0], params=list(range(n_here)))]}
+        super().load_state_dict(sd)                                  # raises ValueError on a genuine size mismatch
+        steps = []
+        for p in self.param_groups[0]["params"]:
+            stt = self.state.get(p)
+            m, v = self._moment_views(p)
+            if stt:
+                m.copy_(stt["exp_avg"])
+                v.copy_(stt["exp_avg_sq"])
+                steps.append(int(float(stt["step"])))
+            else:
+                m.zero_()
+                v.zero_()
+        self._step = max(steps) if steps else 0
+        self.state.clear()

@@ -596,7 +596,9 @@ def of_film_fwd(groups, num_groups, total_rows, x, M, K, out):
 
 def of_film_bwd(groups, chunks, num_chunks, dss, x, M, K, d_emb):
     X = v2(x, F32, M, K)
-    for g in _film_groups(groups, num_groups=len(set(_mem(chunks, 2 * num_chunks, torch.int32)[0::2].tolist()))):
+    idx = sorted(set(_mem(chunks, 2 * num_chunks, torch.int32)[0::2].tolist()))    # a launch may cover a sub-range of the heads
+    all_groups = _film_groups(groups, num_groups=max(idx) + 1)
+    for g in (all_groups[i] for i in idx):
         d = _mem(dss + 4 * g.out_off, M * g.N, F32).view(M, g.N)
         if g.dW:
             v2(g.dW, F32, g.N, K).copy_(d.t() @ X)

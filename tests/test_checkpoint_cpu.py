@@ -98,3 +98,59 @@ def test_adapter_directory_roundtrip_and_merged_model(tmp_path):
     assert set(merged) == base_keys
     if w_eff is not None:
         assert torch.allclose(merged[names[0] + ".weight"], w_eff, atol=1e-5)
+
+
+def test_fused_adamw_state_dict_is_torch_format_both_directions(tmp_path):
+    """optimizer checkpoints must move between `torch.optim.AdamW(model.parameters())` (what the reference saves,
+    trainer.py:230,167) and FusedAdamW in both directions: per-parameter state in model.parameters() order, moments scattered to /
+    gathered from the arenas.  Host logic only (no kernel launch)."""
+    from oracle.models import DiffusionOsuFusion as OracleModel
+    from osufusion_b200.optim import FusedAdamW
+    m = _model()
+    ref = OracleModel(96, dim_h_mult=TINY["dim_h_mult"], num_layer_blocks=TINY["num_layer_blocks"],
+                      num_middle_transformers=TINY["num_middle_transformers"], attn_dim_head=TINY["attn_dim_head"],
+                      attn_heads=TINY["attn_heads"])
+    ref.load_state_dict(m.state_dict())
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-5)
+    g = torch.Generator().manual_seed(3)
+    for _ in range(2):
+        for p in ref.parameters():
+            p.grad = torch.randn(p.shape, generator=g)
+        ropt.step()
+    sd = ropt.state_dict()
+    opt = FusedAdamW(m, lr=1e-5)
+    assert opt.state_dict()["state"] == {}                      # like torch before the first step
+    opt.load_state_dict(copy.deepcopy(sd))                       # reference -> ours
+    assert opt._step == 2
+    for p, q in zip(m.parameters(), ref.parameters()):
+        mv, vv = opt._moment_views(p)
+        assert torch.equal(mv, ropt.state[q]["exp_avg"]) and torch.equal(vv, ropt.state[q]["exp_avg_sq"])
+    out = opt.state_dict()                                       # ours -> reference
+    assert out["param_groups"][0]["params"] == sd["param_groups"][0]["params"]
+    ropt2 = torch.optim.AdamW(ref.parameters(), lr=1e-5)
+    ropt2.load_state_dict(out)
+    for q in ref.parameters():
+        assert torch.equal(ropt2.state[q]["exp_avg"], ropt.state[q]["exp_avg"])
+        assert torch.equal(ropt2.state[q]["exp_avg_sq"], ropt.state[q]["exp_avg_sq"])
+        assert float(ropt2.state[q]["step"]) == 2.0
+    # through the reference's checkpoint.pt layout, with the ValueError / RuntimeError fallback exercised by a wrong-size optimizer dict
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+    d = ck.save_checkpoint(m, opt, sched, 4, tmp_path)
+    m2 = _model()
+    opt2 = FusedAdamW(m2, lr=1e-5)
+    assert ck.load_checkpoint(m2, opt2, torch.optim.lr_scheduler.LambdaLR(opt2, lambda s: 1.0), d) == 5
+    assert opt2._step == 2 and torch.equal(opt2.exp_avg, opt.exp_avg)
+    # PEFT: the reference's AdamW covers ALL parameters (frozen ones carry no state); ours covers the adapter tensors
+    m3 = _model()
+    lora.inject_adapters(m3, r=4, lora_alpha=4, use_dora=True)
+    ropt3 = torch.optim.AdamW(m3.parameters(), lr=1e-5)
+    for p in m3.parameters():
+        if p.requires_grad:
+            p.grad = torch.randn(p.shape, generator=g)
+    ropt3.step()
+    opt3 = FusedAdamW(m3, lr=1e-5)
+    opt3.load_state_dict(copy.deepcopy(ropt3.state_dict()))
+    assert opt3._step == 1
+    for p in m3.parameters():
+        if p.requires_grad:
+            assert torch.equal(opt3._moment_views(p)[0], ropt3.state[p]["exp_avg"])

@@ -133,3 +133,71 @@ def test_real_backward_tape_allreduce_world2_gloo(kind):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == "ok" for r in res)
+
+
+def _worker_replica_sync(rank, world, port, out):
+    """(a) replicas built from DIFFERENT seeds must be identical after GradAllReducer construction (DDP's constructor
+    broadcast); (b) a change of the trainable set (adapter injection) rebuilds the arena — buckets and learned readiness must
+    follow it instead of slicing the new arena with stale offsets."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import fake_native
+    from oracle.synth import TINY, synth_inputs
+    from osufusion_b200 import _native, lora
+    from osufusion_b200.ddp import GradAllReducer
+    from osufusion_b200.modules import UNet, UNetFunction
+    _native.call = fake_native.call
+
+    torch.manual_seed(1000 + rank)                      # rank-dependent initialisation
+    net = UNet(6, 96, 5, **TINY)
+    torch.nn.init.normal_(net.final_conv.weight, std=0.02)
+    red = GradAllReducer(net, bucket_bytes=1 << 18)
+    flat = torch.cat([p.detach().flatten() for p in net.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas differ after construction"
+
+    def grads_of(seed):
+        x, a, c, t, noise, keep = synth_inputs(2, 48, seed)
+        net.zero_grad(set_to_none=True)
+        y = UNetFunction.apply(net, x, a, t, c, keep, *list(net.parameters()))
+        torch.nn.functional.mse_loss(y, noise).backward()
+        return {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    for _ in range(2):
+        grads_of(5 + rank)
+    n_buckets_full, key_full = len(red.buckets), red._plan_key
+    assert red.ready_at is not None
+    # change the trainable set: only adapter tensors keep requires_grad -> the engine rebuilds a (much smaller) arena
+    lora.inject_adapters(net, r=4, lora_alpha=4, use_dora=True)
+    with torch.no_grad():
+        for m in net.modules():
+            if hasattr(m, "lora_B"):
+                m.lora_B["default"].weight.normal_(std=0.05)
+    g1 = grads_of(9 + rank)
+    assert red._plan_key != key_full and len(red.buckets) != n_buckets_full
+    assert red.arena.numel() * 4 == sum((e - s) * 4 for s, e, _ in red.buckets)
+    g2 = grads_of(9 + rank)                               # overlapped step with the re-learned readiness
+    for k in g1:
+        assert torch.allclose(g1[k], g2[k], rtol=1e-4, atol=1e-7), k
+    flat = torch.cat([g2[k].flatten() for k in sorted(g2)])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "averaged adapter gradients differ across ranks"
+    out.put((rank, "ok", len(red.buckets)))
+    dist.destroy_process_group()
+
+
+def test_replica_broadcast_and_arena_rebuild_world2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_replica_sync, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == "ok" for r in res)
