@@ -155,7 +155,69 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.ref_validate_frames and args.ref_validate_frames != frames:
+        # ONE step at the workload's own length (batch 1): checks the FLOP-scaled bounded sample above (attention is 6 % of the FLOPs at
+        # 1024 frames and 33 % at 4096, and CPU bf16 SDPA is slower per FLOP than the CPU convolutions)
+        vsec, _, _ = cpu_reference_step_time(args.size, args.ref_validate_frames, 1, 0)
+        vequiv = fwd_tflop(args.size, args.ref_validate_frames) / fwd_tflop(args.size, args.frames)
+        line["validation"] = {"frames": args.ref_validate_frames, "batch": 1, "sec_per_step": vsec, "value": vequiv / vsec,
+                              "unit": "samples/s", "note": "single cold step (no warm-up) at the workload's sequence length; "
+                                                           "the headline value of this line is the bounded-sample figure"}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(size: str, dx, da, dc, steps: int = 3):
+    """"The reference on the same box" (SURVEY.md §2.3 / §8d): the oracle port of the reference's module tree under
+    torch.autocast(cuda, bf16) — cuDNN convs, cuBLAS linears, SDPA flash attention, ATen norms, torch autograd — on the SAME GPU,
+    SAME batch, in the same run: eager (what trainer.py runs) and captured as one CUDA graph (host launch overhead excluded).
+    A reported baseline; never on the product path."""
+    from oracle.models import DiffusionOsuFusion as OracleModel
+    dev = dx.device
+    torch.manual_seed(0)
+    ora = OracleModel(SIZES[size]).to(dev)
+    torch.nn.init.normal_(ora.unet.final_conv.weight, std=0.02)
+
+    def step():
+        ora.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = ora(dx, da, dc)
+        loss.backward()
+        return loss
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    out = {"what": "oracle port of the reference under torch.autocast(bf16): torch eager + cuDNN/cuBLAS/SDPA on this GPU, same batch"}
+    for _ in range(2):
+        step()
+    out["eager_ms_per_step"] = timed(step, steps)
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        ora.zero_grad(set_to_none=True)
+        with torch.cuda.graph(g):
+            step()
+        g.replay()
+        out["cuda_graph_ms_per_step"] = timed(g.replay, steps)
+        del g
+    except Exception as e:  # noqa: BLE001
+        out["cuda_graph_ms_per_step"] = None
+        out["cuda_graph_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+    del ora
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -297,6 +359,43 @@ def run_ours(args) -> None:
                "sample": f"mean of 4 steps (after 1 warm-up) of batch 1 x {args.ref_frames} frames = {equiv:.3f} workload samples each by "
                          f"algorithmic FLOPs, fp32 oracle port on the host CPU ({sec:.1f} s per step)"}
 
+    # ---- cost of the gradient exchange (N > 1): the same captured step with the collectives removed (a) keeping the launch schedule
+    # and the SM reservation, (b) without either = the single-GPU step in this process
+    comm = None
+    if world > 1 and sync is not None and not args.no_comm_breakdown:
+        def time_variant(dry_run, world_one):
+            sync.dry_run = dry_run
+            saved = sync.world
+            if world_one:
+                sync.world = 1
+            g2 = GraphedTrainStep(model, dx, da, dc, warmup=2)
+            for _ in range(3):
+                g2()
+            barrier()
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0_.record()
+            for _ in range(args.steps):
+                g2()
+            t1_.record()
+            barrier()
+            sync.dry_run, sync.world = False, saved
+            t = torch.tensor([t0_.elapsed_time(t1_) / args.steps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            del g2
+            return float(t)
+        ms_resv = time_variant(True, False)
+        ms_single = time_variant(False, True)
+        comm = {"step_ms": ms, "no_collective_same_schedule_and_reservation_ms": ms_resv, "no_collective_no_reservation_ms": ms_single,
+                "exposed_comm_ms": ms - ms_resv, "sm_reservation_ms": ms_resv - ms_single, "total_comm_cost_ms": ms - ms_single,
+                "buckets": len(sync.buckets), "bucket_mb": [round((e - s_) * 4 / 2 ** 20, 1) for s_, e, _ in sync.buckets],
+                "gradient_bytes": int(sync.arena.numel() * 4)}
+    eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager_baseline:
+        eager = gpu_eager_baseline(size, dx, da, dc)
+        eager["speedup_vs_eager"] = eager["eager_ms_per_step"] / ms
+        if eager.get("cuda_graph_ms_per_step"):
+            eager["speedup_vs_eager_cuda_graph"] = eager["cuda_graph_ms_per_step"] / ms
+
     if rank == 0:
         tf_peak, _, _ = peaks()
         step_tflop = 3 * fwd_tflop(size, n) * B
@@ -316,7 +415,7 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step * args.steps),
             "model_tflops_per_gpu": step_tflop / (ms * 1e-3), "mfu_vs_measured_peak": step_tflop / (ms * 1e-3) / tf_peak,
-            "roofline": roof, "cpu_baseline": cpu, "loss": float(step.loss.detach()),
+            "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "comm": comm, "loss": float(step.loss.detach()),
             "optimizer_ms_per_step": opt_ms,
         }
         print(json.dumps(line), flush=True)
@@ -429,6 +528,10 @@ def main() -> None:
     ap.add_argument("--frames", type=int, default=4096)
     ap.add_argument("--ref-frames", type=int, default=1024, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true", help="skip timing the oracle under torch eager bf16 on the same GPU")
+    ap.add_argument("--no-comm-breakdown", action="store_true", help="N>1: skip the two extra captured steps that isolate the all-reduce cost")
+    ap.add_argument("--ref-validate-frames", type=int, default=4096,
+                    help="--impl reference: also time ONE step at this length (batch 1) to validate the FLOP-scaled bounded sample; 0 = off")
     ap.add_argument("--reserve-sms", type=int, default=16,
                     help="N>1: SMs left to the overlapped NCCL all-reduce (NCCL_MAX_CTAS and the persistent GEMM grid; measured at 2 GPUs: "
                          "0 -> 67.9 ms, 8 -> 70.0, 16 -> 65.7, 32 -> 70.2)")

@@ -272,6 +272,11 @@ int of_mse_bwd(const void* pred, long long ld, long long bs, const float* x, con
 int of_sampler_update(const float* xin, const void* cond, const void* null_, long long ld, long long bs, float cond_scale,
                       int mode, float c_eps, float c_div, float c_x0, float c_dir, int B, int C, int N, float* xout,
                       void* packed, int Lp, int Cp, float pad_value, void* stream);
+/* same, with the four per-step coefficients {c_eps, c_div, c_x0, c_dir} read from DEVICE memory, so that one captured CUDA graph
+ * (denoiser evaluation + update) serves every step of the loop (diffusion.py:71-75, rectified_flow.py:69-79) */
+int of_sampler_update_dev(const float* xin, const void* cond, const void* null_, long long ld, long long bs, float cond_scale,
+                          int mode, const float* coef_dev, int B, int C, int N, float* xout, void* packed, int Lp, int Cp,
+                          float pad_value, void* stream);
 int of_pack_conv_weight(const float* w, int Cout, int Cin, int k, void* out, int Cin_pad, int tap_offset, int taps_total,
                         void* stream);
 int of_unpack_conv_wgrad(float* packed, int Cout, int Cin, int k, int Cin_pad, int tap_offset, float* dw, int accumulate,

@@ -121,6 +121,7 @@ _SIGS = {
     "of_mse_fwd": [P, LL, LL, P, P, F, F, P, I, I, I, P, P, P],
     "of_mse_bwd": [P, LL, LL, P, P, F, F, P, I, I, I, I, I, P, P, P, P],
     "of_sampler_update": [P, P, P, LL, LL, F, I, F, F, F, F, I, I, I, P, P, I, I, F, P],
+    "of_sampler_update_dev": [P, P, P, LL, LL, F, I, P, I, I, I, P, P, I, I, F, P],
     "of_pack_conv_weight": [P, I, I, I, P, I, I, I, P],
     "of_unpack_conv_wgrad": [P, I, I, I, I, I, P, I, I, P],
     "of_cast_f32_bf16": [P, P, LL, P],

@@ -722,9 +722,12 @@ __global__ void sampler_update_kernel(const float* __restrict__ xin, const __nv_
                                       const __nv_bfloat16* __restrict__ null_, long long ld, long long bs, float s, int mode,
                                       float c_eps, float c_div, float c_x0, float c_dir, int B, int C, int N,
                                       float* __restrict__ xout, __nv_bfloat16* __restrict__ packed, int Lp, int Cp,
-                                      float pad_value) {
+                                      float pad_value, const float* __restrict__ coef_dev) {
   pdl_launch_dependents();
   pdl_wait();
+  if (coef_dev) {   // per-step coefficients in device memory: the launch (and a CUDA graph holding it) is step-independent
+    c_eps = coef_dev[0]; c_div = coef_dev[1]; c_x0 = coef_dev[2]; c_dir = coef_dev[3];
+  }
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Lp * Cp;
   if (idx >= total) return;
@@ -1035,7 +1038,18 @@ extern "C" int of_sampler_update(const float* xin, const void* cond, const void*
   long long total = (long long)B * Lp * Cp;
   OF_CHECK_CUDA(launch_pdl(sampler_update_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, 
       xin, reinterpret_cast<const __nv_bfloat16*>(cond), reinterpret_cast<const __nv_bfloat16*>(null_), ld, bs, cond_scale, mode, c_eps,
-      c_div, c_x0, c_dir, B, C, N, xout, reinterpret_cast<__nv_bfloat16*>(packed), Lp, Cp, pad_value));
+      c_div, c_x0, c_dir, B, C, N, xout, reinterpret_cast<__nv_bfloat16*>(packed), Lp, Cp, pad_value, (const float*)nullptr));
+  DONE()
+}
+
+extern "C" int of_sampler_update_dev(const float* xin, const void* cond, const void* null_, long long ld, long long bs, float cond_scale,
+                                     int mode, const float* coef_dev, int B, int C, int N, float* xout, void* packed, int Lp, int Cp,
+                                     float pad_value, void* stream) {
+  OF_REQUIRE(xin && cond && xout && coef_dev, "of_sampler_update_dev: null pointer");
+  long long total = (long long)B * Lp * Cp;
+  OF_CHECK_CUDA(launch_pdl(sampler_update_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM,
+      xin, reinterpret_cast<const __nv_bfloat16*>(cond), reinterpret_cast<const __nv_bfloat16*>(null_), ld, bs, cond_scale, mode, 0.f,
+      1.f, 0.f, 0.f, B, C, N, xout, reinterpret_cast<__nv_bfloat16*>(packed), Lp, Cp, pad_value, coef_dev));
   DONE()
 }
 

@@ -59,6 +59,7 @@ class GradAllReducer:
         self.reserve_sms = reserve_sms if (dev.type == "cuda" and self.world > 1) else 0
         self._sms = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 0
         self._reserved = False
+        self.dry_run = False
         self._touch_log = {}
         self._op = None
         self._launched = set()
@@ -147,6 +148,9 @@ class GradAllReducer:
     def _launch(self, bi: int) -> None:
         self._launched.add(bi)
         s, e, _ = self.buckets[bi]
+        if self.dry_run:                   # bench.py: same launch schedule and SM reservation, no collective (isolates its cost)
+            self._set_reserved(True)
+            return
         if self.comm is None:
             self._reduce(self.arena[s:e])
             return

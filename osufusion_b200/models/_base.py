@@ -2,6 +2,7 @@
 and the CFG-batched, audio-cached sampling loop."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -112,6 +113,71 @@ class BaseOsuFusion(nn.Module):
         if s.cfg:
             return out16[:s.b], out16[s.b:]
         return out16, None
+
+    # ------------------------------------------------------------------ sampling, one CUDA graph per step
+    def _graph_key(self, s, cond_scale, tag):
+        st = self.unet._store
+        vers = sum(p._version for p in self.unet.parameters())
+        return (tag, s.b, s.n, bool(s.cfg), float(cond_scale), str(s.x.device), st.param_epoch, vers)
+
+    def _sampler_graphs(self, s, cond_scale, tag, kinds):
+        """CUDA graphs of one sampler step each: `[cond; null]` denoiser evaluation (~1.3 k launches) + fused CFG / update kernel,
+        with the timestep and the update coefficients read from device buffers, so the same graph is replayed for every step of
+        the loop (diffusion.py:71-75, rectified_flow.py:69-79) and for every later `sample()` call of the same shape.
+        `kinds`: one (mode, src, dst_x, dst_packed) tuple per graph over the state's static buffers.  Returns None when graphs are
+        disabled (OF_SAMPLER_GRAPH=0)."""
+        if os.environ.get("OF_SAMPLER_GRAPH", "1") == "0" or not s.x.is_cuda:
+            return None
+        cache = self.__dict__.setdefault("_sgraphs", {})
+        key = self._graph_key(s, cond_scale, tag)
+        hit = cache.get(key)
+        if hit is None:
+            cache.clear()                      # weights / shapes changed: the old graphs reference stale operand buffers
+            dev = s.x.device
+            st = BaseOsuFusion._SamplerState()
+            st.ctx, st.cfg, st.b, st.n, st.Lp = s.ctx, s.cfg, s.b, s.n, s.Lp
+            st.a_feat = Act(None, s.a_feat.bf16.clone())
+            st.c, st.keep = s.c.clone(), s.keep.clone()
+            st.x = torch.empty_like(s.x)
+            st.xtmp = torch.empty_like(s.x)
+            st.x16 = torch.empty_like(s.x16)
+            st.xmid16 = torch.empty_like(s.x16)
+            st.t_buf = torch.zeros(s.b, dtype=F32, device=dev)
+            st.coef = torch.zeros(4, dtype=F32, device=dev)
+            st.x.copy_(s.x)
+            st.x16.copy_(s.x16)
+            st.xmid16.copy_(s.x16)
+
+            def body(mode, src, dst_x, dst_packed):
+                # a fresh pool of zero-initialised scratch per evaluation: its chunk fills must be nodes of the captured graph
+                # (a chunk zeroed before the capture would carry the previous replay's accumulators)
+                st.ctx.zpool = E.ZeroPool(dev)
+                E.use_pool(st.ctx.zpool)
+                cond16, null16 = self._eval_denoiser(st, getattr(st, src), st.t_buf)
+                bs, ld = E._bl(cond16)
+                N.call("of_sampler_update_dev", st.x.data_ptr(), cond16.data_ptr(), E._p(null16), ld, bs, float(cond_scale), mode,
+                       st.coef.data_ptr(), st.b, TOTAL_DIM, st.n, getattr(st, dst_x).data_ptr(), getattr(st, dst_packed).data_ptr(),
+                       st.Lp, 8, X_PAD_VALUE)
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for k in kinds:                 # warm-up: populates operand / RoPE / FiLM-plan caches outside the capture
+                    body(*k)
+            torch.cuda.current_stream().wait_stream(side)
+            graphs = []
+            for k in kinds:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    body(*k)
+                graphs.append(g)
+            hit = cache[key] = (st, graphs)
+        st, graphs = hit
+        st.a_feat.bf16.copy_(s.a_feat.bf16)
+        st.c.copy_(s.c)
+        st.x.copy_(s.x)
+        st.x16.copy_(s.x16)
+        return st, graphs
 
     def _update(self, s, xin, cond16, null16, cond_scale, mode, c_eps, c_div=1.0, c_x0=0.0, c_dir=0.0):
         xout = torch.empty_like(xin)

@@ -60,8 +60,19 @@ class OsuFusion(BaseOsuFusion):
         """diffusion.py:59-77.  Audio encoder evaluated once (loop-invariant), cond+null batched, CFG+DDIM update fused."""
         s = self._sampler_setup(a, c, x, cond_scale)
         self.scheduler.set_timesteps(self.sampling_timesteps)
+        steps = self.scheduler.timesteps.tolist()
+        g = self._sampler_graphs(s, cond_scale, "ddim", [(0, "x16", "x", "x16")])
+        if g is not None:
+            st, (graph,) = g
+            tt = torch.tensor(steps, dtype=torch.float32).to(a.device)
+            coefs = torch.tensor([self.scheduler.step_coeffs(t) for t in steps], dtype=torch.float32).to(a.device)
+            for i in range(len(steps)):
+                st.t_buf.copy_(tt[i].expand(st.b))          # timestep and DDIM coefficients are device data of the captured step
+                st.coef.copy_(coefs[i])
+                graph.replay()
+            return st.x.clone()
         xcur, x16 = s.x, s.x16
-        for t in self.scheduler.timesteps.tolist():
+        for t in steps:
             tb = torch.full((s.b,), t, dtype=torch.int64, device=a.device)
             cond16, null16 = self._eval_denoiser(s, x16, tb)
             c_eps, c_div, c_x0, c_dir = self.scheduler.step_coeffs(t)

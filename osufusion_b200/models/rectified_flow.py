@@ -27,6 +27,22 @@ class OsuFusion(BaseOsuFusion):
         """rectified_flow.py:57-79: midpoint over linspace(0, 1, sample_timesteps): two CFG evaluations per interval."""
         s = self._sampler_setup(a, c, x, cond_scale)
         times = torch.linspace(0.0, 1.0, self.sample_timesteps)
+        g = self._sampler_graphs(s, cond_scale, "midpoint", [(1, "x16", "xtmp", "xmid16"), (1, "xmid16", "x", "x16")])
+        if g is not None:
+            st, (g_half, g_full) = g
+            t0s, t1s = times[:-1], times[1:]
+            dts = t1s - t0s
+            zero = torch.zeros_like(dts)
+            one = torch.ones_like(dts)
+            # rows: [t, c_eps, c_div, c_x0, c_dir] for the half step (y_mid = y + f(t0, y) dt/2) and the full step (y += dt f(t0 + dt/2, y_mid))
+            half = torch.stack([t0s, 0.5 * dts, one, zero, zero], 1).to(a.device)
+            full = torch.stack([t0s + 0.5 * dts, dts, one, zero, zero], 1).to(a.device)
+            for i in range(dts.numel()):
+                for row, graph in ((half[i], g_half), (full[i], g_full)):
+                    st.t_buf.copy_(row[0].expand(st.b))
+                    st.coef.copy_(row[1:])
+                    graph.replay()
+            return st.x.clone()
         y, y16 = s.x, s.x16
         for t0, t1 in zip(times[:-1].tolist(), times[1:].tolist()):
             dt = t1 - t0

@@ -129,4 +129,6 @@ def attn_bwd(q, k, v, out, lse, dout, delta, dq, dk, dv, *, H, KVH, D, variant=0
     g.dk, g.dv = dk.data_ptr(), dv.data_ptr()
     assert _bl(dk) == _bl(dv)
     g.dkv_batch_stride, g.dkv_ld = _bl(dk)
-    N.call("of_attn_bwd", C.byref(g), flops=10.0 * g.B * H * g.L * g.L * D, family="attn_bwd_kernel (tcgen05 MQA flash)")
+    # algorithmic FLOPs: backward counted as 2x forward = 8 B H L^2 D; the S = QK^T recompute (another 2 B H L^2 D
+    # executed by the kernel) is not credited
+    N.call("of_attn_bwd", C.byref(g), flops=8.0 * g.B * H * g.L * g.L * D, family="attn_bwd_kernel (tcgen05 MQA flash)")

@@ -655,6 +655,11 @@ def of_sampler_update(xin, cond, null_, ld, bs, s, mode, c_eps, c_div, c_x0, c_d
         _mem(packed, B * Lp * Cp, BF16).view(B, Lp, Cp).copy_(pk.to(BF16))
 
 
+def of_sampler_update_dev(xin, cond, null_, ld, bs, s, mode, coef, B, Cc, n, xout, packed, Lp, Cp, pad):
+    c = _mem(coef, 4, F32).tolist()
+    of_sampler_update(xin, cond, null_, ld, bs, s, mode, c[0], c[1], c[2], c[3], B, Cc, n, xout, packed, Lp, Cp, pad)
+
+
 # ------------------------------------------------------------------------------------------------ LoRA / DoRA, optimizer
 def _packed_view(ptr, dtype, k, Cout, cin_pad, tap_stride):
     return _mem(ptr, (k - 1) * tap_stride + Cout * cin_pad, dtype).as_strided((k, Cout, cin_pad), (tap_stride, cin_pad, 1))

@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def test_reference_arm_prints_contract_line():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--size", "S", "--ref-frames", "256", "--steps", "1",
-                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+                        "--warmup", "1", "--ref-validate-frames", "512"], capture_output=True, text=True, timeout=600, cwd=str(ROOT))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, r.stdout
@@ -21,3 +21,4 @@ def test_reference_arm_prints_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "sample" in d["config"]
+    assert d["validation"]["frames"] == 512 and d["validation"]["value"] > 0
