@@ -176,6 +176,7 @@ def gpu_eager_baseline(size: str, dx, da, dc, steps: int = 3):
     torch.manual_seed(0)
     ora = OracleModel(SIZES[size]).to(dev)
     torch.nn.init.normal_(ora.unet.final_conv.weight, std=0.02)
+    ora.scheduler.alphas_cumprod = ora.scheduler.alphas_cumprod.to(dev)      # no host->device copy inside the captured step
 
     def step():
         ora.zero_grad(set_to_none=True)

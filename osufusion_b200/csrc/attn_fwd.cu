@@ -12,6 +12,8 @@
 //               (row max, then exp2 / row sum / bf16 P), lazy rescale of the TMEM O accumulator, final O/l and log-sum-exp.
 //   While one group runs its softmax the tensor core works for the other, hiding mbarrier / TMEM round trips.
 // Head dim D <= 64 (zero-padded to 64 by TMA out-of-bounds fill); any L (key tail masked).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -39,10 +41,37 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// exp2 of a PAIR on the FMA pipe (the MUFU unit, 16 ex2/clk/SM, is the busiest pipe of this kernel at D = 64: 2 x 128 x 64 exps
+// per KV tile against 512 clk of tensor work).  Cody-Waite: n = round(x) through the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, far below the bf16 rounding of P), 2^n by adding n to the exponent
+// field.  x <= 8 by construction (lazy rescale threshold); clamped at -126 so the exponent add cannot wrap.
+__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  const unsigned long long xc = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const unsigned long long magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+  const unsigned long long t = add_f32x2(xc, magic);
+  const unsigned long long n = add_f32x2(t, nmagic);
+  const unsigned long long f = fma_f32x2(n, pack_f32x2(-1.0f, -1.0f), xc);
+  unsigned long long q = fma_f32x2(pack_f32x2(0.055171649903059006f, 0.055171649903059006f), f, pack_f32x2(0.2426111251115799f, 0.2426111251115799f));
+  q = fma_f32x2(q, f, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+  q = fma_f32x2(q, f, pack_f32x2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  unpack_f32x2(q, q0, q1);
+  unpack_f32x2(t, t0, t1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
 // One CTA owns TWO 128-row Q tiles (same batch / head), one softmax warpgroup each; K/V stream in 64-key tiles.  With the small
 // KV tile, S and P are DOUBLE-buffered per group inside the 512 TMEM columns, so S_w(j+1), S_w(j+2) are computed while group w
 // still works on tile j and the softmax threads never wait for the tensor core (nor the tensor core for them):
 //   TMEM columns: S[w][b] = w*128 + b*64 (0..255) | O[w] = 256 + w*64 | P[w][b] = 384 + w*64 + b*32 (bf16x2 packed)
+// kPoly: how many of the 32 element pairs of a row of a KV tile take the polynomial exp2 (the rest use MUFU).
+// kAlt : the two softmax groups take turns in their exp phase (named barriers 2 / 3), so the MUFU unit of every SM sub-partition
+//        serves one warp at a time while the other warp of that sub-partition does its MUFU-free work (TMEM load, row max, P store,
+//        barrier traffic): left alone the symmetric groups fall into lockstep and the MUFU idles ~40 % of the time.
+template <int kPoly, bool kAlt>
 __global__ void __launch_bounds__(kAThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
@@ -174,6 +203,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const uint32_t tO = tmem + 256 + w * 64;
     float m_run = -INFINITY, m_used = -INFINITY, l = 0.f;
+    if (kAlt && w == 1) named_bar_arrive(2, 256);   // group 0 takes the first turn
     for (int j = 0; j < n; ++j) {
       const int bf = j & 1;
       const uint32_t tS = tmem + w * 128 + bf * 64, tP = tmem + 384 + w * 64 + bf * 32;
@@ -235,16 +265,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         m_used = m_run;
       }
       uint32_t pk[32];
+      if (kAlt) named_bar_sync(2 + w, 256);        // my turn on the MUFU
       if (full) {
-        float sa = 0.f, sb = 0.f;
+        const unsigned long long sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(-m_used, -m_used);
+        unsigned long long sum2 = 0ull;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), p.scale_log2, -m_used));
-          const float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.scale_log2, -m_used));
-          sa += p0;
-          sb += p1;
+          const unsigned long long x2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+          float p0, p1;
+          if (((i + 1) * kPoly) / 32 != (i * kPoly) / 32) {     // kPoly of the 32 pairs, evenly interleaved with the MUFU pairs
+            exp2_poly2(x2, p0, p1);
+          } else {
+            float x0, x1;
+            unpack_f32x2(x2, x0, x1);
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+          }
+          sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
           pk[i] = pack_bf16x2(p0, p1);
         }
+        float sa, sb;
+        unpack_f32x2(sum2, sa, sb);
         l += sa + sb;
       } else {
         float sum = 0.f;
@@ -259,6 +300,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         l += sum;
       }
+      if (kAlt && !(w == 1 && j == n - 1)) named_bar_arrive(2 + (w ^ 1), 256);   // hand the MUFU to the other group
       mbar_wait(&p_empty[w * 2 + bf], ((j >> 1) & 1) ^ 1);   // P V of tile j-2 has finished reading this P buffer
       tc_fence_after();
       {
@@ -308,6 +350,261 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Version 3: TWO CTAs per SM.  Measured on the B200 (tools/ubench/ubench_sm.cu): one warp can issue a MUFU.EX2 only every ~12 clk,
+// two warps per SM sub-partition reach 8.8 clk, four reach the unit's 8 clk — and the serial, latency-bound sections of a softmax
+// warp (TMEM load, row-max chain, TMEM store, barrier round trips, ~400 clk per tile) leave the MUFU idle unless other warps of the
+// same sub-partition have exp work.  The kernel above has 2 softmax warps per sub-partition (MUFU 58 % busy under ncu); this one
+// halves every per-CTA resource so that two CTAs (4 softmax warps per sub-partition) share an SM:
+//   * 256 TMEM columns: S is single-buffered and P (bf16x2) is written over the first 32 columns of its own S tile — S_w(j+1) is
+//     issued right after P_w(j) V_j (tcgen05.mma execute in issue order), so neither `s_empty` nor `p_empty` barriers exist;
+//     layout: S/P[w] = w*64 | O[w] = 128 + w*64
+//   * <= 102 registers: the softmax makes two passes over S in tensor memory (row max; then exp / sum / pack in two 32-column halves)
+//   * 4 K/V stages (96 KB of shared memory per CTA).
+constexpr int kKvStages2 = 4;
+
+template <int kPoly>
+__global__ void __launch_bounds__(kAThreads, 2)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                  // 2 x 16 KB
+  uint8_t* sKV = sQ + 2 * kTileBytes;                  // kKvStages2 x (K 8 KB + V 8 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kKvStages2 * 2 * kKvBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                // [kKvStages2]
+  uint64_t* kv_empty = kv_full + kKvStages2;   // [kKvStages2]
+  uint64_t* s_full = kv_empty + kKvStages2;    // [group]
+  uint64_t* p_full = s_full + 2;               // [group]
+  uint64_t* o_full = p_full + 2;               // [group]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int n = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKvStages2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const int kvh = h % p.KVH;
+    if (leader) {
+      mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, h, q0, b);
+      tma_load_4d(sQ + kTileBytes, &tmap_q, q_full, 0, h, q0 + 128, b);
+    }
+    for (int j = 0; j < n; ++j) {
+      const int st = j % kKvStages2, use = j / kKvStages2;
+      mbar_wait(&kv_empty[st], (use & 1) ^ 1);
+      uint8_t* sk = sKV + st * 2 * kKvBytes;
+      if (leader) {
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kKvBytes);
+        tma_load_4d(sk, &tmap_k, &kv_full[st], 0, kvh, j * kKvTile, b);
+        tma_load_4d(sk + kKvBytes, &tmap_v, &kv_full[st], 0, kvh, j * kKvTile, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc_s = make_idesc_bf16(128, kKvTile, 0, 0);
+    const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+    auto issue_s = [&](int w, int j) {     // S_w(j) = Q_w K_j^T into the group's (single) S region, then signal the softmax group
+      const uint32_t aQ = smem_u32(sQ + w * kTileBytes);
+      const uint32_t aK = smem_u32(sKV + (j % kKvStages2) * 2 * kKvBytes);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem + w * 64, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[w]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(1, 0);
+    for (int j = 0; j < n; ++j) {
+      const bool more = j + 1 < n;
+      if (more) mbar_wait(&kv_full[(j + 1) % kKvStages2], ((j + 1) / kKvStages2) & 1);
+      const uint32_t aV = smem_u32(sKV + (j % kKvStages2) * 2 * kKvBytes + kKvBytes);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        mbar_wait(&p_full[w], j & 1);
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < kKvTile / 16; ++k)     // O_w += P_w(j) V_j : P from tensor memory (over its own S tile), V MN-major
+            umma_f16_ts(tmem + 128 + w * 64, tmem + w * 64 + k * 8, make_smem_desc(aV + k * 2048, 8192, 1024), idesc_pv,
+                        (j > 0 || k > 0) ? 1u : 0u);
+          if (!more) umma_commit(&o_full[w]);
+        }
+        __syncwarp();
+        if (more) issue_s(w, j + 1);                // overwrites P_w(j): ordered after the MMAs above (in-order tensor pipe)
+      }
+      if (leader) umma_commit(&kv_empty[j % kKvStages2]);
+      __syncwarp();
+    }
+  } else {
+    const int w = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const uint32_t tS = tmem + w * 64 + lane_off, tO = tmem + 128 + w * 64 + lane_off;
+    float m_run = -INFINITY, m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(&s_full[w], j & 1);   // also implies P_w(j-1) V_(j-1) has completed (commit covers every earlier MMA)
+      tc_fence_after();
+      const int kv_valid = p.L - j * kKvTile;
+      const bool full = kv_valid >= kKvTile;
+      // ---- pass 1: row max
+      float mx;
+      {
+        uint32_t a[32], c[32];
+        tmem_ld_32x32b_x32(tS, a);
+        tmem_ld_32x32b_x32(tS + 32, c);
+        tmem_wait_ld();
+        if (full) {
+          float m0 = fmaxf(__uint_as_float(a[0]), __uint_as_float(a[1])), m1 = fmaxf(__uint_as_float(c[0]), __uint_as_float(c[1]));
+#pragma unroll
+          for (int i = 2; i < 32; i += 2) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(a[i]), __uint_as_float(a[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(c[i]), __uint_as_float(c[i + 1])));
+          }
+          mx = fmaxf(m0, m1);
+        } else {
+          mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < kv_valid) mx = fmaxf(mx, __uint_as_float(a[i]));
+            if (32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(c[i]));
+          }
+        }
+      }
+      m_run = fmaxf(m_run, mx * p.scale_log2);
+      if (j > 0) {
+        const bool need = (m_run - m_used) > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {   // rare: rescale O (every P V issued so far has completed, see above)
+          const float f = ex2(m_used - m_run);
+          m_used = m_run;
+          l *= f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tO + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            uint32_t (&o0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[0]);
+            uint32_t (&o1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[16]);
+            tmem_st_32x32b_x16(tO + c * 32, o0);
+            tmem_st_32x32b_x16(tO + c * 32 + 16, o1);
+          }
+          tmem_wait_st();
+        }
+      } else {
+        m_used = m_run;
+      }
+      // ---- pass 2: P = exp2(S*scale - m_used) in two 32-column halves; the bf16x2 pairs go over the S columns already consumed
+      const unsigned long long sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(-m_used, -m_used);
+      unsigned long long sum2 = 0ull;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t s[32];
+        tmem_ld_32x32b_x32(tS + hh * 32, s);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const unsigned long long x2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+          float p0, p1;
+          if (((i + 1) * kPoly) / 16 != (i * kPoly) / 16) {     // kPoly of the 16 pairs of a half on the FMA pipe
+            exp2_poly2(x2, p0, p1);
+          } else {
+            float x0, x1;
+            unpack_f32x2(x2, x0, x1);
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+          }
+          if (!full) {
+            if (hh * 32 + 2 * i >= kv_valid) p0 = 0.f;
+            if (hh * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
+          }
+          sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x16(tS + hh * 16, pk);
+      }
+      {
+        float sa, sb;
+        unpack_f32x2(sum2, sa, sb);
+        l += sa + sb;
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[w]);
+    }
+    // ---- epilogue
+    mbar_wait(&o_full[w], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int qrow = q0 + w * 128 + row;
+    __nv_bfloat16* dst = p.out + (long long)b * p.out_bs + (long long)qrow * p.out_ld + (long long)h * p.D;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tO + c * 32, o);
+      tmem_wait_ld();
+      if (qrow < p.L) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (c * 32 + g * 8 < p.D) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+            v.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+            v.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+            v.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = v;
+          }
+        }
+      }
+    }
+    if (qrow < p.L && p.lse) p.lse[((long long)b * p.H + h) * p.L + qrow] = m_used + log2f(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
 // (D, heads, L, B) view of a (B, L, heads*D [+ more]) channels-last buffer; box (64, 1, 128, 1).
 int make_head_tmap(CUtensorMap* m, const void* base, int D, int heads, int L, int B, long long ld, long long bs,
                    unsigned box_rows) {
@@ -346,13 +643,54 @@ extern "C" int of_attn_fwd(const of_attn_args* a, void* stream_) {
   p.out_bs = a->out_batch_stride;
   p.lse = a->lse;
   size_t smem_bytes = 1024 + 2 * kTileBytes + kKvStages * 2 * kKvBytes + 512;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   dim3 grid((a->L + 255) / 256, a->H, a->B);
-  OF_CHECK_CUDA(launch_pdl<1>(attn_fwd_kernel, grid, dim3(kAThreads), smem_bytes, stream, tq, tk, tv, p));
+  // variant (tuning / A-B probes; 0 = default): 10 + k -> k*4 polynomial pairs of 32 with alternation; 2 = round-1 schedule (no
+  // alternation, MUFU only)
+  //          30 + k -> version 3 (two CTAs per SM, see attn_fwd2_kernel) with 2k polynomial pairs of 16 per half row.
+  // Measured (B200, H16 KVH1 D64, tools/probe_attn_variants.py): B4 L4096 439 us (round 1) -> 377 us (13) -> 318 us (33);
+  // B1 L32768 6.52 ms -> 5.2 ms; grids of <= one CTA per SM (B2 L1024: 128 CTAs) are faster with one CTA per SM (20 us vs 23 us).
+  int v = a->variant;
+  if (v == 0) {
+    static const int dflt = [] { const char* e = getenv("OF_ATTN_FWD_VARIANT"); return e ? atoi(e) : 0; }();
+    v = dflt;
+    if (v == 0) v = ((long long)grid.x * grid.y * grid.z > (long long)device_sm_count()) ? 33 : 13;
+  }
+#define OF_FWD_CASE(V, POLY, ALT)                                                                                              \
+  if (v == (V)) {                                                                                                               \
+    static bool attr_set = false;                                                                                               \
+    if (!attr_set) {                                                                                                            \
+      OF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<POLY, ALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                                          \
+    }                                                                                                                           \
+    OF_CHECK_CUDA(launch_pdl<1>(attn_fwd_kernel<POLY, ALT>, grid, dim3(kAThreads), smem_bytes, stream, tq, tk, tv, p));         \
+  } else
+  OF_FWD_CASE(1, 0, false)
+  OF_FWD_CASE(2, 0, false)
+  OF_FWD_CASE(10, 0, true)
+  OF_FWD_CASE(11, 4, true)
+  OF_FWD_CASE(12, 8, true)
+  OF_FWD_CASE(13, 12, true)
+  OF_FWD_CASE(14, 16, true)
+  OF_FWD_CASE(21, 4, false)
+  OF_FWD_CASE(22, 8, false)
+#define OF_FWD2_CASE(V, POLY)                                                                                                  \
+  if (v == (V)) {                                                                                                               \
+    static bool attr_set = false;                                                                                               \
+    const size_t smem2 = 1024 + 2 * kTileBytes + kKvStages2 * 2 * kKvBytes + 256;                                               \
+    if (!attr_set) {                                                                                                            \
+      OF_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));     \
+      attr_set = true;                                                                                                          \
+    }                                                                                                                           \
+    OF_CHECK_CUDA(launch_pdl<1>(attn_fwd2_kernel<POLY>, grid, dim3(kAThreads), smem2, stream, tq, tk, tv, p));                  \
+  } else
+  OF_FWD2_CASE(30, 0)
+  OF_FWD2_CASE(31, 2)
+  OF_FWD2_CASE(32, 4)
+  OF_FWD2_CASE(33, 6)
+  OF_FWD2_CASE(34, 8)
+  { OF_REQUIRE(false, "of_attn_fwd: unknown variant %d", v); }
+#undef OF_FWD2_CASE
+#undef OF_FWD_CASE
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

@@ -143,7 +143,7 @@ class BaseOsuFusion(nn.Module):
             st.x16 = torch.empty_like(s.x16)
             st.xmid16 = torch.empty_like(s.x16)
             st.t_buf = torch.zeros(s.b, dtype=F32, device=dev)
-            st.coef = torch.zeros(4, dtype=F32, device=dev)
+            st.coef = torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=F32).to(dev)     # identity update during the warm-up evaluation
             st.x.copy_(s.x)
             st.x16.copy_(s.x16)
             st.xmid16.copy_(s.x16)

@@ -321,6 +321,8 @@ class UNet(nn.Module):
                 ctx.film_bwd = film_bwd
 
             def backward():
+                if plan is not None and self.grad_sync is None:
+                    ctx.film_bwd(plan["heads"])
                 dcat = E.empty((B, 2 * Em), F32, dev)
                 N.call("of_silu_small", cat.data_ptr(), ctx.d_emb_act.data_ptr(), dcat.data_ptr(), cat.numel())
                 dt = dcat[:, :Em]
@@ -339,8 +341,8 @@ class UNet(nn.Module):
     def _film_unit(self, ctx: Ctx, modules) -> None:
         """Tape marker placed BEFORE a unit's forward ops: in backward it runs right after the unit and produces the weight
         gradients of the unit's FiLM heads, so they (and their all-reduce bucket) complete progressively instead of at the end."""
-        if ctx.tape is None or ctx.film_bwd is None:
-            return
+        if ctx.tape is None or ctx.film_bwd is None or self.grad_sync is None:
+            return         # single GPU: one grouped launch over ALL heads at the end of backward (conditioning) is cheaper
         heads = [m for u in modules for m in u.modules() if type(m).__name__ == "ResidualBlock" and m.mlp is not None]
         if heads:
             ctx.tape.push(lambda: ctx.film_bwd(heads))

@@ -97,7 +97,7 @@ def ref_attn(q, k, v, H, KVH, D):
     return o.transpose(1, 2).reshape(B, L, H * D), torch.logsumexp(s, -1) * 1.4426950408889634
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 2, 10, 14, 22, 30, 32, 34])   # default / round-1 schedule / alternation / + polynomial exp2 / 2 CTAs per SM
 @pytest.mark.parametrize("B,L,H,KVH,D,qs", [(1, 128, 1, 1, 64, 1.0), (2, 1024, 16, 1, 64, 1.0), (2, 200, 2, 1, 16, 1.0), (1, 72, 4, 2, 32, 1.0),
                                             (1, 512, 4, 1, 64, 6.0)])
 def test_attention_forward(B, L, H, KVH, D, qs, variant):

@@ -163,6 +163,8 @@ def test_effective_weight_matches_reference_merged_weight_golden(name):
     N.call("of_dora_merge", W.data_ptr(), A.data_ptr(), Bm.data_ptr(), mag.data_ptr(), sc, Cout, Cin, k, r, n2.data_ptr(),
            packed.data_ptr(), Cin, Cout * Cin, None)
     assert nrel(packed, ref) < 1e-2
+    if r % 8 or E % 8:
+        return          # the engine takes the tensor-core path only for r, Cin*k multiples of 8 (engine.ParamStore._dora_merge_into)
     # tensor-core merge: V = W + (scaling B) A as a K = r GEMM, then norm / scale / pack per output channel
     A16 = torch.empty(r, E, device=dev, dtype=torch.bfloat16)
     N.call("of_cast_f32_bf16", A.data_ptr(), A16.data_ptr(), r * E)
