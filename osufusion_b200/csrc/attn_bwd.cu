@@ -9,6 +9,8 @@
 //   dV += P^T dO_i,  dK += dS^T Q_i                      (MN-major A straight from the same smem tiles; TMEM accum)
 //   dQ_i = dS K                                          (TMEM -> fp32 red.global.add, summed over KV tiles)
 // At the end dK/dV tiles are atomically added (fp32) to the shared-KV-head gradient (16 q heads contribute).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -16,6 +18,8 @@ namespace ofx {
 
 int make_head_tmap(CUtensorMap* m, const void* base, int D, int heads, int L, int B, long long ld, long long bs,
                    unsigned box_rows);
+int launch_attn_bwd2(const of_attn_args* a, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                     cudaStream_t stream);
 
 // Softmax / epilogue warps: kNP warps per TMEM lane quarter, each owning 128/kNP key columns of S and dP (and 64/kNP d-columns of
 // dQ, dK, dV).  kNP = 4 (16 warps, twice the warps per scheduler at half the work per thread) was measured: 1063 us vs 1030 us for
@@ -446,6 +450,19 @@ extern "C" int of_attn_bwd(const of_attn_args* a, void* stream_) {
         a->D);
     OF_CHECK_CUDA(cudaGetLastError());
     count_launch();
+  }
+  {
+    // version 2 (attn_bwd2.cu: transposed formulation, P^T / dS^T as tensor-memory operands) unless disabled or L % 4 != 0;
+    // variant 1 / OF_ATTN_BWD_VARIANT=1 selects the version-1 kernel below
+    static const int dflt = [] { const char* e = getenv("OF_ATTN_BWD_VARIANT"); return e ? atoi(e) : 0; }();
+    const int v = a->variant ? a->variant : dflt;
+    if (v != 1 && a->L % 4 == 0) {
+      int rc2 = launch_attn_bwd2(a, tq, tk, tv, tdo, stream);
+      if (rc2 != OF_OK) return rc2;
+      OF_CHECK_CUDA(cudaGetLastError());
+      count_launch();
+      return OF_OK;
+    }
   }
   AttnBwdParams p;
   p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.L = a->L; p.D = a->D;

@@ -35,34 +35,6 @@ struct AttnFwdParams {
   float* lse;  // (B, H, L) log2-domain log-sum-exp
 };
 
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// exp2 of a PAIR on the FMA pipe (the MUFU unit, 16 ex2/clk/SM, is the busiest pipe of this kernel at D = 64: 2 x 128 x 64 exps
-// per KV tile against 512 clk of tensor work).  Cody-Waite: n = round(x) through the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5],
-// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, far below the bf16 rounding of P), 2^n by adding n to the exponent
-// field.  x <= 8 by construction (lazy rescale threshold); clamped at -126 so the exponent add cannot wrap.
-__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& p0, float& p1) {
-  float x0, x1;
-  unpack_f32x2(x2, x0, x1);
-  const unsigned long long xc = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
-  const unsigned long long magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
-  const unsigned long long t = add_f32x2(xc, magic);
-  const unsigned long long n = add_f32x2(t, nmagic);
-  const unsigned long long f = fma_f32x2(n, pack_f32x2(-1.0f, -1.0f), xc);
-  unsigned long long q = fma_f32x2(pack_f32x2(0.055171649903059006f, 0.055171649903059006f), f, pack_f32x2(0.2426111251115799f, 0.2426111251115799f));
-  q = fma_f32x2(q, f, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
-  q = fma_f32x2(q, f, pack_f32x2(0.9999280571937561f, 0.9999280571937561f));
-  float q0, q1, t0, t1;
-  unpack_f32x2(q, q0, q1);
-  unpack_f32x2(t, t0, t1);
-  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
-  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
-}
-
 // One CTA owns TWO 128-row Q tiles (same batch / head), one softmax warpgroup each; K/V stream in 64-key tiles.  With the small
 // KV tile, S and P are DOUBLE-buffered per group inside the 512 TMEM columns, so S_w(j+1), S_w(j+2) are computed while group w
 // still works on tile j and the softmax threads never wait for the tensor core (nor the tensor core for them):

@@ -89,6 +89,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {
   asm volatile(
@@ -288,9 +294,47 @@ __device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, un
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long sub_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // named barriers (ids 1..15; id 0 is __syncthreads): `count` threads in total take part, some syncing, some only arriving
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exp2 of a PAIR on the FMA pipe (the MUFU unit, 16 ex2/clk/SM, is the busiest pipe of this kernel at D = 64: 2 x 128 x 64 exps
+// per KV tile against 512 clk of tensor work).  Cody-Waite: n = round(x) through the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, far below the bf16 rounding of P), 2^n by adding n to the exponent
+// field.  x <= 8 by construction (lazy rescale threshold); clamped at -126 so the exponent add cannot wrap.
+__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  const unsigned long long xc = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const unsigned long long magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+  const unsigned long long t = add_f32x2(xc, magic);
+  const unsigned long long n = add_f32x2(t, nmagic);
+  const unsigned long long f = fma_f32x2(n, pack_f32x2(-1.0f, -1.0f), xc);
+  unsigned long long q = fma_f32x2(pack_f32x2(0.055171649903059006f, 0.055171649903059006f), f, pack_f32x2(0.2426111251115799f, 0.2426111251115799f));
+  q = fma_f32x2(q, f, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+  q = fma_f32x2(q, f, pack_f32x2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  unpack_f32x2(q, q0, q1);
+  unpack_f32x2(t, t0, t1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
 
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
