@@ -355,18 +355,27 @@ int of_pack_seg_ctas(int Cout, int Cin, int k, int cin_pad);
  *   of_grad_sumsq : out[0] = sum g^2 over the arena (double; padding between tensors must be zero)
  *   of_adamw_step : torch.optim.AdamW semantics (decoupled weight decay, bias correction, amsgrad off); gradients are
  *                   scaled by min(1, max_norm / (sqrt(sumsq) + 1e-6)) read from DEVICE memory (sumsq NULL or max_norm <= 0:
- *                   no clipping) -- no host synchronisation.  Bytes per element: 16 read + 12 written.
+ *                   no clipping) -- no host synchronisation.  Bytes per element: 16 read + 12 written (+ 2 written when the
+ *                   bf16 GEMM operand is emitted).
+ *   Two extensions remove a full-tensor pass each from the training step:
+ *     - `operand_bf16` non-NULL: the updated parameter is also written as the bf16 GEMM operand the next forward pass consumes
+ *       (what of_pack_weights produced: the fp32 -> bf16 re-cast torch autocast does on every iteration);
+ *     - `k > 1` ("packed" Conv1d weight): gradient, moments and operand use the GEMM layout [k][Cout][Cin] (the weight-gradient
+ *       GEMM accumulates straight into the arena, no unpack pass), the fp32 master parameter keeps torch's (Cout, Cin, k) layout;
+ *       the kernel converts through a shared-memory slab (CTA = one output channel x 256 input channels, all taps).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
-  float* param;          /* fp32 parameter tensor (contiguous) */
+  float* param;          /* fp32 parameter tensor (contiguous, torch layout) */
   long long arena_off;   /* offset (floats) of its gradient / moments in the arenas */
   long long numel;
-  int cta_begin;         /* running sum of of_opt_tensor_ctas(numel) */
-  int _pad;
+  void* operand_bf16;    /* NULL or the bf16 operand copy to refresh (same layout as the gradient) */
+  int cta_begin;         /* running sum of of_opt_tensor_ctas2(numel, Cout, Cin, k) */
+  int Cout, Cin, k;      /* k > 1: packed conv tensor (numel == Cout*Cin*k); k <= 1: flat */
 } of_opt_tensor;
 
 int of_grad_sumsq(const float* grads, long long n, double* out, void* stream);
 int of_opt_tensor_ctas(long long numel);
+int of_opt_tensor_ctas2(long long numel, int Cout, int Cin, int k);
 int of_adamw_step(const of_opt_tensor* table_dev, int num_tensors, int total_ctas, const float* grads, float* exp_avg,
                   float* exp_avg_sq, const double* sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, void* stream);

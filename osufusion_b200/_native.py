@@ -85,7 +85,7 @@ class PackSeg(C.Structure):
 
 
 class OptTensor(C.Structure):
-    _fields_ = [("param", P), ("arena_off", LL), ("numel", LL), ("cta_begin", I), ("_pad", I)]
+    _fields_ = [("param", P), ("arena_off", LL), ("numel", LL), ("operand_bf16", P), ("cta_begin", I), ("Cout", I), ("Cin", I), ("k", I)]
 
 
 # name -> argtypes (the trailing stream pointer included); mirrors include/osufusion_b200.h
@@ -145,7 +145,7 @@ _SIGS = {
     "of_adaln_bwd": [P, LL, LL, P, LL, LL, I, I, I, P, LL, P, P, LL, LL, P, LL, LL, P, LL, P, LL, P],
     "of_gate_bwd": [P, LL, LL, P, LL, P, LL, LL, I, I, I, I, P, LL, LL, P, LL, P],
 }
-_PLAIN = {"of_set_sm_limit": [I], "of_rb_pool_parts": [C.POINTER(RbArgs)], "of_film_chunk_rows": [], "of_pack_seg_ctas": [I, I, I, I], "of_opt_tensor_ctas": [LL]}    # host-side helpers: no stream argument, return a value
+_PLAIN = {"of_set_sm_limit": [I], "of_rb_pool_parts": [C.POINTER(RbArgs)], "of_film_chunk_rows": [], "of_pack_seg_ctas": [I, I, I, I], "of_opt_tensor_ctas": [LL], "of_opt_tensor_ctas2": [LL, I, I, I]}    # host-side helpers: no stream argument, return a value
 EXPORTS = ["of_last_error", "of_version", "of_launch_count", "of_reset_launch_count", *_SIGS.keys(), *_PLAIN.keys()]
 
 

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   if (threadIdx.x == 0) atomicAdd(out, (double)s);
 }
 
-constexpr int kOptChunk = 4096;   // elements per CTA
+constexpr int kOptChunk = 4096;   // elements per CTA (flat tensors)
+constexpr int kOptPairs = 1024;   // (co, ci) pairs per CTA (packed conv tensors, k <= 4): 256 threads x 4
 
 // torch.optim.AdamW (amsgrad=False, maximize=False) on every tensor of the table; gradients are scaled by
 // clip = min(1, max_norm / (sqrt(sumsq) + 1e-6)) read from device memory (torch.nn.utils.clip_grad_norm_ semantics), without
@@ -295,9 +296,68 @@ __global__ void __launch_bounds__(256) adamw_kernel(const of_opt_tensor* __restr
     const float nrm = (float)sqrt(*sumsq);
     clip = fminf(1.0f, max_norm / (nrm + 1e-6f));
   }
-  const long long base = (long long)(cta - t.cta_begin) * kOptChunk;
   const float step_size = lr / bias_corr1;
   const float decay = 1.0f - lr * weight_decay;
+  __nv_bfloat16* op16 = reinterpret_cast<__nv_bfloat16*>(t.operand_bf16);
+  if (t.k > 1) {
+    // packed conv tensor: gradient / moments / operand are [k][Cout*Cin] planes; the parameter is (Cout*Cin, k) (torch layout).
+    // With q = co*Cin + ci the two layouts are plane[tap][q] and param[q*k + tap]: a CTA takes kOptPairs consecutive q — a contiguous
+    // parameter slab staged through shared memory, and k contiguous runs of the planes (16-byte vectors, all taps in flight).
+    __shared__ float sp[kOptPairs * 4];
+    const long long pairs = (long long)t.Cout * t.Cin;
+    const long long q0 = (long long)(cta - t.cta_begin) * kOptPairs;
+    const int nq = (int)min((long long)kOptPairs, pairs - q0);
+    float* pslab = t.param + q0 * t.k;
+    for (int i = threadIdx.x * 4; i < nq * t.k; i += blockDim.x * 4) {      // nq*k is a multiple of 4 (Cin % 8 == 0)
+      *reinterpret_cast<float4*>(sp + i) = *reinterpret_cast<const float4*>(pslab + i);
+    }
+    __syncthreads();
+    const int q = threadIdx.x * 4;
+    if (q < nq) {
+      float4 g4[4], m4[4], v4[4];
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) {
+        if (tap < t.k) {
+          const long long a = t.arena_off + (long long)tap * pairs + q0 + q;
+          g4[tap] = *reinterpret_cast<const float4*>(grads + a);
+          m4[tap] = *reinterpret_cast<const float4*>(exp_avg + a);
+          v4[tap] = *reinterpret_cast<const float4*>(exp_avg_sq + a);
+        }
+      }
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) {
+        if (tap < t.k) {
+          const long long a = t.arena_off + (long long)tap * pairs + q0 + q;
+          float gg[4] = {g4[tap].x, g4[tap].y, g4[tap].z, g4[tap].w}, mm[4] = {m4[tap].x, m4[tap].y, m4[tap].z, m4[tap].w},
+                vv[4] = {v4[tap].x, v4[tap].y, v4[tap].z, v4[tap].w}, pp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float g = gg[j] * clip;
+            float pv = sp[(q + j) * t.k + tap] * decay;
+            mm[j] = beta1 * mm[j] + (1.0f - beta1) * g;
+            vv[j] = beta2 * vv[j] + (1.0f - beta2) * g * g;
+            pv -= step_size * mm[j] / (sqrtf(vv[j]) / bias_corr2_sqrt + eps);
+            sp[(q + j) * t.k + tap] = pv;
+            pp[j] = pv;
+          }
+          *reinterpret_cast<float4*>(exp_avg + a) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+          *reinterpret_cast<float4*>(exp_avg_sq + a) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          if (op16) {
+            uint2 o;
+            o.x = pack_bf16x2(pp[0], pp[1]);
+            o.y = pack_bf16x2(pp[2], pp[3]);
+            *reinterpret_cast<uint2*>(op16 + (long long)tap * pairs + q0 + q) = o;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x * 4; i < nq * t.k; i += blockDim.x * 4) {
+      *reinterpret_cast<float4*>(pslab + i) = *reinterpret_cast<const float4*>(sp + i);
+    }
+    return;
+  }
+  const long long base = (long long)(cta - t.cta_begin) * kOptChunk;
 #pragma unroll
   for (int it = 0; it < kOptChunk / 1024; ++it) {
     const long long e = base + (it * 256 + threadIdx.x) * 4;
@@ -319,6 +379,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(const of_opt_tensor* __restr
       *reinterpret_cast<float4*>(t.param + e) = make_float4(pp[0], pp[1], pp[2], pp[3]);
       *reinterpret_cast<float4*>(exp_avg + a) = make_float4(mm[0], mm[1], mm[2], mm[3]);
       *reinterpret_cast<float4*>(exp_avg_sq + a) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      if (op16) {
+        uint2 o;
+        o.x = pack_bf16x2(pp[0], pp[1]);
+        o.y = pack_bf16x2(pp[2], pp[3]);
+        *reinterpret_cast<uint2*>(op16 + e) = o;
+      }
     } else {
       for (long long j = e; j < min(e + 4, t.numel); ++j) {
         const float g = grads[t.arena_off + j] * clip;
@@ -329,6 +395,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const of_opt_tensor* __restr
         t.param[j] = p;
         exp_avg[t.arena_off + j] = m;
         exp_avg_sq[t.arena_off + j] = v;
+        if (op16) op16[j] = __float2bfloat16_rn(p);
       }
     }
   }
@@ -350,6 +417,11 @@ extern "C" int of_grad_sumsq(const float* grads, long long n, double* out, void*
 }
 
 extern "C" int of_opt_tensor_ctas(long long numel) { return (int)((numel + kOptChunk - 1) / kOptChunk); }
+extern "C" int of_opt_tensor_ctas2(long long numel, int Cout, int Cin, int k) {
+  if (k <= 1) return of_opt_tensor_ctas(numel);
+  if (k > 4 || (long long)Cout * Cin * k != numel || Cin % 8 != 0) return -1;
+  return (int)(((long long)Cout * Cin + kOptPairs - 1) / kOptPairs);
+}
 
 extern "C" int of_adamw_step(const of_opt_tensor* table_dev, int num_tensors, int total_ctas, const float* grads, float* exp_avg,
                              float* exp_avg_sq, const double* sumsq, float max_norm, float lr, float beta1, float beta2, float eps,

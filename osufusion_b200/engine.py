@@ -26,6 +26,8 @@ GCTX_FUSED = os.environ.get("OF_GCTX_FUSED", "1") != "0"
 LORA_RANK_R = os.environ.get("OF_LORA_RANK_R", "1") != "0"
 # effective-weight merge W + scaling*B*A as a K = r tensor-core GEMM (+ a row-wise norm/scale/pack kernel) vs the CUDA-core kernel
 LORA_MERGE_TC = os.environ.get("OF_LORA_MERGE_TC", "1") != "0"
+# conv-weight gradients / moments in the GEMM layout [k][Cout][Cin] (no unpack pass, no per-layer scratch fill)
+PACKED_ARENA = os.environ.get("OF_PACKED_ARENA", "1") != "0"
 
 
 def _p(t):
@@ -177,6 +179,33 @@ def backward_param_order(unet) -> List[torch.nn.Parameter]:
     return backward_param_plan(unet)[0]
 
 
+def packed_conv_params(unet):
+    """{id(weight): (Cout, Cin, k)} of the k > 1 Conv1d weights whose gradient comes from the implicit-GEMM weight-gradient kernel
+    (`_wgrad_conv`): un-adapted `Block.proj`, `Upsample.conv`, `Parallel.fns[0]` with Cin a multiple of 8.  Their slice of the
+    gradient arena (and of the optimizer's moment arenas) uses the GEMM layout [k][Cout][Cin], so the split-K accumulation lands in
+    place and no unpack pass exists; the fp32 master weight keeps torch's (Cout, Cin, k) layout."""
+    out = {}
+
+    def add(conv):
+        if _adapter(conv) is not None:
+            return
+        w = conv.weight
+        Cout, Cin, k = w.shape
+        if 1 < k <= 4 and Cin % 8 == 0 and w.requires_grad:
+            out[id(w)] = (Cout, Cin, k)
+
+    for m in unet.modules():
+        kind = type(m).__name__
+        if kind == "ResidualBlock":
+            add(m.block1.proj)
+            add(m.block2.proj)
+        elif kind == "Upsample":
+            add(m.conv)
+        elif kind == "Parallel":
+            add(m.fns[0])
+    return out
+
+
 def film_units(unet):
     """Top-level units of the denoiser in FORWARD order, each a list of modules whose FiLM heads (`ResidualBlock.mlp`) get their
     weight gradients from ONE grouped `of_film_bwd` launch as soon as the unit's backward has run (modules.UNet.denoise)."""
@@ -273,6 +302,8 @@ class ParamStore:
         self.arena_offsets = []      # (start, end) in floats, aligned
         self.arena_key = None
         self.film_floats = None      # [(start, end)] float ranges of the FiLM-head blocks (written, never accumulated -> not zeroed)
+        self.packed = {}             # id(p) -> (Cout, Cin, k): conv weights whose gradient lives in the GEMM layout [k][Cout][Cin]
+        self.arena_packed_views = {} # id(p) -> (k, Cout, Cin) contiguous view of the same arena slice
         self.touched = set()
         self.param_epoch = 0         # bumped by optimizers that update parameters through raw pointers (osufusion_b200/optim.py)
         self.pack_plan = None
@@ -304,11 +335,20 @@ class ParamStore:
         dev = params[0].device
         self.arena = torch.zeros(max(total, 1), dtype=F32, device=dev)
         self.arena_views, self.arena_params, self.arena_offsets = {}, params, []
+        self.packed = packed_conv_params(unet) if PACKED_ARENA and custom is None else {}
+        self.arena_packed_views = {}
         off = 0
         ranges = []
         for p in params:
             n = (p.numel() + A - 1) // A * A
-            self.arena_views[id(p)] = self.arena[off:off + p.numel()].view(p.shape)
+            if id(p) in self.packed:
+                # gradient kept in the weight-gradient GEMM's own layout [k][Cout][Cin]; `p.grad` is the (Cout, Cin, k) permuted view
+                Cout, Cin, k = self.packed[id(p)]
+                pv = self.arena[off:off + p.numel()].view(k, Cout, Cin)
+                self.arena_packed_views[id(p)] = pv
+                self.arena_views[id(p)] = pv.permute(1, 2, 0)
+            else:
+                self.arena_views[id(p)] = self.arena[off:off + p.numel()].view(p.shape)
             self.arena_offsets.append((off, off + n))
             if id(p) in film_ids:
                 if ranges and ranges[-1][1] == off:
@@ -414,6 +454,7 @@ class ParamStore:
         buf = torch.empty(total, dtype=BF16, device=dev)
         lib = N.lib()
         segs = []
+        segs_host = [seg for _, _, seglist, _, _ in entries for seg in seglist]
         cta = 0
         for _, _, seglist, _, _ in entries:
             for (w, Cout, Cin, k, cp, off) in seglist:
@@ -430,7 +471,8 @@ class ParamStore:
                 n *= d
             views.append((key, params, buf[off0:off0 + n].view(shape)))
         ptrs = tuple(p.data_ptr() for _, ps, _ in views for p in ps)
-        return {"table": table, "num_segs": len(segs), "ctas": cta, "views": views, "ptrs": ptrs, "buf": buf, "vers": None}
+        return {"table": table, "num_segs": len(segs), "ctas": cta, "views": views, "ptrs": ptrs, "buf": buf, "vers": None,
+                "segs_host": segs_host}
 
     def refresh_operands(self, unet) -> None:
         plan = self.pack_plan
@@ -448,12 +490,34 @@ class ParamStore:
                 return
             plan["n_adapters"] = n_adapters
         vers = tuple(p._version for _, ps, _ in plan["views"] for p in ps) + (self.param_epoch,)
-        if not self.refresh and vers == plan["vers"]:
-            return
-        N.call("of_pack_weights", plan["table"].data_ptr(), plan["num_segs"], plan["ctas"])
-        plan["vers"] = vers
+        if vers != plan["vers"]:
+            # weights changed since the operand buffer was written (foreign optimizer, load_state_dict, ...).  The fused optimizer
+            # (optim.FusedAdamW) emits the bf16 operands itself while it updates the fp32 masters and marks them current
+            # (mark_operands_current), so a training loop built on it never comes through here.
+            N.call("of_pack_weights", plan["table"].data_ptr(), plan["num_segs"], plan["ctas"])
+            plan["vers"] = vers
         for key, params, view in plan["views"]:
             self.cache[key] = (tuple((p.data_ptr(), p._version) for p in params) + (self.param_epoch,), view, self.epoch)
+
+    def operand_targets(self, unet):
+        """{id(param): (device pointer of its bf16 operand copy, element pitch check)} for every weight of the grouped pack plan — what
+        the fused optimizer writes while updating the master weights.  Conv operands are only offered when unpadded (cin_pad == Cin)."""
+        if self.pack_plan is None:
+            self.refresh_operands(unet)
+        plan = self.pack_plan
+        out = {}
+        if plan is None:
+            return out
+        for (w, Cout, Cin, k, cp, off) in plan["segs_host"]:
+            if cp == Cin:
+                out[id(w)] = plan["buf"].data_ptr() + 2 * off
+        return out
+
+    def mark_operands_current(self) -> None:
+        """Called by the fused optimizer after a step in which it refreshed EVERY operand of the pack plan."""
+        plan = self.pack_plan
+        if plan is not None:
+            plan["vers"] = tuple(p._version for _, ps, _ in plan["views"] for p in ps) + (self.param_epoch,)
 
     # ---- grouped FiLM heads
     def film_plan(self, unet, B: int, with_grads: bool):
@@ -679,7 +743,16 @@ class ParamStore:
         for p in params:
             if p.requires_grad and id(p) in self.touched:
                 v = self.arena_views[id(p)]
-                out.append(v.view(v.shape))
+                if id(p) in self.packed:
+                    # permuted view of the GEMM-layout slice: autograd's AccumulateGrad would copy it into the parameter's own
+                    # layout (its "gradient layout contract"), so `.grad` is assigned here and autograd is told nothing
+                    if p.grad is None:
+                        p.grad = v.view(v.shape)
+                    elif p.grad.data_ptr() != v.data_ptr():
+                        p.grad.add_(v)
+                    out.append(None)
+                else:
+                    out.append(v.view(v.shape))
             else:
                 out.append(None)
         return out
@@ -787,6 +860,11 @@ def _wgrad_conv(store: ParamStore, w: torch.nn.Parameter, dy16, x16, taps, shift
         return
     Cout, Cin, k = w.shape
     cp = (Cin + 7) // 8 * 8
+    pv = store.arena_packed_views.get(id(w))
+    if pv is not None:       # the arena slice IS the packed accumulator (zeroed at the start of backward)
+        store.touch(w)
+        R.gemm_wgrad(dy16, x16, pv, M=Cout, N_out=Cin, taps=taps, shift0=shift0, shift_step=1)
+        return
     # a fresh allocation (not a persistent scratch): the caching allocator hands back the block the previous layer just released,
     # so fill -> split-K atomics -> unpack stay L2-resident (measured: a persistent 3 GB scratch made the unpack 6x slower)
     tmp = zeros((k, Cout, cp), F32, w.device)

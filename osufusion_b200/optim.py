@@ -40,8 +40,9 @@ class FusedAdamW(torch.optim.Optimizer):
     this repo in both directions.  Internally the moments live in two flat arenas with the gradient arena's layout."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 max_grad_norm: Optional[float] = 1.0) -> None:
+                 max_grad_norm: Optional[float] = 1.0, emit_operands: bool = True) -> None:
         unet = model.unet if hasattr(model, "unet") else model
+        self.emit_operands = emit_operands
         self.unet = unet
         store = unet._store
         store.ensure_arena(unet)
@@ -65,18 +66,28 @@ class FusedAdamW(torch.optim.Optimizer):
             return hit
         st = self.store
         lib = N.lib()
-        rows, cta = [], 0
+        targets = st.operand_targets(self.unet) if self.emit_operands else {}
+        rows, cta, emitted = [], 0, 0
         for p, (s0, _) in zip(st.arena_params, st.arena_offsets):
             if id(p) in skip:
                 continue
             assert p.is_contiguous() and p.dtype == torch.float32
-            rows.append(N.OptTensor(p.data_ptr(), s0, p.numel(), cta, 0))
-            cta += lib.of_opt_tensor_ctas(p.numel())
+            Cout, Cin, k = st.packed.get(id(p), (0, 0, 1))
+            dst = targets.get(id(p), 0)
+            if k == 1 and p.dim() == 3 and p.shape[2] > 1:
+                dst = 0          # a k > 1 conv whose gradient is NOT packed: its operand layout differs from the parameter's
+            emitted += 1 if dst else 0
+            rows.append(N.OptTensor(p.data_ptr(), s0, p.numel(), dst, cta, Cout, Cin, k))
+            n = lib.of_opt_tensor_ctas2(p.numel(), Cout, Cin, k)
+            assert n > 0
+            cta += n
         if not rows:
-            hit = (None, 0, 0)
+            hit = (None, 0, 0, False)
         else:
             arr = (N.OptTensor * len(rows))(*rows)
-            hit = (torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(st.arena.device), len(rows), cta)
+            # operands are complete only if every weight of the pack plan was refreshed by this table
+            complete = bool(targets) and emitted == len(targets)
+            hit = (torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(st.arena.device), len(rows), cta, complete)
         self._tables[skip] = hit
         return hit
 
@@ -89,6 +100,8 @@ class FusedAdamW(torch.optim.Optimizer):
             self.exp_avg_sq = torch.zeros_like(st.arena)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self._plan_key = (st.arena.data_ptr(), tuple(p.data_ptr() for p in st.arena_params))
+        # the operand buffer moves when the pack plan is rebuilt (adapter injection): tables are rebuilt with it
+        self._pack_buf = st.pack_plan["buf"].data_ptr() if st.pack_plan is not None else 0
 
     @property
     def grad_norm(self) -> torch.Tensor:
@@ -99,7 +112,8 @@ class FusedAdamW(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         st = self.store
-        if self._plan_key != (st.arena.data_ptr(), tuple(p.data_ptr() for p in st.arena_params)):
+        buf = st.pack_plan["buf"].data_ptr() if st.pack_plan is not None else 0
+        if self._plan_key != (st.arena.data_ptr(), tuple(p.data_ptr() for p in st.arena_params)) or buf != self._pack_buf:
             self._build()
         # gradients must be the engine's arena views (they are after a backward pass of the engine); anything else is copied in
         skip = []
@@ -110,7 +124,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 skip.append(id(p))
             elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
-        table, num, ctas = self._table(frozenset(skip))
+        table, num, ctas, complete = self._table(frozenset(skip))
         g = self.param_groups[0]
         self._step += 1
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
@@ -121,11 +135,17 @@ class FusedAdamW(torch.optim.Optimizer):
                    self.exp_avg_sq.data_ptr(), self._sumsq.data_ptr() if clip else None, float(self.max_grad_norm or 0.0), float(g["lr"]),
                    float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self._step)
         st.param_epoch += 1     # parameters changed through raw pointers (torch's _version did not move): invalidate operand caches
+        if complete:
+            st.mark_operands_current()      # ... except the grouped bf16 GEMM operands, which the kernel has just rewritten
         return loss
 
     # ---- checkpoints: torch.optim.AdamW's own state layout
     def _moment_views(self, p):
         (s0, _) = self.store.arena_offsets[self._arena_index[id(p)]]
+        if id(p) in self.store.packed:      # moments share the gradient's GEMM layout [k][Cout][Cin]
+            Cout, Cin, k = self.store.packed[id(p)]
+            return (self.exp_avg[s0:s0 + p.numel()].view(k, Cout, Cin).permute(1, 2, 0),
+                    self.exp_avg_sq[s0:s0 + p.numel()].view(k, Cout, Cin).permute(1, 2, 0))
         return self.exp_avg[s0:s0 + p.numel()].view(p.shape), self.exp_avg_sq[s0:s0 + p.numel()].view(p.shape)
 
     @property

@@ -734,10 +734,15 @@ def of_adamw_step(table, num, total_ctas, grads, exp_avg, exp_avg_sq, sumsq, max
         p = _mem(t.param, t.numel, F32)
         g = _mem(grads + 4 * t.arena_off, t.numel, F32) * clip
         m, v = _mem(exp_avg + 4 * t.arena_off, t.numel, F32), _mem(exp_avg_sq + 4 * t.arena_off, t.numel, F32)
+        if t.k > 1:     # packed conv tensor: gradient / moments / operand [k][Cout][Cin], parameter (Cout, Cin, k)
+            p = p.view(t.Cout, t.Cin, t.k).permute(2, 0, 1)
+            g, m, v = (x.view(t.k, t.Cout, t.Cin) for x in (g, m, v))
         p.mul_(1.0 - lr * wd)
         m.mul_(b1).add_((1.0 - b1) * g)
         v.mul_(b2).add_((1.0 - b2) * g * g)
         p.sub_((lr / bc1) * m / (v.sqrt() / bc2s + eps))
+        if t.operand_bf16:
+            _mem(t.operand_bf16, t.numel, BF16).view(p.shape).copy_(p.to(BF16))
 
 
 _TABLE = {k: v for k, v in globals().items() if k.startswith("of_")}

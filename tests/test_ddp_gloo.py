@@ -43,7 +43,11 @@ def _worker(rank, world, port, out):
             net.grad_sync(op)
         net.grad_finish()
         expect = (1 + step) * sum(r + 1 for r in range(world)) / world
-        grads = st.take_grads(list(net.parameters()))
+        plist = list(net.parameters())
+        for p_ in plist:
+            p_.grad = None
+        # packed conv gradients are assigned to `.grad` by take_grads itself (autograd would re-lay them out); the rest is returned
+        grads = [g if g is not None else p_.grad for g, p_ in zip(st.take_grads(plist), plist)]
         assert all(torch.allclose(g, torch.full_like(g, expect)) for g in grads), (rank, step)
         if step == 1:
             assert red.ready_at is not None and len(red._launched) == len(red.buckets)

@@ -76,8 +76,8 @@ def test_unet_tape_matches_oracle_through_emulated_abi(fake_abi, monkeypatch, in
     assert not bad, bad[:6]
     used = set(fake_abi.CALLS)
     assert {"of_pack_weights", "of_film_fwd", "of_film_bwd", "of_rb_apply_fwd", "of_rb_gate_fwd", "of_rb_bwd_pass1", "of_rb_bwd_apply",
-            "of_rope_fwd", "of_rope_bwd", "of_attn_fwd", "of_attn_bwd", "of_upsample2x_fwd", "of_upsample2x_bwd",
-            "of_unpack_conv_wgrad"} <= used
+            "of_rope_fwd", "of_rope_bwd", "of_attn_fwd", "of_attn_bwd", "of_upsample2x_fwd", "of_upsample2x_bwd"} <= used
+    assert "of_unpack_conv_wgrad" not in used      # conv weight gradients accumulate straight into the packed arena slices
     assert ("of_rb_logit_pool" in used) == fused_gctx and ("of_rb_pool" in used) == (not fused_gctx)
     # second backward without zero_grad accumulates (p.grad aliases the arena after the first one)
     y2 = UNetFunction.apply(new, x, a, t, c, keep, *list(new.parameters()))
@@ -264,10 +264,21 @@ def test_fused_adamw_host_logic_matches_torch(fake_abi, max_norm):
             assert abs(float(opt.grad_norm) - float(tn)) <= 1e-4 * float(tn)
         worst = max(((p - q).abs().max() / q.abs().max().clamp_min(1e-12)).item() for p, q in zip(net.parameters(), ref.parameters()))
         assert worst < 1e-5, (it, worst)
-    # parameters were updated through raw pointers: the operand caches must have been invalidated (param_epoch)
+    # parameters were updated through raw pointers: the operand caches must have been invalidated (param_epoch) ...
     with torch.no_grad():
         out16, _ = net.run(None, x, a, t, c, keep)
-        assert nrel(net.unpack(out16, 48), y0) > 1e-4
+        y3 = net.unpack(out16, 48)
+        assert nrel(y3, y0) > 1e-4
+    # ... while the grouped bf16 GEMM operands were rewritten by the optimizer kernel itself: ONE of_pack_weights launch in total
+    # (the first forward), and the result equals a fresh model that packs the updated weights from scratch
+    assert fake_abi.CALLS.count("of_pack_weights") == 1
+    fresh = UNet(6, 96, 5, **TINY)
+    fresh.load_state_dict(net.state_dict())
+    with torch.no_grad():
+        out16f, _ = fresh.run(None, x, a, t, c, keep)
+    assert nrel(y3, fresh.unpack(out16f, 48)) <= 1e-6
+    assert len(net._store.packed) > 0 and all(net._store.arena_views[i].stride() != net._store.arena_views[i].contiguous().stride()
+                                               for i in net._store.packed)
 
 
 @pytest.mark.parametrize("use_dora", [True, False])
