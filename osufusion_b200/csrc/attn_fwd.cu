@@ -333,6 +333,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 //     layout: S/P[w] = w*64 | O[w] = 128 + w*64
 //   * <= 102 registers: the softmax makes two passes over S in tensor memory (row max; then exp / sum / pack in two 32-column halves)
 //   * 4 K/V stages (96 KB of shared memory per CTA).
+// Tried and dropped (B4 L4096, 322 us for this kernel): three groups in one CTA with a separate P region so that S_w(j+1) overlaps
+// the softmax of tile j (480 TMEM columns, event-driven MMA issue): 413-424 us — a group's tile takes ~2.7 k clk in both layouts
+// (a latency chain of TMEM round trips, row-max / sum chains and barrier hand-offs), so what counts is how many groups share an SM.
 constexpr int kKvStages2 = 4;
 
 template <int kPoly>
