@@ -111,7 +111,8 @@ int of_gemm(const of_gemm_args* args, void* stream);
  *   kv head i % KVH (einops "(r h)" ordering).  D <= 64, D % 8 == 0.  scale <= 0 selects 1/sqrt(D).
  * fwd: out (B, L, H*D) bf16, lse (B, H, L) fp32 = log2-domain log-sum-exp (row max + log2 sum), saved for bwd.
  * bwd: inputs q,k,v,out,dout (bf16), lse; workspace delta (B,H,L) fp32;
- *      dq (B, L, H*D) fp32 and dkv = [dk | dv] (B, L, 2*KVH*D) fp32 are ACCUMULATED atomically: caller zero-fills.
+ *      dq (B, L, H*D) fp32 and dkv = [dk | dv] (B, L, 2*KVH*D) fp32 are ACCUMULATED atomically: the caller zero-fills them, or sets
+ *      zero_grads and the delta pre-pass (one pass over out / dout that every call runs anyway) does it: no fill launches.
  * variant: 0 = default (P operand kept in tensor memory), 1 = P staged through shared memory.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -127,6 +128,7 @@ typedef struct {
   float* delta;                                        /* (B, H, L) workspace */
   float* dq; long long dq_ld, dq_batch_stride;
   float* dk; float* dv; long long dkv_ld, dkv_batch_stride;
+  int zero_grads;                                      /* bwd: != 0 -> the delta pre-pass zero-fills dq / dk / dv itself */
 } of_attn_args;
 
 int of_attn_fwd(const of_attn_args* args, void* stream);

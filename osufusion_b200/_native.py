@@ -50,6 +50,7 @@ class AttnArgs(C.Structure):
         ("delta", P),
         ("dq", P), ("dq_ld", LL), ("dq_batch_stride", LL),
         ("dk", P), ("dv", P), ("dkv_ld", LL), ("dkv_batch_stride", LL),
+        ("zero_grads", I),
     ]
 
 

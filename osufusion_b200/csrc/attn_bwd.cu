@@ -397,29 +397,70 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// delta[b,h,l] = sum_d dO[b,l,h,d] * O[b,l,h,d]
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, long long out_ld, long long out_bs,
-                                  const __nv_bfloat16* __restrict__ dout, long long do_ld, long long do_bs,
-                                  float* __restrict__ delta, int B, int H, int L, int D) {
+// delta[b,h,l] = sum_d dO[b,l,h,d] * O[b,l,h,d]; optionally zero-fills the fp32 gradient accumulators of of_attn_bwd in the same pass
+// (dq: this warp's own (b, l, h) slice; dk / dv rows of kv head h from the warps with h < KVH) so the caller launches no fill kernels.
+// warp = (b, h, 32 consecutive l).  8 lanes x 16 bytes cover one head row (D <= 64): 4 rows per iteration, all 8 iterations' loads
+// are issued before any arithmetic; the 32 row sums are transposed onto the lanes with shuffles so delta leaves as one 128-byte store.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ out, long long out_ld, long long out_bs,
+                  const __nv_bfloat16* __restrict__ dout, long long do_ld, long long do_bs, float* __restrict__ delta,
+                  float* __restrict__ dq, long long dq_ld, long long dq_bs, float* __restrict__ dk, float* __restrict__ dv,
+                  long long dkv_ld, long long dkv_bs, int KVH, int B, int H, int L, int D) {
   pdl_launch_dependents();
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * L * H;
-  if (idx >= total) return;
-  int h = (int)(idx % H);
-  long long r = idx / H;
-  int l = (int)(r % L);
-  int b = (int)(r / L);
-  const __nv_bfloat16* o = out + (long long)b * out_bs + (long long)l * out_ld + (long long)h * D;
-  const __nv_bfloat16* d = dout + (long long)b * do_bs + (long long)l * do_ld + (long long)h * D;
-  float acc = 0.f;
-  for (int c = 0; c < D; c += 8) {
-    uint4 uo = *reinterpret_cast<const uint4*>(o + c);
-    uint4 ud = *reinterpret_cast<const uint4*>(d + c);
-    float2 a0 = unpack_bf16x2(uo.x), a1 = unpack_bf16x2(uo.y), a2 = unpack_bf16x2(uo.z), a3 = unpack_bf16x2(uo.w);
-    float2 b0 = unpack_bf16x2(ud.x), b1 = unpack_bf16x2(ud.y), b2 = unpack_bf16x2(ud.z), b3 = unpack_bf16x2(ud.w);
-    acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+  const int lane = threadIdx.x & 31;
+  const int nlb = (L + 31) >> 5;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)B * H * nlb) return;
+  const int h = (int)(wid % H);
+  const int lb = (int)((wid / H) % nlb);
+  const int b = (int)(wid / ((long long)H * nlb));
+  const int sub = lane >> 3, col = (lane & 7) * 8;
+  const bool col_ok = col < D;
+  uint4 uo[8], ud[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int l = lb * 32 + it * 4 + sub;
+    uo[it] = make_uint4(0, 0, 0, 0);
+    ud[it] = make_uint4(0, 0, 0, 0);
+    if (l < L && col_ok) {
+      uo[it] = *reinterpret_cast<const uint4*>(out + (long long)b * out_bs + (long long)l * out_ld + (long long)h * D + col);
+      ud[it] = *reinterpret_cast<const uint4*>(dout + (long long)b * do_bs + (long long)l * do_ld + (long long)h * D + col);
+    }
   }
-  delta[((long long)b * H + h) * L + l] = acc;
+  if (dq != nullptr) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int l = lb * 32 + it * 4 + sub;
+      if (l < L && col_ok) {
+        float* p = dq + (long long)b * dq_bs + (long long)l * dq_ld + (long long)h * D + col;
+        *reinterpret_cast<float4*>(p) = z;
+        *reinterpret_cast<float4*>(p + 4) = z;
+        if (h < KVH) {
+          float* pk = dk + (long long)b * dkv_bs + (long long)l * dkv_ld + (long long)h * D + col;
+          float* pv = dv + (long long)b * dkv_bs + (long long)l * dkv_ld + (long long)h * D + col;
+          *reinterpret_cast<float4*>(pk) = z;
+          *reinterpret_cast<float4*>(pk + 4) = z;
+          *reinterpret_cast<float4*>(pv) = z;
+          *reinterpret_cast<float4*>(pv + 4) = z;
+        }
+      }
+    }
+  }
+  float mine = 0.f;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const float2 a0 = unpack_bf16x2(uo[it].x), a1 = unpack_bf16x2(uo[it].y), a2 = unpack_bf16x2(uo[it].z), a3 = unpack_bf16x2(uo[it].w);
+    const float2 b0 = unpack_bf16x2(ud[it].x), b1 = unpack_bf16x2(ud[it].y), b2 = unpack_bf16x2(ud[it].z), b3 = unpack_bf16x2(ud[it].w);
+    float acc = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    const float t = __shfl_sync(0xffffffffu, acc, (lane & 3) * 8);     // row it*4 + (lane & 3)
+    if ((lane >> 2) == it) mine = t;
+  }
+  const int l = lb * 32 + lane;
+  if (l < L) delta[((long long)b * H + h) * L + l] = mine;
 }
 
 }  // namespace ofx
@@ -441,13 +482,16 @@ extern "C" int of_attn_bwd(const of_attn_args* a, void* stream_) {
   if ((rc = make_head_tmap(&tdo, a->dout, a->D, a->H, a->L, a->B, a->dout_ld, a->dout_batch_stride, 128)) != OF_OK)
     return rc;
   {
-    long long total = (long long)a->B * a->L * a->H;
-    int threads = 256;
-    long long blocks = (total + threads - 1) / threads;
+    const long long warps = (long long)a->B * a->H * ((a->L + 31) / 32);
+    const int threads = 256;
+    const long long blocks = (warps + 7) / 8;
+    const bool zf = a->zero_grads != 0;
+    if (zf) OF_REQUIRE(a->dq_ld % 4 == 0 && a->dq_batch_stride % 4 == 0 && a->dkv_batch_stride % 4 == 0 && a->D % 8 == 0,
+                       "of_attn_bwd: zero_grads needs 16-byte aligned gradient rows");
     attn_delta_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(a->out), a->out_ld, a->out_batch_stride,
-        reinterpret_cast<const __nv_bfloat16*>(a->dout), a->dout_ld, a->dout_batch_stride, a->delta, a->B, a->H, a->L,
-        a->D);
+        reinterpret_cast<const __nv_bfloat16*>(a->dout), a->dout_ld, a->dout_batch_stride, a->delta, zf ? a->dq : nullptr, a->dq_ld,
+        a->dq_batch_stride, a->dk, a->dv, a->dkv_ld, a->dkv_batch_stride, a->KVH, a->B, a->H, a->L, a->D);
     OF_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }

@@ -157,6 +157,9 @@ class GradAllReducer:
         self._set_reserved(True)
         cur = torch.cuda.current_stream()
         self.comm.wait_stream(cur)
+        side = self.store.side
+        if side is not None and side.active:     # weight gradients of the bucket may still be running on the engine's second stream
+            self.comm.wait_stream(side.stream)
         with torch.cuda.stream(self.comm):
             self._reduce(self.arena[s:e])
 

@@ -28,6 +28,10 @@ LORA_RANK_R = os.environ.get("OF_LORA_RANK_R", "1") != "0"
 LORA_MERGE_TC = os.environ.get("OF_LORA_MERGE_TC", "1") != "0"
 # conv-weight gradients / moments in the GEMM layout [k][Cout][Cin] (no unpack pass, no per-layer scratch fill)
 PACKED_ARENA = os.environ.get("OF_PACKED_ARENA", "1") != "0"
+# weight / bias gradients of backward on a second stream (parallel branches of the captured graph), off the dgrad critical path
+WGRAD_SIDE = os.environ.get("OF_WGRAD_SIDE", "1") != "0"
+# training forward: the audio encoder (independent of x and t) on the second stream, concurrent with the down path
+FWD_SIDE = os.environ.get("OF_FWD_SIDE", "1") != "0"
 
 
 def _p(t):
@@ -65,14 +69,63 @@ class Tape:
     def push(self, fn: Callable[[], None]) -> None:
         self.ops.append(fn)
 
-    def run_backward(self, after_op: Optional[Callable[[int], None]] = None) -> None:
+    def run_backward(self, after_op: Optional[Callable[[int], None]] = None, side: Optional["SideLane"] = None) -> None:
         n = len(self.ops)
         for i in range(n - 1, -1, -1):
             self.ops[i]()
             self.ops[i] = None
+            if side is not None:
+                side.rotate()
             if after_op is not None:
                 after_op(i)
         self.ops.clear()
+
+
+class SideLane:
+    """Second CUDA stream for the part of backward that nothing downstream waits for: weight- and bias-gradient kernels.
+
+    The critical path of backward is the chain dY -> dgrad GEMM -> norm / activation backward -> next dgrad; the weight-gradient
+    GEMMs (half of backward's FLOPs) only feed the gradient arena.  Issued in stream order they sit between the chain's kernels,
+    so every under-filled launch of the chain (65-86 % SM fill at the deep levels, one-CTA-per-sample reductions, the tails of
+    33 us persistent GEMMs) leaves SMs idle.  On a second stream — a parallel branch once the step is captured as a CUDA graph —
+    their CTAs are scheduled into exactly those holes.
+
+    Memory safety without `record_stream` (which would defer every free to the end of a capture): tensors a side kernel reads are
+    kept alive here and released only after the main stream has waited for the side work of that generation; a generation = one
+    tape op (one block's backward), and the main stream may run at most `LAG` generations ahead."""
+    LAG = int(os.environ.get("OF_SIDE_LAG", "2"))
+
+    def __init__(self, device) -> None:
+        self.stream = torch.cuda.Stream(device=device)
+        self.gens: list = []
+        self.cur: list = []
+        self.active = False
+
+    def run(self, fn: Callable[[], None], *keep) -> None:
+        main = torch.cuda.current_stream()
+        self.stream.wait_stream(main)         # everything launched so far (the producers of dY, the saved activations) is visible
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.cur.append(keep)
+        self.active = True
+
+    def rotate(self) -> None:
+        """End of a tape op: close the current generation, make the main stream wait for the one LAG ops back and drop its tensors."""
+        ev = None
+        if self.cur:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.gens.append((ev, self.cur))
+        self.cur = []
+        while len(self.gens) > self.LAG:
+            old, _keep = self.gens.pop(0)
+            if old is not None:
+                torch.cuda.current_stream().wait_event(old)
+
+    def join(self) -> None:
+        if self.active:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.gens, self.cur, self.active = [], [], False
 
 
 # ------------------------------------------------------------------------------------------------ raw helpers
@@ -310,6 +363,7 @@ class ParamStore:
         self._film_heads = None
         self._n_adapters = None
         self.film_plans = {}
+        self.side: Optional[SideLane] = None     # second stream of the current backward pass (weight / bias gradients), or None
         # set by ddp.GradAllReducer
         self.on_backward_begin = None
         self.on_touch = None
@@ -863,7 +917,7 @@ def _wgrad_conv(store: ParamStore, w: torch.nn.Parameter, dy16, x16, taps, shift
     pv = store.arena_packed_views.get(id(w))
     if pv is not None:       # the arena slice IS the packed accumulator (zeroed at the start of backward)
         store.touch(w)
-        R.gemm_wgrad(dy16, x16, pv, M=Cout, N_out=Cin, taps=taps, shift0=shift0, shift_step=1)
+        _off_path(store, lambda: R.gemm_wgrad(dy16, x16, pv, M=Cout, N_out=Cin, taps=taps, shift0=shift0, shift_step=1), dy16, x16)
         return
     # a fresh allocation (not a persistent scratch): the caching allocator hands back the block the previous layer just released,
     # so fill -> split-K atomics -> unpack stay L2-resident (measured: a persistent 3 GB scratch made the unpack 6x slower)
@@ -881,12 +935,21 @@ def _wgrad_linear(store: ParamStore, w: torch.nn.Parameter, dy16, x16, row0: int
     g = store.grad(w)
     Nn = w.shape[0] if rows is None else rows
     K = w.shape[1]
-    R.gemm_wgrad(dy16, x16, g.view(1, w.shape[0], K)[:, row0:row0 + Nn], M=Nn, N_out=K)
+    _off_path(store, lambda: R.gemm_wgrad(dy16, x16, g.view(1, w.shape[0], K)[:, row0:row0 + Nn], M=Nn, N_out=K), dy16, x16)
 
 
 def _bias_grad(store: ParamStore, b: Optional[torch.nn.Parameter], dy16) -> None:
     if b is not None and b.requires_grad:
-        colsum(dy16, store.grad(b))
+        g = store.grad(b)
+        _off_path(store, lambda: colsum(dy16, g), dy16)
+
+
+def _off_path(store: ParamStore, fn: Callable[[], None], *keep) -> None:
+    """Run a weight- / bias-gradient launch off the critical path (SideLane) when the backward pass has a second stream."""
+    if store.side is not None:
+        store.side.run(fn, *keep)
+    else:
+        fn()
 
 
 def _dgrad_into(x: Act, dy16, wpack, *, N_out, K, taps=1, shift0=0, shift_step=0, b_ld=None, want_bf16=False,
@@ -1079,7 +1142,7 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
             b1.dxhat_bf16 = dxh1.data_ptr()
             b1.dxhat_bs, b1.dxhat_ld = _bl(dxh1)
             N.call("of_rb_bwd_pass1", C.byref(b1))
-            dy1 = dy2  # reuse
+            dy1 = dy2 if st.side is None else empty((B, L, Cout), BF16, dev)   # conv2's weight gradient may still be reading dy2
             b1.dy_bf16 = dy1.data_ptr()
             b1.dy_bs, b1.dy_ld = _bl(dy1)
             b1.dbias = _p(st.grad_opt(_base(m.block1.proj).bias))
@@ -1182,9 +1245,9 @@ def transformer_block(ctx: Ctx, m, x: Act) -> Act:
             _bias_grad(st, at.to_out.bias, dx2_16)
             # attention core
             delta = empty((B, H, L), F32, dev)
-            dq = zeros((B, L, HD), F32, dev)
-            dkv = zeros((B, L, 2 * KD), F32, dev)
-            R.attn_bwd(q, k, v, o16, lse, dO, delta, dq, dkv[:, :, :KD], dkv[:, :, KD:], H=H, KVH=KVH, D=D)
+            dq = empty((B, L, HD), F32, dev)         # zero-filled by the delta pre-pass of of_attn_bwd
+            dkv = empty((B, L, 2 * KD), F32, dev)
+            R.attn_bwd(q, k, v, o16, lse, dO, delta, dq, dkv[:, :, :KD], dkv[:, :, KD:], H=H, KVH=KVH, D=D, zero_grads=True)
             dqkv = empty((B, L, HD + 2 * KD), BF16, dev)
             dq_bs, dq_ld = _bl(dq)
             dkv_bs, dkv_ld = _bl(dkv)

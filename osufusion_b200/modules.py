@@ -221,6 +221,7 @@ class UNet(nn.Module):
         self.attn_variant = 0
         self.grad_sync = None    # set by osufusion_b200.ddp.GradAllReducer: called after every backward tape op
         self.grad_finish = None  # ... and once at the end of backward (launch remaining buckets, join the comm stream)
+        self._side_stream = None # second stream of backward (weight / bias gradients), created on first use
 
     # ------------------------------------------------------------------ reference API
     def set_gradient_checkpointing(self, value: bool) -> None:
@@ -354,6 +355,12 @@ class UNet(nn.Module):
         down block — not the 26 % audio encoder — is the un-overlappable tail of the gradient all-reduce."""
         st, dev = ctx.store, ctx.device
         self.conditioning(ctx, t, c, keep)
+        # the audio encoder and the down path are independent until `middle_resnet1`: the training step runs the encoder on the
+        # second stream (a parallel branch of the captured graph), so each branch fills the other's under-filled launches
+        fork = None
+        if callable(a_feat) and ctx.tape is not None and E.FWD_SIDE and dev.type == "cuda":
+            fork = torch.cuda.Event()
+            fork.record()
         x = E.cross_embed(ctx, self.init_x, x16)
         r = x
         skips = []
@@ -361,7 +368,25 @@ class UNet(nn.Module):
             self._film_unit(ctx, [layer])
             x, s = E.unet_block(ctx, layer, x)
             skips.append(s)
-        if callable(a_feat):
+        if callable(a_feat) and fork is not None:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=dev)
+            side = self._side_stream
+            side.wait_event(fork)
+            main_pool, main_rope = ctx.zpool, ctx.rope_cache
+            side_pool = E.ZeroPool(dev)
+            try:
+                with torch.cuda.stream(side):
+                    # scratch chunks are zero-filled on the stream that creates them and the RoPE tables are generated lazily: the
+                    # branch gets its own so that it never reads what the main stream produced after the fork
+                    ctx.zpool, ctx.rope_cache = side_pool, {}
+                    E.use_pool(side_pool)
+                    a_feat = a_feat()
+            finally:
+                ctx.zpool, ctx.rope_cache = main_pool, main_rope
+                E.use_pool(main_pool)
+            torch.cuda.current_stream().wait_stream(side)
+        elif callable(a_feat):
             a_feat = a_feat()
         self._film_unit(ctx, [self.middle_resnet1, self.middle_resnet2])
         x = E.concat(ctx, x, a_feat)
@@ -414,12 +439,23 @@ class UNet(nn.Module):
         st = ctx.store
         E.use_pool(ctx.zpool)
         st.begin_backward(self, film_overwritten=ctx.film_dss is not None)
-        if self.grad_sync is not None:
-            self.grad_sync(len(ctx.tape.ops) + 1)
-        self.final_backward(ctx, xf, dY16)
-        ctx.tape.run_backward(self.grad_sync)
-        if self.grad_finish is not None:
-            self.grad_finish()
+        # weight / bias gradients go to a second stream (engine.SideLane): parallel branches of the captured step
+        st.side = E.SideLane(ctx.device) if (E.WGRAD_SIDE and ctx.device.type == "cuda") else None
+        if st.side is not None and self._side_stream is not None:
+            st.side.stream = self._side_stream        # one stream per model, not one per step
+        elif st.side is not None:
+            self._side_stream = st.side.stream
+        try:
+            if self.grad_sync is not None:
+                self.grad_sync(len(ctx.tape.ops) + 1)
+            self.final_backward(ctx, xf, dY16)
+            ctx.tape.run_backward(self.grad_sync, st.side)
+            if self.grad_finish is not None:
+                self.grad_finish()
+        finally:
+            if st.side is not None:
+                st.side.join()
+            st.side = None
         return st.take_grads(params)
 
 

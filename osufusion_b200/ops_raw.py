@@ -116,8 +116,10 @@ def attn_fwd(q, k, v, out, lse, *, H, KVH, D, variant=0):
     N.call("of_attn_fwd", C.byref(g), flops=4.0 * g.B * H * g.L * g.L * D, family="attn_fwd_kernel (tcgen05 MQA flash)")
 
 
-def attn_bwd(q, k, v, out, lse, dout, delta, dq, dk, dv, *, H, KVH, D, variant=0):
+def attn_bwd(q, k, v, out, lse, dout, delta, dq, dk, dv, *, H, KVH, D, variant=0, zero_grads=False):
+    """dq / dk / dv are accumulated into; zero_grads=True makes the delta pre-pass zero-fill them (uninitialised buffers are fine)."""
     g = _attn_common(q, k, v, H, KVH, D, variant)
+    g.zero_grads = int(zero_grads)
     g.out = out.data_ptr()
     g.out_batch_stride, g.out_ld = _bl(out)
     g.lse = lse.data_ptr()

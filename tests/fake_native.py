@@ -142,6 +142,10 @@ def of_attn_bwd(g):
     ds = p * (dp - (dp * p).sum(-1, keepdim=True)) / math.sqrt(D)
     dq = ds @ k
     dk = ds.transpose(-1, -2) @ q
+    if g.zero_grads:
+        v3(g.dq, F32, B, L, H * D, g.dq_batch_stride, g.dq_ld).zero_()
+        v3(g.dk, F32, B, L, KVH * D, g.dkv_batch_stride, g.dkv_ld).zero_()
+        v3(g.dv, F32, B, L, KVH * D, g.dkv_batch_stride, g.dkv_ld).zero_()
     v3(g.dq, F32, B, L, H * D, g.dq_batch_stride, g.dq_ld).add_(dq.transpose(1, 2).reshape(B, L, H * D))
     dkk = torch.zeros(B, KVH, L, D)
     dvv = torch.zeros(B, KVH, L, D)

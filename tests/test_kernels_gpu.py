@@ -113,8 +113,9 @@ def test_attention_forward(B, L, H, KVH, D, qs, variant):
     assert rel(lse, lse_ref) < 1e-4
 
 
+@pytest.mark.parametrize("zero_grads", [False, True])     # True: the delta pre-pass zero-fills dq / dk / dv (buffers start as garbage)
 @pytest.mark.parametrize("B,L,H,KVH,D", [(1, 128, 1, 1, 64), (2, 1024, 16, 1, 64), (2, 200, 2, 1, 16), (1, 72, 4, 2, 32)])
-def test_attention_backward(B, L, H, KVH, D):
+def test_attention_backward(B, L, H, KVH, D, zero_grads):
     from osufusion_b200 import ops_raw as R
     torch.manual_seed(5)
     qkv = torch.randn(B, L, (H + 2 * KVH) * D, device=dev).bfloat16()
@@ -124,9 +125,10 @@ def test_attention_backward(B, L, H, KVH, D):
     R.attn_fwd(q, k, v, out, lse, H=H, KVH=KVH, D=D)
     dout = torch.randn(B, L, H * D, device=dev).bfloat16()
     delta = torch.zeros(B, H, L, device=dev)
-    dq = torch.zeros(B, L, H * D, device=dev)
-    dkv = torch.zeros(B, L, 2 * KVH * D, device=dev)
-    R.attn_bwd(q, k, v, out, lse, dout, delta, dq, dkv[:, :, :KVH * D], dkv[:, :, KVH * D:], H=H, KVH=KVH, D=D)
+    fill = 7.5 if zero_grads else 0.0
+    dq = torch.full((B, L, H * D), fill, device=dev)
+    dkv = torch.full((B, L, 2 * KVH * D), fill, device=dev)
+    R.attn_bwd(q, k, v, out, lse, dout, delta, dq, dkv[:, :, :KVH * D], dkv[:, :, KVH * D:], H=H, KVH=KVH, D=D, zero_grads=zero_grads)
     qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
     o_ref, _ = ref_attn(qf, kf, vf, H, KVH, D)
     o_ref.backward(dout.float())
