@@ -308,6 +308,24 @@ int of_dora_rankr_finish(const float* dBraw, const float* rowscale, float* gB, c
 int of_dora_scale_pack(const float* V, const float* mag, int Cout, int Cin, int k, float* n2_out, void* packed_bf16, int cin_pad,
                        long long tap_stride, void* stream);
 int of_scale_cast_f32_bf16(const float* src, float scale, void* dst, long long n, void* stream);
+/* of_dora_scale_pack + of_dora_rankr_prep in one launch (the CTA that owns output channel co knows s[co]): additionally writes
+ *   rowscale[co] = scaling * s[co]  and  Bst[j][co] = bf16(rowscale[co] * B[co][j])  for the rank-r backward. */
+int of_dora_scale_pack_prep(const float* V, const float* mag, int Cout, int Cin, int k, float* n2_out, void* packed_bf16, int cin_pad,
+                            long long tap_stride, const float* B, float scaling, int r, void* Bst_bf16, float* rowscale, void* stream);
+/* of_dora_rankr_finish for every adapted layer of the model in ONE launch at the end of backward (table in device memory; layer i
+ * owns CTAs [cta_begin_i, cta_begin_{i+1}) of 256 threads, one thread per element of B). */
+typedef struct {
+  const float* dBraw;     /* (Cout, r) fp32 = dy^T u accumulated by the weight-gradient GEMM */
+  const float* rowscale;  /* (Cout) */
+  float* gB;              /* (Cout, r) gradient of lora_B (accumulated into) */
+  const float* dm;        /* (Cout) sum_l dy (y - b), or NULL without magnitude */
+  const float* mag;       /* (Cout) or NULL */
+  float* gmag;            /* (Cout) gradient of the magnitude vector (accumulated into) or NULL */
+  int Cout, r;
+  int cta_begin;
+  int _pad;
+} of_lora_finish_seg;
+int of_lora_finish_all(const of_lora_finish_seg* segs_dev, int num_segs, int total_ctas, void* stream);
 int of_dora_grad(const float* W, const float* A, const float* B, const float* mag, float scaling, int Cout, int Cin, int k, int r,
                  const float* n2, const float* dW_packed, int Cin_pad, long long tap_stride, float* dA, float* dB, float* dmag,
                  void* stream);
@@ -340,7 +358,7 @@ typedef struct {
   void* dst;
   int Cout, Cin, k, cin_pad;
   int cta_begin;
-  int _pad;
+  float scale;         /* dst = bf16(scale * src); 0 means 1 (plain cast) */
 } of_pack_seg;
 
 int of_film_fwd(const of_film_group* groups_dev, int num_groups, int total_rows, const float* x, int M, int K, float* out,

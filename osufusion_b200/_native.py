@@ -82,7 +82,11 @@ class FilmGroup(C.Structure):
 
 
 class PackSeg(C.Structure):
-    _fields_ = [("src", P), ("dst", P), ("Cout", I), ("Cin", I), ("k", I), ("cin_pad", I), ("cta_begin", I), ("_pad", I)]
+    _fields_ = [("src", P), ("dst", P), ("Cout", I), ("Cin", I), ("k", I), ("cin_pad", I), ("cta_begin", I), ("scale", F)]
+
+
+class LoraFinishSeg(C.Structure):
+    _fields_ = [("dBraw", P), ("rowscale", P), ("gB", P), ("dm", P), ("mag", P), ("gmag", P), ("Cout", I), ("r", I), ("cta_begin", I), ("_pad", I)]
 
 
 class OptTensor(C.Structure):
@@ -135,6 +139,8 @@ _SIGS = {
     "of_dora_rankr_finish": [P, P, P, P, P, P, I, I, P],
     "of_dora_scale_pack": [P, P, I, I, I, P, P, I, LL, P],
     "of_scale_cast_f32_bf16": [P, F, P, LL, P],
+    "of_dora_scale_pack_prep": [P, P, I, I, I, P, P, I, LL, P, F, I, P, P, P],
+    "of_lora_finish_all": [P, I, I, P],
     "of_dora_merge": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P],
     "of_dora_grad": [P, P, P, P, F, I, I, I, I, P, P, I, LL, P, P, P, P],
     "of_gate_residual_fwd": [P, P, LL, LL, P, LL, LL, P, LL, I, I, I, I, P, LL, LL, P],

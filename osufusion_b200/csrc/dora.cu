@@ -297,7 +297,9 @@ __global__ void dora_rankr_finish_kernel(const float* __restrict__ dBraw, const 
 constexpr int kScalePackMaxPerThread = 32;
 __global__ void __launch_bounds__(256) dora_scale_pack_kernel(const float* __restrict__ V, const float* __restrict__ mag, int Cin, int k,
                                                               float* __restrict__ n2_out, __nv_bfloat16* __restrict__ packed,
-                                                              int cin_pad, long long tap_stride) {
+                                                              int cin_pad, long long tap_stride, const float* __restrict__ B,
+                                                              float scaling, int r, __nv_bfloat16* __restrict__ Bst,
+                                                              float* __restrict__ rowscale) {
   __shared__ float sm[32];
   const int co = blockIdx.x;
   const int E = Cin * k;
@@ -313,6 +315,11 @@ __global__ void __launch_bounds__(256) dora_scale_pack_kernel(const float* __res
   sq = block_sum(sq, sm);
   if (threadIdx.x == 0 && n2_out) n2_out[co] = sq;
   const float s = mag ? mag[co] * rsqrtf(sq) : 1.0f;
+  if (rowscale) {      // operands of the rank-r backward (what of_dora_rankr_prep produces)
+    const float rs = scaling * s;
+    if (threadIdx.x == 0) rowscale[co] = rs;
+    for (int j = threadIdx.x; j < r; j += blockDim.x) Bst[(long long)j * gridDim.x + co] = __float2bfloat16_rn(rs * B[(long long)co * r + j]);
+  }
 #pragma unroll
   for (int i = 0; i < kScalePackMaxPerThread; ++i) {
     const int e = i * 256 + threadIdx.x;
@@ -321,6 +328,23 @@ __global__ void __launch_bounds__(256) dora_scale_pack_kernel(const float* __res
       packed[(long long)t * tap_stride + (long long)co * cin_pad + ci] = __float2bfloat16_rn(s * v[i]);
     }
   }
+}
+
+// every adapted layer's of_dora_rankr_finish in one launch
+__global__ void __launch_bounds__(256) lora_finish_all_kernel(const of_lora_finish_seg* __restrict__ segs, int num_segs) {
+  int lo = 0, hi = num_segs - 1;
+  const int cta = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].cta_begin <= cta) lo = mid;
+    else hi = mid - 1;
+  }
+  const of_lora_finish_seg sg = segs[lo];
+  const int idx = (cta - sg.cta_begin) * 256 + threadIdx.x;
+  if (idx >= sg.Cout * sg.r) return;
+  const int co = idx / sg.r, j = idx - co * sg.r;
+  sg.gB[idx] += sg.rowscale[co] * sg.dBraw[idx];
+  if (j == 0 && sg.mag && sg.gmag) sg.gmag[co] += sg.dm[co] / sg.mag[co];
 }
 // dst = bf16(scale * src)
 __global__ void scale_cast_bf16_kernel(const float* __restrict__ src, float scale, __nv_bfloat16* __restrict__ dst, long long n) {
@@ -429,7 +453,30 @@ extern "C" int of_dora_scale_pack(const float* V, const float* mag, int Cout, in
   OF_REQUIRE(V && packed_bf16 && Cout >= 1 && Cin >= 1 && k >= 1 && cin_pad >= Cin, "of_dora_scale_pack: bad args");
   OF_REQUIRE((long long)Cin * k <= 256LL * kScalePackMaxPerThread, "of_dora_scale_pack: row of %d x %d elements is too long", Cin, k);
   dora_scale_pack_kernel<<<Cout, 256, 0, stream>>>(V, mag, Cin, k, n2_out, reinterpret_cast<__nv_bfloat16*>(packed_bf16), cin_pad,
-                                                    tap_stride);
+                                                    tap_stride, nullptr, 0.f, 0, nullptr, nullptr);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
+
+extern "C" int of_dora_scale_pack_prep(const float* V, const float* mag, int Cout, int Cin, int k, float* n2_out, void* packed_bf16,
+                                       int cin_pad, long long tap_stride, const float* B, float scaling, int r, void* Bst_bf16,
+                                       float* rowscale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(V && packed_bf16 && Cout >= 1 && Cin >= 1 && k >= 1 && cin_pad >= Cin, "of_dora_scale_pack_prep: bad args");
+  OF_REQUIRE(B && Bst_bf16 && rowscale && r >= 1, "of_dora_scale_pack_prep: null rank-r operand");
+  OF_REQUIRE((long long)Cin * k <= 256LL * kScalePackMaxPerThread, "of_dora_scale_pack_prep: row of %d x %d elements is too long", Cin, k);
+  dora_scale_pack_kernel<<<Cout, 256, 0, stream>>>(V, mag, Cin, k, n2_out, reinterpret_cast<__nv_bfloat16*>(packed_bf16), cin_pad,
+                                                    tap_stride, B, scaling, r, reinterpret_cast<__nv_bfloat16*>(Bst_bf16), rowscale);
+  OF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OF_OK;
+}
+
+extern "C" int of_lora_finish_all(const of_lora_finish_seg* segs_dev, int num_segs, int total_ctas, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  OF_REQUIRE(segs_dev && num_segs >= 1 && total_ctas >= 1, "of_lora_finish_all: bad args");
+  lora_finish_all_kernel<<<total_ctas, 256, 0, stream>>>(segs_dev, num_segs);
   OF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OF_OK;

@@ -660,10 +660,28 @@ extern "C" int of_gemm(const of_gemm_args* a, void* stream_) {
     else if (a->N > 64) BN = 128;
     else if (a->N > 32) BN = 64;
     else BN = b_mn ? 64 : 32;
-    // prefer more tiles when the grid would be badly under-filled
+    // Tile width by a small cost model: rounds of the persistent grid x time of one tile.  A CTA pair owns one 256-row tile, so a
+    // paired launch has sm/2 slots.  Per FLOP a narrower tile needs more operand bytes from L2 (A is re-read per N tile: 24 KB per
+    // k-step at BN=128 against 32 KB for twice the work at BN=256), hence the penalties; ties go to the wider tile.
     if (!wgrad && BN == 256) {
-      long long tiles256 = (long long)a->batch * ceil_div(a->rows, kBM) * ceil_div(a->N, 256);
-      if (tiles256 < device_sm_count()) BN = 128;
+      const int mt = ceil_div(a->rows, kBM);
+      const bool pair = mt >= 2;
+      const long long rows_units = (long long)a->batch * (pair ? ceil_div(mt, 2) : mt);
+      const int slots = pair ? device_sm_count() / 2 : device_sm_count();
+      static const int legacy = [] { const char* e = getenv("OF_GEMM_BN_LEGACY"); return e ? atoi(e) : 0; }();
+      if (legacy) {
+        long long tiles256 = (long long)a->batch * mt * ceil_div(a->N, 256);
+        if (tiles256 < device_sm_count()) BN = 128;
+      } else {
+        auto rounds = [&](int bn) { return (double)((rows_units * ceil_div(a->N, bn) + slots - 1) / slots); };
+        double best = rounds(256) * 2.0;
+        const double c128 = rounds(128) * 1.15;
+        if (c128 < best) best = c128, BN = 128;
+        if (!b_mn) {                                   // MN-major B pairs need an even number of 64-column swizzle atoms
+          const double c192 = rounds(192) * 1.55;
+          if (c192 < best) best = c192, BN = 192;
+        }
+      }
     }
   }
   OF_REQUIRE(BN % 32 == 0 && BN >= 32 && BN <= 256, "of_gemm: block_n=%d invalid", BN);

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const of_pack_seg* __
   }
   const of_pack_seg sg = segs[lo];
   const int item = cta - sg.cta_begin;
+  const float sc = sg.scale != 0.f ? sg.scale : 1.0f;      // 0 = plain cast (x * 1.0f is exact, so one code path serves both)
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sg.dst);
   if (sg.k == 1 && sg.cin_pad == sg.Cin) {
     const long long n = (long long)sg.Cout * sg.Cin;
@@ -170,10 +171,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const of_pack_seg* __
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const long long e = base + (i * 256 + threadIdx.x) * 4;
-        if (e < n) *reinterpret_cast<uint2*>(dst + e) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+        if (e < n) *reinterpret_cast<uint2*>(dst + e) = make_uint2(pack_bf16x2(sc * v[i].x, sc * v[i].y), pack_bf16x2(sc * v[i].z, sc * v[i].w));
       }
     } else {
-      for (long long e = base + threadIdx.x; e < min(base + kPackFlat, n); e += 256) dst[e] = __float2bfloat16_rn(sg.src[e]);
+      for (long long e = base + threadIdx.x; e < min(base + kPackFlat, n); e += 256) dst[e] = __float2bfloat16_rn(sc * sg.src[e]);
     }
     return;
   }
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const of_pack_seg* __
   __syncthreads();
   for (int i = threadIdx.x; i < nci * k; i += blockDim.x) {
     const int t = i / nci, ci = i - t * nci;
-    const float v = ci < nreal ? s_w[ci * k + t] : 0.f;
+    const float v = ci < nreal ? sc * s_w[ci * k + t] : 0.f;
     dst[((long long)t * sg.Cout + co) * sg.cin_pad + ci0 + ci] = __float2bfloat16_rn(v);
   }
 }

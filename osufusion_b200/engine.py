@@ -26,6 +26,10 @@ GCTX_FUSED = os.environ.get("OF_GCTX_FUSED", "1") != "0"
 LORA_RANK_R = os.environ.get("OF_LORA_RANK_R", "1") != "0"
 # effective-weight merge W + scaling*B*A as a K = r tensor-core GEMM (+ a row-wise norm/scale/pack kernel) vs the CUDA-core kernel
 LORA_MERGE_TC = os.environ.get("OF_LORA_MERGE_TC", "1") != "0"
+# adapter-side operands of ALL adapted layers from one grouped launch per step, rank-r glue folded into the merge kernel, one grouped
+# finishing launch at the end of backward, lora_A conv gradients accumulated in the GEMM layout (no per-layer cast / pack / prep /
+# unpack / finish launches)
+LORA_GROUPED = os.environ.get("OF_LORA_GROUPED", "1") != "0"
 # conv-weight gradients / moments in the GEMM layout [k][Cout][Cin] (no unpack pass, no per-layer scratch fill)
 PACKED_ARENA = os.environ.get("OF_PACKED_ARENA", "1") != "0"
 # weight / bias gradients of backward on a second stream (parallel branches of the captured graph), off the dgrad critical path
@@ -226,6 +230,15 @@ def _adapter(m):
     return m if hasattr(m, "base_layer") else None
 
 
+def _lora_fast(ad) -> bool:
+    """Adapted layer handled by the grouped LoRA / DoRA path (ParamStore.refresh_lora): tensor-core merge + rank-r backward."""
+    W = ad.base_layer.weight
+    Cin = W.shape[1]
+    k = W.shape[2] if W.dim() == 3 else 1
+    return (LORA_GROUPED and LORA_RANK_R and LORA_MERGE_TC and ad.r % 8 == 0 and Cin % 8 == 0 and Cin * k <= 8192 and k <= 4
+            and W.is_contiguous() and ad.lora_A["default"].weight.requires_grad)
+
+
 # ------------------------------------------------------------------------------------------------ parameter staging
 def backward_param_order(unet) -> List[torch.nn.Parameter]:
     """Parameters in the order their gradients become final during the engine's backward pass (see backward_param_plan)."""
@@ -240,7 +253,11 @@ def packed_conv_params(unet):
     out = {}
 
     def add(conv):
-        if _adapter(conv) is not None:
+        ad = _adapter(conv)
+        if ad is not None:
+            A = ad.lora_A["default"].weight      # (r, Cin, k): its rank-r weight gradient lands in [k][r][Cin] as well
+            if _lora_fast(ad) and A.dim() == 3 and A.shape[2] > 1:
+                out[id(A)] = tuple(A.shape)
             return
         w = conv.weight
         Cout, Cin, k = w.shape
@@ -360,6 +377,7 @@ class ParamStore:
         self.touched = set()
         self.param_epoch = 0         # bumped by optimizers that update parameters through raw pointers (osufusion_b200/optim.py)
         self.pack_plan = None
+        self.lora_plan = None
         self._film_heads = None
         self._n_adapters = None
         self.film_plans = {}
@@ -435,6 +453,9 @@ class ParamStore:
         else:
             self.arena.zero_()
         self.touched = set()
+        if self.lora_plan is not None:
+            self.lora_plan["acc32"].zero_()      # dB_raw / d magnitude accumulators of every adapted layer: one memset
+            self.lora_plan["pending"] = False
         if self.on_backward_begin is not None:
             self.on_backward_begin()
 
@@ -552,6 +573,121 @@ class ParamStore:
             plan["vers"] = vers
         for key, params, view in plan["views"]:
             self.cache[key] = (tuple((p.data_ptr(), p._version) for p in params) + (self.param_epoch,), view, self.epoch)
+        self.refresh_lora(unet, n_adapters)
+
+    # ---- grouped LoRA / DoRA operands
+    def refresh_lora(self, unet, n_adapters: int) -> None:
+        """bf16 operands of every adapted layer's adapter side — A as the merge GEMM's operand (r, Cin*k), A in the conv layout
+        [k][r][Cin] for u = conv(x, A), scaling * B — written by ONE grouped launch (of_pack_weights) whenever an adapter tensor
+        changed; plus persistent per-layer buffers for what the merge kernel leaves for backward (n2, rowscale, (scaling s B)^T) and
+        the accumulators backward fills (dB_raw, d magnitude)."""
+        if n_adapters == 0 or not LORA_GROUPED:
+            self.lora_plan = None
+            return
+        ads = [m for m in unet.modules() if hasattr(m, "base_layer") and _lora_fast(m)]
+        if not ads:
+            self.lora_plan = None
+            return
+        plan = self.lora_plan
+        ptrs = tuple(t.data_ptr() for ad in ads for t in (ad.lora_A["default"].weight, ad.lora_B["default"].weight))
+        if plan is None or plan["ptrs"] != ptrs:
+            plan = self.lora_plan = self._build_lora_plan(ads, ptrs)
+        vers = tuple(t._version for ad in ads for t in (ad.lora_A["default"].weight, ad.lora_B["default"].weight)) + (self.param_epoch,)
+        if vers != plan["vers"]:
+            N.call("of_pack_weights", plan["table"].data_ptr(), plan["num_segs"], plan["ctas"])
+            plan["vers"] = vers
+
+    def _build_lora_plan(self, ads, ptrs):
+        lib = N.lib()
+        dev = ads[0].base_layer.weight.device
+        al = lambda n: (n + 127) // 128 * 128
+        n16 = n32 = nacc = 0
+        lay = []
+        for ad in ads:
+            W = ad.base_layer.weight
+            Cout, Cin = W.shape[0], W.shape[1]
+            k = W.shape[2] if W.dim() == 3 else 1
+            r, E = ad.r, Cin * k
+            o = {"A16": n16}
+            n16 += al(r * E)
+            if k > 1:
+                o["Apk"] = n16
+                n16 += al(r * E)
+            o["B16s"] = n16
+            n16 += al(Cout * r)
+            o["Bst"] = n16
+            n16 += al(Cout * r)
+            o["n2"], o["rowscale"] = n32, n32 + al(Cout)
+            n32 += 2 * al(Cout)
+            o["dBraw"], o["dm"] = nacc, nacc + al(Cout * r)
+            nacc += al(Cout * r) + al(Cout)
+            lay.append((ad, Cout, Cin, k, r, E, o))
+        buf16 = torch.zeros(n16, dtype=BF16, device=dev)
+        buf32 = torch.zeros(n32, dtype=F32, device=dev)
+        acc32 = torch.zeros(nacc, dtype=F32, device=dev)
+        segs, cta, entries = [], 0, {}
+
+        def seg(src, dst_off, Cout, Cin, k, cp, scale):
+            nonlocal cta
+            n = lib.of_pack_seg_ctas(Cout, Cin, k, cp)
+            assert n > 0
+            segs.append(N.PackSeg(src.data_ptr(), buf16.data_ptr() + 2 * dst_off, Cout, Cin, k, cp, cta, scale))
+            cta += n
+
+        for ad, Cout, Cin, k, r, E, o in lay:
+            A, Bm = ad.lora_A["default"].weight, ad.lora_B["default"].weight
+            seg(A, o["A16"], r, E, 1, E, 0.0)
+            if k > 1:
+                seg(A, o["Apk"], r, Cin, k, Cin, 0.0)
+            seg(Bm, o["B16s"], Cout, r, 1, r, float(ad.scaling))
+            A16 = buf16[o["A16"]:o["A16"] + r * E].view(r, E)
+            entries[id(ad)] = {
+                "A16": A16, "Apk": buf16[o["Apk"]:o["Apk"] + r * E].view(k, r, Cin) if k > 1 else A16.view(1, r, Cin),
+                "B16s": buf16[o["B16s"]:o["B16s"] + Cout * r].view(Cout, r), "Bst": buf16[o["Bst"]:o["Bst"] + Cout * r].view(r, Cout),
+                "n2": buf32[o["n2"]:o["n2"] + Cout], "rowscale": buf32[o["rowscale"]:o["rowscale"] + Cout],
+                "dBraw": acc32[o["dBraw"]:o["dBraw"] + Cout * r].view(1, Cout, r), "dm": acc32[o["dm"]:o["dm"] + Cout],
+            }
+        arr = (N.PackSeg * len(segs))(*segs)
+        return {"ptrs": ptrs, "vers": None, "table": torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev),
+                "num_segs": len(segs), "ctas": cta, "buf16": buf16, "buf32": buf32, "acc32": acc32, "entries": entries, "ads": ads,
+                "finish": None, "pending": False}
+
+    def lora_entry(self, ad):
+        plan = self.lora_plan
+        return None if plan is None else plan["entries"].get(id(ad))
+
+    def lora_finish(self) -> None:
+        """End of backward: gB += rowscale * dB_raw and g_mag += dm / mag for EVERY adapted layer in one launch."""
+        plan = self.lora_plan
+        if plan is None or not plan["pending"]:
+            return
+        plan["pending"] = False
+        fin = plan["finish"]
+        key = self.arena.data_ptr() if self.arena is not None else 0
+        if fin is None or fin["key"] != key:
+            segs, cta = [], 0
+            for ad in plan["ads"]:
+                e = plan["entries"][id(ad)]
+                Bm, mag = ad.lora_B["default"].weight, ad.magnitude()
+                if not Bm.requires_grad:
+                    continue
+                Cout, r = Bm.shape[0], ad.r
+                has_mag = mag is not None and mag.requires_grad
+                segs.append(N.LoraFinishSeg(e["dBraw"].data_ptr(), e["rowscale"].data_ptr(), self.arena_views[id(Bm)].data_ptr(),
+                                            e["dm"].data_ptr() if has_mag else 0, mag.data_ptr() if has_mag else 0,
+                                            self.arena_views[id(mag)].data_ptr() if has_mag else 0, Cout, r, cta, 0))
+                cta += (Cout * r + 255) // 256
+            arr = (N.LoraFinishSeg * len(segs))(*segs)
+            fin = plan["finish"] = {"key": key, "num": len(segs), "ctas": cta,
+                                    "table": torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.arena.device)}
+        for ad in plan["ads"]:
+            Bm, mag = ad.lora_B["default"].weight, ad.magnitude()
+            if Bm.requires_grad:
+                self.touch(Bm)
+            if mag is not None and mag.requires_grad:
+                self.touch(mag)
+        if fin["num"]:
+            _off_path(self, lambda: N.call("of_lora_finish_all", fin["table"].data_ptr(), fin["num"], fin["ctas"]))
 
     def operand_targets(self, unet):
         """{id(param): (device pointer of its bf16 operand copy, element pitch check)} for every weight of the grouped pack plan — what
@@ -694,8 +830,18 @@ class ParamStore:
         Cout, Cin = W.shape[0], W.shape[1]
         k = W.shape[2] if W.dim() == 3 else 1
         A, Bm, mag = ad.lora_A["default"].weight, ad.lora_B["default"].weight, ad.magnitude()
-        n2 = empty((Cout,), F32, W.device)
         E = Cin * k
+        ent = self.lora_entry(ad)
+        if ent is not None and cin_pad == Cin:
+            # grouped path: A / scaling*B operands come from the step's one grouped launch; the norm / scale / pack kernel also leaves
+            # rowscale = scaling * s and (rowscale (.) B)^T for the rank-r backward
+            V = empty((1, Cout, E), F32, W.device)
+            R.gemm_fwd(ent["B16s"].view(1, Cout, ad.r), ent["A16"].view(1, ad.r, E), N_out=E, K=ad.r, b_mn_major=True,
+                       aux_f32=W.detach().view(1, Cout, E), out_f32=V)
+            N.call("of_dora_scale_pack_prep", _p(V), _p(mag), Cout, Cin, k, ent["n2"].data_ptr(), out_rows.data_ptr(), cin_pad, tap_stride,
+                   _p(Bm), float(ad.scaling), ad.r, ent["Bst"].data_ptr(), ent["rowscale"].data_ptr())
+            return ent["n2"]
+        n2 = empty((Cout,), F32, W.device)
         if LORA_MERGE_TC and ad.r % 8 == 0 and E % 8 == 0 and cin_pad == Cin and E <= 8192 and W.is_contiguous():
             # V = W + scaling * B A on the tensor cores (K = r GEMM with the fp32 weight as residual), then norm + scale + pack per row
             r = ad.r
@@ -853,6 +999,27 @@ def _adapter_backward_rank_r(store: ParamStore, ad, dy16, x16, y16, taps, shift0
     A, Bm, mag = ad.lora_A["default"].weight, ad.lora_B["default"].weight, ad.magnitude()
     cp = (Cin + 7) // 8 * 8
     Bsz, L = x16.shape[0], x16.shape[1]
+    ent = store.lora_entry(ad)
+    if ent is not None:
+        # grouped path: operands were prepared by the forward merge, accumulators are persistent (zeroed once per backward), lora_A's
+        # gradient accumulates in place, the finishing arithmetic runs once for all layers (ParamStore.lora_finish); nothing here is
+        # on the critical path of backward, so the four GEMMs go to the second stream
+        u = empty((Bsz, L, r), BF16, dev)
+        e = empty((Bsz, L, r), BF16, dev)
+        store.touch(A)
+        gA = store.arena_packed_views[id(A)] if k > 1 else store.arena_views[id(A)].view(1, r, Cin)
+        step = 1 if k > 1 else 0
+
+        def rank_r():
+            R.gemm_fwd(x16, ent["Apk"], N_out=r, K=Cin, taps=k, shift0=shift0, shift_step=step, out_bf16=u)
+            R.gemm_wgrad(dy16, u, ent["dBraw"], M=Cout, N_out=r)
+            R.gemm_fwd(dy16, ent["Bst"].view(1, r, Cout), N_out=r, K=Cout, out_bf16=e)
+            R.gemm_wgrad(e, x16, gA, M=r, N_out=Cin, taps=taps, shift0=shift0, shift_step=step)
+            if mag is not None:
+                _coldot(dy16, y16, base.bias, ent["dm"])
+        _off_path(store, rank_r, dy16, x16, y16, u, e)
+        store.lora_plan["pending"] = True
+        return
     n2 = store.dora_n2(ad) if mag is not None else None
     # scaled B^T operand and the per-row factor scaling * s in one tiny launch
     Bst = empty((r, Cout), BF16, dev)

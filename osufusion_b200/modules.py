@@ -450,6 +450,7 @@ class UNet(nn.Module):
                 self.grad_sync(len(ctx.tape.ops) + 1)
             self.final_backward(ctx, xf, dY16)
             ctx.tape.run_backward(self.grad_sync, st.side)
+            st.lora_finish()
             if self.grad_finish is not None:
                 self.grad_finish()
         finally:

@@ -337,12 +337,13 @@ def of_pack_weights(table, num_segs, total_ctas):
     ctas = 0
     for sg in segs:
         assert sg.cta_begin == ctas
+        sc = sg.scale if sg.scale != 0.0 else 1.0
         if sg.k == 1 and sg.cin_pad == sg.Cin:
             n = sg.Cout * sg.Cin
-            _mem(sg.dst, n, BF16).copy_(_mem(sg.src, n, F32).to(BF16))
+            _mem(sg.dst, n, BF16).copy_((sc * _mem(sg.src, n, F32)).to(BF16))
             ctas += (n + 4095) // 4096
         else:
-            w = _mem(sg.src, sg.Cout * sg.Cin * sg.k, F32).view(sg.Cout, sg.Cin, sg.k)
+            w = sc * _mem(sg.src, sg.Cout * sg.Cin * sg.k, F32).view(sg.Cout, sg.Cin, sg.k)
             out = torch.zeros(sg.k, sg.Cout, sg.cin_pad)
             out[:, :, :sg.Cin] = w.permute(2, 0, 1)
             _mem(sg.dst, sg.k * sg.Cout * sg.cin_pad, BF16).copy_(out.reshape(-1).to(BF16))
@@ -680,6 +681,22 @@ def of_dora_scale_pack(V, mag, Cout, Cin, k, n2_out, packed, cin_pad, tap_stride
     sc = _mem(mag, Cout, F32) / n2.sqrt() if mag else torch.ones(Cout)
     out = _packed_view(packed, BF16, k, Cout, cin_pad, tap_stride)
     out[:, :, :Cin] = (sc[:, None] * Vm).view(Cout, Cin, k).permute(2, 0, 1).to(BF16)
+
+
+def of_dora_scale_pack_prep(V, mag, Cout, Cin, k, n2_out, packed, cin_pad, tap_stride, Bm, scaling, r, Bst, rowscale):
+    of_dora_scale_pack(V, mag, Cout, Cin, k, n2_out, packed, cin_pad, tap_stride)
+    of_dora_rankr_prep(Bm, mag, n2_out, scaling, Cout, r, Bst, rowscale)
+
+
+def of_lora_finish_all(table, num_segs, total_ctas):
+    from osufusion_b200._native import LoraFinishSeg
+    segs = (LoraFinishSeg * num_segs).from_address(int(table))
+    ctas = 0
+    for sg in segs:
+        assert sg.cta_begin == ctas
+        of_dora_rankr_finish(sg.dBraw, sg.rowscale, sg.gB, sg.dm, sg.mag, sg.gmag, sg.Cout, sg.r)
+        ctas += (sg.Cout * sg.r + 255) // 256
+    assert ctas == total_ctas, (ctas, total_ctas)
 
 
 def of_dora_merge(W, A, Bm, mag, scaling, Cout, Cin, k, r, n2_ws, packed, cin_pad, tap_stride, s_out):

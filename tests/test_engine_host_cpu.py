@@ -184,14 +184,15 @@ def _lora_build(use_dora):
     return ora, new, names, leaves
 
 
-@pytest.mark.parametrize("rank_r,merge_tc", [(True, True), (False, False)])
+@pytest.mark.parametrize("rank_r,merge_tc,grouped", [(True, True, True), (True, True, False), (False, False, False)])
 @pytest.mark.parametrize("use_dora", [True, False])
-def test_lora_dora_tape_matches_oracle(fake_abi, monkeypatch, use_dora, rank_r, merge_tc):
+def test_lora_dora_tape_matches_oracle(fake_abi, monkeypatch, use_dora, rank_r, merge_tc, grouped):
     from oracle.synth import synth_inputs
     from osufusion_b200 import engine
     from osufusion_b200.modules import UNetFunction
     monkeypatch.setattr(engine, "LORA_RANK_R", rank_r)
     monkeypatch.setattr(engine, "LORA_MERGE_TC", merge_tc)
+    monkeypatch.setattr(engine, "LORA_GROUPED", grouped)
     ora, new, names, leaves = _lora_build(use_dora)
     x, a, c, t, noise, keep = synth_inputs(2, 56, 5)
 
@@ -223,11 +224,15 @@ def test_lora_dora_tape_matches_oracle(fake_abi, monkeypatch, use_dora, rank_r, 
                 bad.append((n, which, e_new, e_ref))
     assert not bad, bad[:6]
     used = set(fake_abi.CALLS)
-    if rank_r:
+    if grouped:      # one grouped operand launch, prep folded into the merge kernel, one finishing launch, no unpack pass
+        assert {"of_dora_scale_pack_prep", "of_lora_finish_all"} <= used
+        assert not ({"of_dora_rankr_prep", "of_dora_rankr_finish", "of_dora_grad", "of_unpack_conv_wgrad", "of_scale_cast_f32_bf16"} & used)
+    elif rank_r:
         assert {"of_dora_rankr_prep", "of_dora_rankr_finish"} <= used and "of_dora_grad" not in used
     else:
         assert "of_dora_grad" in used
-    assert ("of_dora_scale_pack" in used) == merge_tc and ("of_dora_merge" in used) == (not merge_tc)
+    if not grouped:
+        assert ("of_dora_scale_pack" in used) == merge_tc and ("of_dora_merge" in used) == (not merge_tc)
 
 
 @pytest.mark.parametrize("max_norm", [1.0, None])
