@@ -30,6 +30,9 @@ LORA_MERGE_TC = os.environ.get("OF_LORA_MERGE_TC", "1") != "0"
 # finishing launch at the end of backward, lora_A conv gradients accumulated in the GEMM layout (no per-layer cast / pack / prep /
 # unpack / finish launches)
 LORA_GROUPED = os.environ.get("OF_LORA_GROUPED", "1") != "0"
+# training forward with adapters: every layer's effective-weight merge is issued at the start of the step on the second stream, in the
+# order the forward pass will need them (learned from the previous forward); the main stream waits per layer
+LORA_MERGE_AHEAD = os.environ.get("OF_LORA_MERGE_AHEAD", "1") != "0"
 # conv-weight gradients / moments in the GEMM layout [k][Cout][Cin] (no unpack pass, no per-layer scratch fill)
 PACKED_ARENA = os.environ.get("OF_PACKED_ARENA", "1") != "0"
 # weight / bias gradients of backward on a second stream (parallel branches of the captured graph), off the dgrad critical path
@@ -378,6 +381,10 @@ class ParamStore:
         self.param_epoch = 0         # bumped by optimizers that update parameters through raw pointers (osufusion_b200/optim.py)
         self.pack_plan = None
         self.lora_plan = None
+        self._merge_log = None        # merges of the forward pass being recorded, in first-use order: [(key, thunk)]
+        self._merge_order = None      # ... of the previous forward pass (what merge-ahead replays)
+        self._merge_events = {}
+        self._merge_stream = None
         self._film_heads = None
         self._n_adapters = None
         self.film_plans = {}
@@ -464,6 +471,50 @@ class ParamStore:
         self.epoch += 1
         if unet is not None:
             self.refresh_operands(unet)
+            self._merge_ahead()
+
+    def _merge_ahead(self) -> None:
+        """LoRA / DoRA training forward: issue every effective-weight merge now, on the second stream, in first-use order."""
+        order, self._merge_order = self._merge_order, None
+        self._merge_events = {}
+        self._merge_log = [] if (self.lora_plan is not None and self.refresh) else None
+        if self._merge_log is None or not order or not LORA_MERGE_AHEAD or self.lora_plan["buf16"].device.type != "cuda":
+            return
+        if order[0] != self.lora_plan["ptrs"]:
+            return
+        if self._merge_stream is None:
+            self._merge_stream = torch.cuda.Stream(device=self.lora_plan["buf16"].device)
+        side, main = self._merge_stream, torch.cuda.current_stream()
+        side.wait_stream(main)
+        pool = _POOL
+        use_pool(None)           # scratch chunks are zero-filled on the stream that creates them: none may be born on the side stream
+        try:
+            with torch.cuda.stream(side):
+                for key, thunk in order[1]:
+                    thunk()
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    self._merge_events[key] = ev
+        finally:
+            use_pool(pool)
+
+    def _merged(self, key, thunk, val):
+        """Bookkeeping of one adapted operand at its first use in a forward pass: log it for the next step's merge-ahead and make
+        the main stream wait for the side-stream merge that produced it."""
+        if self._merge_log is not None and all(k != key for k, _ in self._merge_log):
+            self._merge_log.append((key, thunk))
+        ev = self._merge_events.pop(key, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        return val
+
+    def end_forward(self) -> None:
+        if self._merge_log is not None and self.lora_plan is not None:
+            self._merge_order = (self.lora_plan["ptrs"], self._merge_log)
+        self._merge_log = None
+        for ev in self._merge_events.values():       # merged but unused this pass (should not happen): still join the side stream
+            torch.cuda.current_stream().wait_event(ev)
+        self._merge_events = {}
 
     # ---- grouped operand packing: every plain Conv1d / Linear weight of the denoiser in one launch
     def _build_pack_plan(self, unet):
@@ -872,7 +923,8 @@ class ParamStore:
             out = zeros((k, Cout, cp), BF16, W.device) if cp != Cin else empty((k, Cout, cp), BF16, W.device)
             n2 = self._dora_merge_into(ad, out, cp, Cout * cp)
             return out, n2
-        return self._cached(("dconv", id(W)), ps, build)[0]
+        key = ("dconv", id(W))
+        return self._merged(key, lambda: self.conv_w_mod(conv), self._cached(key, ps, build)[0])
 
     def dora_n2(self, mod):
         W = mod.base_layer.weight
@@ -904,7 +956,8 @@ class ParamStore:
                     self.cache[("dlin", id(w))] = (None, (None, n2), self.epoch)
                 r += w.shape[0]
             return out
-        return self._cached(("linm",) + tuple(id(_base(m).weight) for m in mods), tuple(ps), build)
+        key = ("linm",) + tuple(id(_base(m).weight) for m in mods)
+        return self._merged(key, lambda: self.linear_w_mods(*mods), self._cached(key, tuple(ps), build))
 
     # ---- gradient buffers: zero-initialised fp32 views of the arena in the reference's parameter layout
     def touch(self, p: torch.nn.Parameter) -> bool:
@@ -1113,10 +1166,15 @@ def _bias_grad(store: ParamStore, b: Optional[torch.nn.Parameter], dy16) -> None
 
 def _off_path(store: ParamStore, fn: Callable[[], None], *keep) -> None:
     """Run a weight- / bias-gradient launch off the critical path (SideLane) when the backward pass has a second stream."""
+    if _DEBUG_SKIP_OFFPATH:      # measurement only (wrong gradients): how long is the critical path alone?
+        return
     if store.side is not None:
         store.side.run(fn, *keep)
     else:
         fn()
+
+
+_DEBUG_SKIP_OFFPATH = os.environ.get("OF_DEBUG_SKIP_OFFPATH", "0") == "1"
 
 
 def _dgrad_into(x: Act, dy16, wpack, *, N_out, K, taps=1, shift0=0, shift_step=0, b_ld=None, want_bf16=False,

@@ -433,6 +433,7 @@ class UNet(nn.Module):
         x16 = _pack(x, 8, Lp, X_PAD_VALUE, noise, ca, cb)
         a16 = _pack(a, self.dim_in_a, Lp, A_PAD_VALUE)
         out16, xf = self.denoise(ctx, x16, lambda: self.encode_audio(ctx, a16), t, c, keep)
+        self._store.end_forward()
         return out16, (ctx, xf)
 
     def backward_from(self, ctx: Ctx, xf: Act, dY16: torch.Tensor, params):
