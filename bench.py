@@ -384,8 +384,14 @@ def run_ours(args) -> None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             del g2
             return float(t)
-        ms_resv = time_variant(True, False)
-        ms_single = time_variant(False, True)
+        try:
+            ms_resv = time_variant(True, False)
+            ms_single = time_variant(False, True)
+        except Exception as e:  # noqa: BLE001  (the breakdown is extra information: never lose the bench line over it)
+            ms_resv = ms_single = float("nan")
+            sync.dry_run = False
+            sync.world = world
+            print(f"comm breakdown failed: {type(e).__name__}: {str(e)[:300]}", file=sys.stderr, flush=True)
         comm = {"step_ms": ms, "no_collective_same_schedule_and_reservation_ms": ms_resv, "no_collective_no_reservation_ms": ms_single,
                 "exposed_comm_ms": ms - ms_resv, "sm_reservation_ms": ms_resv - ms_single, "total_comm_cost_ms": ms - ms_single,
                 "buckets": len(sync.buckets), "bucket_mb": [round((e - s_) * 4 / 2 ** 20, 1) for s_, e, _ in sync.buckets],

@@ -63,6 +63,7 @@ class GradAllReducer:
         self._touch_log = {}
         self._op = None
         self._launched = set()
+        self._comm_used = False
 
     # ---- replica consistency
     def broadcast_parameters(self, model: torch.nn.Module, src: int = 0) -> None:
@@ -160,6 +161,7 @@ class GradAllReducer:
         side = self.store.side
         if side is not None and side.active:     # weight gradients of the bucket may still be running on the engine's second stream
             self.comm.wait_stream(side.stream)
+        self._comm_used = True
         with torch.cuda.stream(self.comm):
             self._reduce(self.arena[s:e])
 
@@ -169,8 +171,9 @@ class GradAllReducer:
             for bi in range(len(self.buckets)):
                 if bi not in self._launched:
                     self._launch(bi)
-            if self.comm is not None:
+            if self.comm is not None and self._comm_used:      # (a dry run launches nothing there: no edge to an uncaptured stream)
                 torch.cuda.current_stream().wait_stream(self.comm)
+        self._comm_used = False
         self._set_reserved(False)
         if self.ready_at is None and self._touch_log:
             ready = []
