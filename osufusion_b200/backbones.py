@@ -530,6 +530,7 @@ class _Backbone(nn.Module):
         self.attn_variant = 0
         self.grad_sync = None
         self.grad_finish = None
+        self.grad_prescale = 1.0
         self._mod_plans = {}     # adaLN-head descriptor tables per (with gradients?) — device tensors, not part of the state_dict
 
     # ---- reference API

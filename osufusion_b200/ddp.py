@@ -17,6 +17,7 @@ The path has exactly one exchange step: sum of gradients; every
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -34,7 +35,9 @@ class GradAllReducer:
 
     def __init__(self, model: torch.nn.Module, bucket_bytes: int = 256 << 20, group=None, overlap: bool = True,
                  reserve_sms: int = 0, tail_bucket_bytes: int = 32 << 20, tail_bytes: int = 192 << 20,
-                 broadcast_params: bool = True) -> None:
+                 broadcast_params: bool = True, registered_arena: Optional[bool] = None) -> None:
+        if registered_arena is None:
+            registered_arena = os.environ.get("OF_DDP_REGISTERED_ARENA", "1") != "0"
         unet = model.unet if hasattr(model, "unet") else model
         self.unet, self.group, self.overlap = unet, group, overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -43,6 +46,9 @@ class GradAllReducer:
         self.store = store
         if broadcast_params and self.world > 1:
             self.broadcast_parameters(model)
+        self.registered = False
+        if self.world > 1 and registered_arena and dist.get_backend(group) == "nccl":
+            self._use_registered_arena(store)
         store.ensure_arena(unet)                 # the engine owns the gradient arena; buckets are contiguous slices of it
         dev = store.arena_params[0].device
         self._build_buckets()
@@ -53,6 +59,13 @@ class GradAllReducer:
         unet.grad_sync = self._after_op
         unet.grad_finish = self.finish
         self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        # Mean by pre-division: NCCL's in-switch reduction (NVLS, what makes an 8-GPU NVSwitch all-reduce cheap) exists for SUM but not
+        # for AVG (a pre-multiplied sum): with AVG the tuner falls back to 16-channel rings that move 1.75x the bytes.  For a power-of-two
+        # world the engine scales the loss gradient by 1/world at the start of backward instead — exact in bf16 / fp32 (an exponent
+        # shift commutes with every rounding step of the linear backward pass) — and the buckets are all-reduced with SUM.
+        self.prescale = bool(self._avg and self.world > 1 and (self.world & (self.world - 1)) == 0
+                             and os.environ.get("OF_DDP_PRESCALE", "1") != "0")
+        unet.grad_prescale = 1.0 / self.world if self.prescale else 1.0
         # leave `reserve_sms` SMs to the NCCL kernels WHILE buckets are in flight: the persistent GEMM grid shrinks from the first
         # bucket launch of a backward pass to its end (of_set_sm_limit is read at launch time, i.e. baked into a captured graph);
         # forward and the part of backward before the first bucket keep every SM.
@@ -64,6 +77,36 @@ class GradAllReducer:
         self._op = None
         self._launched = set()
         self._comm_used = False
+
+    # ---- NCCL user-buffer registration
+    def _use_registered_arena(self, store) -> None:
+        """Allocate the gradient arena from NCCL's own allocator (ncclMemAlloc) and register it with the communicator: in-place
+        all-reduces of registered buffers take NCCL's zero-copy NVLS path on an NVSwitch box (the switch reduces, the SMs only
+        issue multimem loads / stores), which needs far fewer CTAs for the same bandwidth than the copy-through-FIFO path.
+        Falls back to a plain arena when the backend cannot do it."""
+        try:
+            pg = self.group if self.group is not None else dist.distributed_c10d._get_default_group()
+            dev = next(self.unet.parameters()).device
+            backend = pg._get_backend(dev)
+            pool = torch.cuda.MemPool(backend.mem_allocator)
+
+            def alloc(n, d):
+                try:
+                    with torch.cuda.use_mem_pool(pool):
+                        t = torch.zeros(n, dtype=torch.float32, device=d)
+                    backend.register_mem_pool(pool)
+                    return t
+                except Exception as e:  # noqa: BLE001
+                    self.registered = False
+                    print(f"[osufusion_b200.ddp] NCCL-registered arena failed ({type(e).__name__}: {str(e)[:200]}); plain arena", flush=True)
+                    return torch.zeros(n, dtype=torch.float32, device=d)
+            store.arena_alloc = alloc
+            store.arena_key = None           # force a rebuild of the arena from the registered pool
+            self._pool, self.registered = pool, True
+        except Exception as e:  # noqa: BLE001
+            store.arena_alloc = None
+            self.registered = False
+            print(f"[osufusion_b200.ddp] NCCL-registered gradient arena unavailable ({type(e).__name__}: {str(e)[:200]}); plain arena", flush=True)
 
     # ---- replica consistency
     def broadcast_parameters(self, model: torch.nn.Module, src: int = 0) -> None:
@@ -140,7 +183,9 @@ class GradAllReducer:
                 self._launch(bi)
 
     def _reduce(self, t: torch.Tensor) -> None:
-        if self._avg:
+        if self.prescale:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        elif self._avg:
             dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
         else:                          # gloo (CPU tests) has no AVG
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

@@ -388,6 +388,7 @@ class ParamStore:
         self._film_heads = None
         self._n_adapters = None
         self.film_plans = {}
+        self.arena_alloc = None      # optional allocator of the gradient arena (ddp: NCCL-registered memory), (numel, device) -> zeros
         self.side: Optional[SideLane] = None     # second stream of the current backward pass (weight / bias gradients), or None
         # set by ddp.GradAllReducer
         self.on_backward_begin = None
@@ -412,7 +413,7 @@ class ParamStore:
         A = self.ALIGN
         total = sum((p.numel() + A - 1) // A * A for p in params)
         dev = params[0].device
-        self.arena = torch.zeros(max(total, 1), dtype=F32, device=dev)
+        self.arena = (self.arena_alloc or (lambda n, d: torch.zeros(n, dtype=F32, device=d)))(max(total, 1), dev)
         self.arena_views, self.arena_params, self.arena_offsets = {}, params, []
         self.packed = packed_conv_params(unet) if PACKED_ARENA and custom is None else {}
         self.arena_packed_views = {}

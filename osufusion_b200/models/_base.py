@@ -45,6 +45,8 @@ class TrainStepFunction(torch.autograd.Function):
         Lp = out16.shape[1]
         bs, ld = E._bl(out16)
         g = gloss.detach().to(F32).reshape(1).contiguous()
+        if unet.grad_prescale != 1.0:
+            g = g * unet.grad_prescale
         dY16 = torch.empty((B, Lp, 8), dtype=BF16, device=x.device)
         N.call("of_mse_bwd", out16.data_ptr(), ld, bs, x.data_ptr(), noise.data_ptr(), float(ta), float(tb), E._p(ol), B, Cc, n, Lp, 8,
                accum.data_ptr(), g.data_ptr(), dY16.data_ptr())

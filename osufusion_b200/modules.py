@@ -221,6 +221,7 @@ class UNet(nn.Module):
         self.attn_variant = 0
         self.grad_sync = None    # set by osufusion_b200.ddp.GradAllReducer: called after every backward tape op
         self.grad_finish = None  # ... and once at the end of backward (launch remaining buckets, join the comm stream)
+        self.grad_prescale = 1.0 # set by ddp.GradAllReducer: loss-gradient scale 1/world when buckets are reduced with SUM
         self._side_stream = None # second stream of backward (weight / bias gradients), created on first use
 
     # ------------------------------------------------------------------ reference API
@@ -475,6 +476,8 @@ class UNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(fctx, dy):
         unet = fctx.unet
+        if unet.grad_prescale != 1.0:
+            dy = dy * unet.grad_prescale
         dY16 = _pack(dy, 8, fctx.Lp, 0.0)
         grads = unet.backward_from(fctx.ctx, fctx.xf, dY16, fctx.params)
         fctx.ctx = fctx.xf = None
