@@ -37,6 +37,9 @@ LORA_MERGE_AHEAD = os.environ.get("OF_LORA_MERGE_AHEAD", "1") != "0"
 PACKED_ARENA = os.environ.get("OF_PACKED_ARENA", "1") != "0"
 # weight / bias gradients of backward on a second stream (parallel branches of the captured graph), off the dgrad critical path
 WGRAD_SIDE = os.environ.get("OF_WGRAD_SIDE", "1") != "0"
+# the dgrad GEMM that completes an activation's gradient also emits its bf16 copy when the producer's backward needs one as a GEMM
+# operand (no separate fp32 -> bf16 cast pass at the start of TransformerBlock / sampler / CrossEmbed backward)
+GRAD16 = os.environ.get("OF_GRAD16", "1") != "0"
 # training forward: the audio encoder (independent of x and t) on the second stream, concurrent with the down path
 FWD_SIDE = os.environ.get("OF_FWD_SIDE", "1") != "0"
 
@@ -52,10 +55,22 @@ def _bl(t: torch.Tensor):
 
 class Act:
     """Channels-last activation (B, L, C): fp32 residual-stream copy and/or bf16 GEMM-operand copy, plus its fp32 grad."""
-    __slots__ = ("f32", "bf16", "grad")
+    __slots__ = ("f32", "bf16", "grad", "grad16", "want16")
 
     def __init__(self, f32: Optional[torch.Tensor] = None, bf16: Optional[torch.Tensor] = None) -> None:
         self.f32, self.bf16, self.grad = f32, bf16, None
+        # grad16: bf16 copy of the COMPLETE gradient, emitted by the dgrad GEMM that makes the last contribution (ResidualBlock's conv1)
+        # when the producer of this activation asked for it (want16): its backward then needs no fp32 -> bf16 cast pass
+        self.grad16, self.want16 = None, False
+
+    def take_grad16(self, shape, device) -> torch.Tensor:
+        """(gradient as a bf16 GEMM operand, fp32 gradient); clears both.  Uses the epilogue-emitted copy when there is one."""
+        g, g16 = self.grad, self.grad16
+        self.grad = self.grad16 = None
+        if g16 is None:
+            g16 = empty(shape, BF16, device)
+            cast_copy(g, g16)
+        return g16, g
 
     @property
     def shape(self):
@@ -63,6 +78,7 @@ class Act:
 
     def add_grad(self, g: torch.Tensor) -> None:
         """Accumulate an fp32 (B, L, C) gradient view; the first contribution is adopted without a copy."""
+        self.grad16 = None
         if self.grad is None:
             self.grad = g
         else:
@@ -1183,6 +1199,7 @@ def _dgrad_into(x: Act, dy16, wpack, *, N_out, K, taps=1, shift0=0, shift_step=0
     """x.grad (+)= dY * W^T.  The GEMM epilogue adds the already-accumulated gradient (aux) and writes in place."""
     B, L = dy16.shape[0], dy16.shape[1]
     prev = x.grad
+    x.grad16 = None
     out = None
     if want_f32:
         out = prev if prev is not None else empty((B, L, N_out), F32, dy16.device)
@@ -1380,7 +1397,9 @@ def residual_block(ctx: Ctx, m, x: Act) -> Act:
                 _dgrad_into(x, dout16, st.linear_w(m.res_conv.weight), N_out=Cin, K=Cout)
             else:
                 x.add_grad(dout)
-            conv3_bwd(ctx, m.block1.proj, x, x16, dy1, y16=y1)
+            g16 = conv3_bwd(ctx, m.block1.proj, x, x16, dy1, y16=y1, want_bf16=x.want16)
+            x.grad16 = g16          # conv1's dgrad is the last contribution to x's gradient (every other consumer of x comes later in
+            #                         forward order, i.e. earlier in backward)
         ctx.tape.push(backward)
     return out
 
@@ -1447,13 +1466,11 @@ def transformer_block(ctx: Ctx, m, x: Act) -> Act:
     out16 = empty((B, L, Cc), BF16, dev)
     R.gemm_fwd(s16, w2, N_out=Cc, K=Ci, bias=ff2.bias, aux_f32=x2_32, out_f32=out32, out_bf16=out16)
     out = Act(out32, out16)
+    out.want16 = GRAD16
 
     if ctx.tape is not None:
         def backward():
-            dout = out.grad
-            out.grad = None
-            dout16 = empty((B, L, Cc), BF16, dev)
-            cast_copy(dout, dout16)
+            dout16, dout = out.take_grad16((B, L, Cc), dev)
             # FeedForward
             dU = empty((B, L, Ci), BF16, dev)
             R.gemm_fwd(dout16, w2, N_out=Ci, K=Cc, b_mn_major=True, aux_bf16=u16, aux_is_dsilu=True, out_bf16=dU)
@@ -1515,13 +1532,11 @@ def downsample(ctx: Ctx, m, x: Act) -> Act:
     ylast = y[:, Lh - 1:Lh, :]
     R.gemm_fwd(xrow, w[1], N_out=Cout, K=Cin, b_ld=2 * Cin, aux_bf16=ylast, out_bf16=ylast)
     out = Act(None, y)
+    out.want16 = GRAD16
 
     if ctx.tape is not None:
         def backward():
-            dy = out.grad
-            out.grad = None
-            dy16 = empty((B, Lh, Cout), BF16, dev)
-            cast_copy(dy, dy16)
+            dy16, dy = out.take_grad16((B, Lh, Cout), dev)
             _bias_grad(st, conv.bias, dy16)
             if conv.weight.requires_grad:
                 tmp = zeros((2, Cout, 2 * Cin), F32, dev)
@@ -1530,6 +1545,7 @@ def downsample(ctx: Ctx, m, x: Act) -> Act:
                 g = torch.stack([tmp[0, :, :Cin], tmp[0, :, Cin:], tmp[1, :, :Cin]], dim=2)
                 st.set_grad(conv.weight, g)
             # dgrad over the (B, Lh, 2Cin) view, then the reflected row
+            x.grad16 = None
             if x.grad is None:
                 x.grad = empty((B, L, Cin), F32, dev)
                 prev = None
@@ -1559,13 +1575,11 @@ def upsample(ctx: Ctx, m, x: Act) -> Act:
     N.call("of_upsample2x_fwd", _p(x16), xl, xb, B, L, Cin, _p(up), Cin, 2 * L * Cin)
     y = conv3(ctx, up, conv)
     out = Act(None, y)
+    out.want16 = GRAD16
 
     if ctx.tape is not None:
         def backward():
-            dy = out.grad
-            out.grad = None
-            dy16 = empty(y.shape, BF16, dev)
-            cast_copy(dy, dy16)
+            dy16, dy = out.take_grad16(y.shape, dev)
             _bias_grad(st, conv.bias, dy16)
             upa = Act(None, up)
             conv3_bwd(ctx, conv, upa, up, dy16)
@@ -1589,13 +1603,11 @@ def parallel_sampler(ctx: Ctx, m, x: Act) -> Act:
     y = empty((B, L, Cout), BF16, dev)
     R.gemm_fwd(x16, w1, N_out=Cout, K=Cin, bias=c1.bias, aux_bf16=y3, out_bf16=y)
     out = Act(None, y)
+    out.want16 = GRAD16
 
     if ctx.tape is not None:
         def backward():
-            dy = out.grad
-            out.grad = None
-            dy16 = empty(y.shape, BF16, dev)
-            cast_copy(dy, dy16)
+            dy16, dy = out.take_grad16(y.shape, dev)
             _bias_grad(st, c3.bias, dy16)
             _bias_grad(st, c1.bias, dy16)
             _wgrad_linear(st, c1.weight, dy16, x16)
@@ -1615,15 +1627,13 @@ def cross_embed(ctx: Ctx, m, x16: torch.Tensor) -> Act:
     y = empty((B, L, Cout), BF16, dev)
     R.gemm_fwd(x16, w, N_out=Cout, K=Cp, taps=kmax, shift0=-(kmax // 2), shift_step=1, bias=bias, out_bf16=y)
     out = Act(None, y)
+    out.want16 = GRAD16
 
     if ctx.tape is not None:
         def backward():
-            dy = out.grad
-            out.grad = None
-            if dy is None:
+            if out.grad is None:
                 return
-            dy16 = empty(y.shape, BF16, dev)
-            cast_copy(dy, dy16)
+            dy16, dy = out.take_grad16(y.shape, dev)
             tmp = zeros((kmax, Cout, Cp), F32, dev)
             R.gemm_wgrad(dy16, x16, tmp, M=Cout, N_out=Cp, taps=kmax, shift0=-(kmax // 2), shift_step=1)
             db = zeros((Cout,), F32, dev)
