@@ -52,16 +52,23 @@ def peaks():
 
 
 def gemm_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step's most frequent GEMM shape, from the committed
-    `ncu --set full` capture (profiles/r01_gemm_ncu_full.json); None when the capture is absent."""
-    p = ROOT / "profiles" / "r01_gemm_ncu_full.json"
-    if not p.exists():
-        return None, None
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step's most frequent GEMM shape (the level-0 3-tap conv,
+    B4 L4096 N512 K512), from the committed `ncu --set full` capture of this round (profiles/r02_attn_gemm_ncu_full.json, written by
+    tools/ncu_rep_summary.py; round-1 file as a fallback); None when absent."""
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    d = json.loads(p.read_text())["launches"][0]
-    t = d["dram_read"] * mult.get(d["dram_read_unit"], 1.0) + d["dram_write"] * mult.get(d["dram_write_unit"], 1.0)
-    return t, (f"bytes per launch of {d['shape']} ({d['duration_us']:.1f} us under ncu); algorithmic 35.1 MB = 16.8 MB activations + "
-               "1.5 MB weights read, 16.8 MB written (the write stays in the 126 MB L2 during the capture)")
+    for name in ("r02_attn_gemm_ncu_full.json", "r01_gemm_ncu_full.json"):
+        p = ROOT / "profiles" / name
+        if not p.exists():
+            continue
+        launches = [l for l in json.loads(p.read_text())["launches"] if "gemm_kernel" in l.get("kernel", "gemm_kernel")]
+        if not launches:
+            continue
+        d = launches[0]
+        t = d["dram_read"] * mult.get(d["dram_read_unit"], 1.0) + d["dram_write"] * mult.get(d["dram_write_unit"], 1.0)
+        dur = d.get("duration_us", d.get("duration"))
+        return t, (f"bytes per launch of the level-0 3-tap conv GEMM B4 L4096 N512 K512 ({dur:.1f} us under ncu, {name}); algorithmic 35.1 MB = "
+                   "16.8 MB activations + 1.5 MB weights read, 16.8 MB written (the write stays in the 126 MB L2 during the capture)")
+    return None, None
 
 
 class ClockSampler:
@@ -312,10 +319,16 @@ def run_ours(args) -> None:
     roof = None
     del loss
     model.zero_grad(set_to_none=True)
+    # ... on ONE stream: with the second-stream branches on, launches of the two streams share the SMs and each one's event-to-event
+    # time would include its neighbour's work
+    from osufusion_b200 import engine as EN
+    saved_flags = (EN.WGRAD_SIDE, EN.FWD_SIDE, EN.LORA_MERGE_AHEAD)
+    EN.WGRAD_SIDE = EN.FWD_SIDE = EN.LORA_MERGE_AHEAD = False
     NN.PROFILE = []
     l2 = model(dx, da, dc)
     l2.backward()
     torch.cuda.synchronize()
+    EN.WGRAD_SIDE, EN.FWD_SIDE, EN.LORA_MERGE_AHEAD = saved_flags
     if rank == 0:
         tf_peak, hbm_peak, how = peaks()
         agg = {}

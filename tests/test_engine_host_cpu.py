@@ -345,3 +345,51 @@ def test_training_rng_draw_order_matches_reference(fake_abi, kind):
         assert after_new == after_ref          # the generator was advanced by exactly the same draws
         losses.append(l_ref)
     assert abs(losses[0] - losses[1]) > 1e-3   # the draws do matter: a different seed gives a different loss
+
+
+@pytest.mark.parametrize("grad16", [True, False])
+def test_grad_prescale_is_an_exact_power_of_two_shift(fake_abi, monkeypatch, grad16):
+    """ddp.GradAllReducer takes the mean by pre-division: `unet.grad_prescale = 1 / world` scales the loss gradient at the start of
+    backward and the buckets are all-reduced with SUM (the NVLS path has no AVG).  For a power-of-two world that is exact: every
+    gradient is bit-for-bit the unscaled one times 1 / world.  Also covers the epilogue-emitted bf16 gradient copies (OF_GRAD16):
+    both settings must give the same gradients as the cast pass they replace."""
+    from oracle.synth import synth_inputs
+    from osufusion_b200 import engine
+    from osufusion_b200.modules import UNetFunction
+    monkeypatch.setattr(engine, "GRAD16", grad16)
+    _, new = _unet_pair("default")
+    x, a, c, t, noise, keep = synth_inputs(2, 48, 11)
+
+    def grads(scale):
+        new.grad_prescale = scale
+        new.zero_grad(set_to_none=True)
+        y = UNetFunction.apply(new, x, a, t, c, keep, *list(new.parameters()))
+        torch.nn.functional.mse_loss(y, noise).backward()
+        return {k: p.grad.detach().clone() for k, p in new.named_parameters()}
+
+    g1, g8 = grads(1.0), grads(0.125)
+    new.grad_prescale = 1.0
+    assert all(torch.equal(g8[k], g1[k] * 0.125) for k in g1), [k for k in g1 if not torch.equal(g8[k], g1[k] * 0.125)][:5]
+    calls = fake_abi.CALLS
+    assert ("of_cast_copy" in calls) or grad16
+
+
+def test_epilogue_emitted_bf16_gradients_equal_the_cast_pass(fake_abi, monkeypatch):
+    """OF_GRAD16: the dgrad GEMM that completes an activation's gradient also writes its bf16 copy; the values every consumer sees
+    are those the separate fp32 -> bf16 cast pass produced (bf16 of the same fp32 sum), so all parameter gradients are identical."""
+    from oracle.synth import synth_inputs
+    from osufusion_b200 import engine
+    from osufusion_b200.modules import UNetFunction
+    _, new = _unet_pair("default")
+    x, a, c, t, noise, keep = synth_inputs(2, 64, 12)
+    out = {}
+    for flag in (True, False):
+        monkeypatch.setattr(engine, "GRAD16", flag)
+        fake_abi.CALLS.clear()
+        new.zero_grad(set_to_none=True)
+        y = UNetFunction.apply(new, x, a, t, c, keep, *list(new.parameters()))
+        torch.nn.functional.mse_loss(y, noise).backward()
+        out[flag] = ({k: p.grad.detach().clone() for k, p in new.named_parameters()}, list(fake_abi.CALLS).count("of_cast_copy"))
+    (g_on, n_on), (g_off, n_off) = out[True], out[False]
+    assert n_on < n_off, (n_on, n_off)
+    assert all(torch.equal(g_on[k], g_off[k]) for k in g_on)
