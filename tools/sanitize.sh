@@ -7,10 +7,10 @@ OUT=${1:-gpurun_out}
 mkdir -p "$OUT"
 SAN=${SANITIZER:-/usr/local/cuda/bin/compute-sanitizer}
 export OF_SANITIZE=1
-timeout 900 $SAN --tool memcheck --print-limit 20 --error-exitcode 9 \
+timeout ${SANITIZER_TIMEOUT:-900} $SAN --tool memcheck --print-limit 20 --error-exitcode 9 \
     python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/sanitize_memcheck.log" 2>&1
 echo "memcheck rc $?" >> "$OUT/sanitize_memcheck.log"
-timeout 900 $SAN --tool racecheck --racecheck-report analysis --print-limit 20 --error-exitcode 9 \
+timeout ${SANITIZER_TIMEOUT:-900} $SAN --tool racecheck --racecheck-report analysis --print-limit 20 --error-exitcode 9 \
     python -m pytest -x -q tests/test_kernels_gpu.py -k "(test_gemm_conv_forward and 2-200-96-96-3) or (test_gemm_dgrad_mn_major and 2-200-136-96-3) or (test_gemm_wgrad_splitk and 2-200-96-136-3) or (test_attention_forward and 1-128-1-1-64 and 0) or (test_attention_backward and 1-128-1-1-64)" \
     > "$OUT/sanitize_racecheck.log" 2>&1
 echo "racecheck rc $?" >> "$OUT/sanitize_racecheck.log"
