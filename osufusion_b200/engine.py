@@ -400,7 +400,9 @@ class ParamStore:
         self._merge_log = None        # merges of the forward pass being recorded, in first-use order: [(key, thunk)]
         self._merge_order = None      # ... of the previous forward pass (what merge-ahead replays)
         self._merge_events = {}
+        self._merge_seen = set()
         self._merge_stream = None
+        self._lora_ads = None         # (parameter count, [adapted layers on the grouped path]): the module tree is walked once
         self._film_heads = None
         self._n_adapters = None
         self.film_plans = {}
@@ -495,6 +497,7 @@ class ParamStore:
         order, self._merge_order = self._merge_order, None
         self._merge_events = {}
         self._merge_log = [] if (self.lora_plan is not None and self.refresh) else None
+        self._merge_seen = set()
         if self._merge_log is None or not order or not LORA_MERGE_AHEAD or self.lora_plan["buf16"].device.type != "cuda":
             return
         if order[0] != self.lora_plan["ptrs"]:
@@ -518,7 +521,8 @@ class ParamStore:
     def _merged(self, key, thunk, val):
         """Bookkeeping of one adapted operand at its first use in a forward pass: log it for the next step's merge-ahead and make
         the main stream wait for the side-stream merge that produced it."""
-        if self._merge_log is not None and all(k != key for k, _ in self._merge_log):
+        if self._merge_log is not None and key not in self._merge_seen:
+            self._merge_seen.add(key)
             self._merge_log.append((key, thunk))
         ev = self._merge_events.pop(key, None)
         if ev is not None:
@@ -652,7 +656,10 @@ class ParamStore:
         if n_adapters == 0 or not LORA_GROUPED:
             self.lora_plan = None
             return
-        ads = [m for m in unet.modules() if hasattr(m, "base_layer") and _lora_fast(m)]
+        n_params = self._n_adapters[0] if self._n_adapters else -1
+        if self._lora_ads is None or self._lora_ads[0] != n_params:
+            self._lora_ads = (n_params, [m for m in unet.modules() if hasattr(m, "base_layer") and _lora_fast(m)])
+        ads = self._lora_ads[1]
         if not ads:
             self.lora_plan = None
             return
@@ -1184,6 +1191,11 @@ def _bias_grad(store: ParamStore, b: Optional[torch.nn.Parameter], dy16) -> None
 def _off_path(store: ParamStore, fn: Callable[[], None], *keep) -> None:
     """Run a weight- / bias-gradient launch off the critical path (SideLane) when the backward pass has a second stream."""
     if _DEBUG_SKIP_OFFPATH:      # measurement only (wrong gradients): how long is the critical path alone?
+        global _debug_warned
+        if not _debug_warned:
+            import sys
+            print("[osufusion_b200] OF_DEBUG_SKIP_OFFPATH=1: weight / bias gradients are NOT computed (timing aid only)", file=sys.stderr)
+            _debug_warned = True
         return
     if store.side is not None:
         store.side.run(fn, *keep)
@@ -1192,6 +1204,7 @@ def _off_path(store: ParamStore, fn: Callable[[], None], *keep) -> None:
 
 
 _DEBUG_SKIP_OFFPATH = os.environ.get("OF_DEBUG_SKIP_OFFPATH", "0") == "1"
+_debug_warned = False
 
 
 def _dgrad_into(x: Act, dy16, wpack, *, N_out, K, taps=1, shift0=0, shift_step=0, b_ld=None, want_bf16=False,
