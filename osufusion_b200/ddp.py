@@ -11,6 +11,11 @@ trainer.py:211-220,264-269,301).  Differences that matter on an NVSwitch box:
     to its end): the engine's persistent GEMM sizes its grid for the remaining SMs (of_set_sm_limit), otherwise every GEMM
     launched while a bucket is in flight runs as two waves (measured at 2 GPUs: 67.9 -> 65.7 ms per step with 16 reserved SMs
     and NCCL_MAX_CTAS=16); the forward pass keeps every SM;
+  * the mean is taken by PRE-DIVISION for power-of-two worlds: the loss gradient is scaled by 1/world at the start of backward (exact:
+    an exponent shift) and buckets are reduced with SUM, the only form NCCL's in-switch NVLS reduction supports — with AVG the tuner
+    falls back to 16-channel rings (8 x B200: 61.3 -> 55.1 ms per step); the arena can live in NCCL-registered memory
+    (`registered_arena`, ncclMemAlloc + register_mem_pool) so the collective runs zero-copy on the user buffer;
+  * the engine's second stream (weight gradients, engine.SideLane) is a dependency of every bucket launch, like the main stream;
   * buckets taper: 256 MB while plenty of backward is left to hide them, 32 MB over the last 192 MB of the arena, and the arena
     order puts the audio encoder BEFORE the down path (engine.backward_param_plan), so the exposed tail is one small bucket.
 The path has exactly one exchange step: sum of gradients; everything else is batch-sharded.
@@ -35,7 +40,7 @@ class GradAllReducer:
 
     def __init__(self, model: torch.nn.Module, bucket_bytes: int = 256 << 20, group=None, overlap: bool = True,
                  reserve_sms: int = 0, tail_bucket_bytes: int = 32 << 20, tail_bytes: int = 192 << 20,
-                 broadcast_params: bool = True, registered_arena: Optional[bool] = None) -> None:
+                 broadcast_params: bool = True, registered_arena: Optional[bool] = None, prescale: Optional[bool] = None) -> None:
         if registered_arena is None:
             registered_arena = os.environ.get("OF_DDP_REGISTERED_ARENA", "1") != "0"
         unet = model.unet if hasattr(model, "unet") else model
@@ -63,8 +68,10 @@ class GradAllReducer:
         # for AVG (a pre-multiplied sum): with AVG the tuner falls back to 16-channel rings that move 1.75x the bytes.  For a power-of-two
         # world the engine scales the loss gradient by 1/world at the start of backward instead — exact in bf16 / fp32 (an exponent
         # shift commutes with every rounding step of the linear backward pass) — and the buckets are all-reduced with SUM.
-        self.prescale = bool(self._avg and self.world > 1 and (self.world & (self.world - 1)) == 0
-                             and os.environ.get("OF_DDP_PRESCALE", "1") != "0")
+        pow2 = self.world > 1 and (self.world & (self.world - 1)) == 0
+        if prescale is None:             # automatic: NCCL + power-of-two world; `prescale=True` forces it on any backend (CPU tests)
+            prescale = self._avg and os.environ.get("OF_DDP_PRESCALE", "1") != "0"
+        self.prescale = bool(prescale and pow2)
         unet.grad_prescale = 1.0 / self.world if self.prescale else 1.0
         # leave `reserve_sms` SMs to the NCCL kernels WHILE buckets are in flight: the persistent GEMM grid shrinks from the first
         # bucket launch of a backward pass to its end (of_set_sm_limit is read at launch time, i.e. baked into a captured graph);

@@ -69,7 +69,7 @@ def test_bucketed_allreduce_world2_gloo():
     assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == "ok" for r in res)
 
 
-def _worker_real_tape(rank, world, port, out, kind="unet"):
+def _worker_real_tape(rank, world, port, out, kind="unet", prescale=None):
     """Every rank runs the real engine forward/backward (through the emulated C-ABI) on its own batch with the bucketed all-reduce
     hooked into the tape; the result must equal the mean of the per-rank gradients computed without any reducer — in the learning
     step (all buckets reduced at the end) and in the overlapped step (buckets launched from inside backward)."""
@@ -106,8 +106,11 @@ def _worker_real_tape(rank, world, port, out, kind="unet"):
     per_rank = [grads_of(copy.deepcopy(base), 100 + r) for r in range(world)]
     expect = [sum(gs) / world for gs in zip(*per_rank)]
     net = copy.deepcopy(base)
-    red = GradAllReducer(net, bucket_bytes=1 << 18)
+    red = GradAllReducer(net, bucket_bytes=1 << 18, prescale=prescale)
     assert len(red.buckets) > 4
+    # mean by pre-division (loss gradient x 1/world, buckets reduced with SUM: the NVLS-capable form used on NCCL) or, by default on
+    # gloo, SUM followed by a division — both must give the mean of the per-rank gradients
+    assert red.prescale == bool(prescale) and net.grad_prescale == (1.0 / world if prescale else 1.0)
     for step in range(2):
         got = grads_of(net, 100 + rank)
         assert len(got) == len(expect)
@@ -124,12 +127,12 @@ def _worker_real_tape(rank, world, port, out, kind="unet"):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("kind", ["unet", "mmdit"])
-def test_real_backward_tape_allreduce_world2_gloo(kind):
+@pytest.mark.parametrize("kind,prescale", [("unet", None), ("mmdit", None), ("unet", True)])
+def test_real_backward_tape_allreduce_world2_gloo(kind, prescale):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_real_tape, args=(r, 2, port, out, kind)) for r in range(2)]
+    procs = [ctx.Process(target=_worker_real_tape, args=(r, 2, port, out, kind, prescale)) for r in range(2)]
     for p in procs:
         p.start()
     res = [out.get(timeout=300) for _ in procs]
