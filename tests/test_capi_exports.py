@@ -105,3 +105,50 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
     assert lib.of_gate_bwd(p, 8, 8, p, 8, None, 8, 8, 1, 1, 1, 8, p, 8, 8, p, 8, None) == -1 and "null" in last()
     assert lib.of_linear_small_fwd(p, 8, 17, 8, 8, p, 8, None, 0, 1, p, 8, None, None) == -1 and "out of range" in last()
     assert lib.of_row_mean_std(p, 1, 1, 1, p, None) == -1 and "of_row_mean_std" in last()
+
+
+def test_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    """The C-ABI passes arguments in structs: include/osufusion_b200.h is compiled with gcc (plain C: the header must stay C-clean) and
+    sizeof / offsetof of every field are compared with the ctypes mirrors in osufusion_b200/_native.py — a field added on one side only
+    would otherwise corrupt arguments silently."""
+    import ctypes as C
+    import re
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    from osufusion_b200 import _native as N
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    root = Path(__file__).resolve().parent.parent
+    header = (root / "include" / "osufusion_b200.h").read_text()
+    pairs = {"of_gemm_args": N.GemmArgs, "of_attn_args": N.AttnArgs, "of_rb_args": N.RbArgs, "of_film_group": N.FilmGroup,
+             "of_pack_seg": N.PackSeg, "of_lora_finish_seg": N.LoraFinishSeg, "of_opt_tensor": N.OptTensor}
+    declared = set(re.findall(r"^\} (of_\w+);", header, flags=re.M))
+    assert declared == set(pairs), declared ^ set(pairs)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "osufusion_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-I", str(root / "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]       # also fails when a ctypes field name does not exist in the C struct
+    got = {}
+    for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines():
+        s, f, v = line.split()
+        got[(s, f)] = int(v)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), (cname, got[(cname, "size")], C.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+        # same number of fields: count the declarators of the C struct body
+        head = header[:header.index("} " + cname + ";")]
+        body = head[head.rindex("typedef struct {") + len("typedef struct {"):]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        n_c = sum(len(stmt.split(",")) for stmt in body.split(";") if stmt.strip())
+        assert n_c == len(cls._fields_), (cname, n_c, len(cls._fields_))
