@@ -124,3 +124,19 @@ def test_accepts_sampler_output_tensors_and_batches():
     out = D.decode_batch(D.Metadata(**META), batch, ft, 180.0)
     assert [v for v, _ in out] == ["Insane (1/2)", "Insane (2/2)"]
     assert out[0][1] == a.replace("Version: Insane", "Version: Insane (1/2)")
+
+
+def test_parallel_slider_fits_give_the_same_text():
+    """`workers > 1` spreads the curve fits of a song over host processes; every fit runs the same arithmetic wherever it runs, so the
+    text is identical — including the failure on a degenerate slider path."""
+    for seed, rough in ((21, False), (24, True)):
+        sig = synth_signal(seed, 1500, 60, rough)
+        ft = np.arange(1500) * FRAME_MS
+        serial = run(D, sig, ft, None, True)
+        assert serial.count(",B|") >= 4
+        with contextlib.redirect_stdout(io.StringIO()):
+            assert D.decode_beatmap(D.Metadata(**META), sig, ft, None, True, True, workers=2) == serial
+    g = np.load(GOLD, allow_pickle=False)
+    sig = g["degenerate_slider_path.signal"]
+    with pytest.raises(RecursionError):
+        D.decode_beatmap(D.Metadata(**META), sig, np.arange(sig.shape[1]) * FRAME_MS, None, True, False, workers=2)
